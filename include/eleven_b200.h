@@ -1,0 +1,212 @@
+/*
+ * eleven_b200.h — C ABI of the B200-native path-tracing hot path.
+ *
+ * This is the drop-in boundary for the four C++ entry points of the reference
+ * renderer (S/ = /root/reference/src/tfg-pathtracer/):
+ *
+ *     cudaError_t renderSetup(Scene*)                          S/kernel.h:80, S/kernel.cu:566
+ *     cudaError_t renderCuda(Scene*, int sampleTarget)         S/kernel.h:78, S/kernel.cu:665
+ *     cudaError_t getBuffers(RenderData&, int*, int)           S/kernel.h:82, S/kernel.cu:688
+ *     int         getSamples()                                 S/kernel.h:84, S/kernel.cu:712
+ *
+ * Everything crossing the boundary is a plain pointer + size; no C++ types,
+ * no torch types, no std::string.  All structs are POD, 4-byte aligned,
+ * little-endian.  Every function returns ELEVEN_OK (0) or a negative error
+ * code; eleven_last_error() returns the message of the last failure on the
+ * calling thread.  Nothing is printed-and-ignored (contrast S/kernel.cu:657).
+ */
+#ifndef ELEVEN_B200_H
+#define ELEVEN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ELEVEN_ABI_VERSION 1
+
+/* ---- status codes ------------------------------------------------------- */
+enum {
+    ELEVEN_OK            =  0,
+    ELEVEN_ERR_ARG       = -1,   /* bad argument / null pointer / bad size      */
+    ELEVEN_ERR_CUDA      = -2,   /* a CUDA runtime call failed                   */
+    ELEVEN_ERR_STATE     = -3,   /* call order violated (e.g. render before upload) */
+    ELEVEN_ERR_NOMEM     = -4,
+    ELEVEN_ERR_UNSUPPORTED = -5
+};
+
+/* ---- film passes: same numbering as enum Passes, S/kernel.h:7 ----------- */
+enum { ELEVEN_PASS_BEAUTY = 0, ELEVEN_PASS_DENOISE = 1, ELEVEN_PASS_NORMAL = 2,
+       ELEVEN_PASS_TANGENT = 3, ELEVEN_PASS_BITANGENT = 4, ELEVEN_PASS_COUNT = 5 };
+
+/* ---- configuration ------------------------------------------------------ */
+enum { ELEVEN_RNG_REFERENCE = 0,   /* per-pixel XORWOW, curand_init(0, idx, 0) (S/kernel.cu:140); stream-exact, 1 GPU */
+       ELEVEN_RNG_FAST      = 1 }; /* counter-based hash keyed by (pixel, sample, dimension); multi-GPU safe       */
+enum { ELEVEN_ENV_CDF   = 0,       /* the reference's flat float CDF + its binarySearch (S/HDRI.hpp:107-162)      */
+       ELEVEN_ENV_ALIAS = 1 };     /* Walker alias table over the same texel weights                              */
+enum { ELEVEN_HIT_KEY   = 0,       /* closest = min |hit.position-origin| with shadow-terminator shift (S/BVH.hpp:170) */
+       ELEVEN_HIT_MIN_T = 1 };     /* closest = min t (classic); differs only inside the per-scene shift bound    */
+
+typedef struct ElevenConfig {
+    int32_t  device;        /* CUDA device ordinal                                                     */
+    uint32_t rng_mode;      /* ELEVEN_RNG_*                                                            */
+    uint32_t env_mode;      /* ELEVEN_ENV_*                                                            */
+    uint32_t hit_mode;      /* ELEVEN_HIT_*                                                            */
+    uint32_t max_bounces;   /* MAXBOUNCES, S/Definitions.h:9 (5)                                       */
+    uint32_t sample_offset; /* fast rng: global index of this context's first sample (multi-GPU split) */
+    uint32_t sample_stride; /* fast rng: global sample index advances by this per local sample (>=1)   */
+    uint32_t flags;         /* ELEVEN_FLAG_*                                                           */
+    uint64_t seed;          /* fast rng key; the reference mode always uses seed 0 like the reference  */
+} ElevenConfig;
+
+#define ELEVEN_FLAG_TERMINATE_DEAD_PATHS 1u  /* stop paths whose throughput is exactly 0 (only legal with RNG_FAST) */
+#define ELEVEN_FLAG_COUNTERS             2u  /* count nodes/triangles visited per ray (slower; for the roofline)    */
+
+/* ---- scene description (what renderSetup copies out of Scene, S/kernel.cu:566-661) ---- */
+
+/* Camera.hpp:6-40 */
+typedef struct ElevenCamera {
+    uint32_t xRes, yRes;
+    float    focalLength, sensorWidth, sensorHeight, aperture, focusDistance;
+    float    rotation[3];     /* degrees, applied X then Y then Z (S/kernel.cu:299-306) */
+    float    position[3];
+    uint32_t bokeh;
+} ElevenCamera;
+
+/* Tri.hpp:13-19, 152 bytes, identical field order so a std::vector<Tri> can be passed as is. */
+typedef struct ElevenTri {
+    float   vertices[3][3];
+    float   uv[3][3];        /* z unused */
+    float   normals[3][3];
+    float   tangents[3][3];
+    float   tangentsSign;
+    int32_t objectID;
+} ElevenTri;
+
+/* Material.hpp:8-37 without the std::string name. */
+typedef struct ElevenMaterial {
+    int32_t albedoTextureID, emissionTextureID, roughnessTextureID,
+            metallicTextureID, normalTextureID, opacityTextureID;
+    float   albedo[3], emission[3], opacity[3];
+    float   roughness, metallic, clearcoatGloss, clearcoat, anisotropic, eta,
+            transmission, specular, specularTint, sheenTint, subsurface, sheen;
+} ElevenMaterial;
+
+enum { ELEVEN_TEX_F32_RGB   = 0,   /* float RGB, 12 B/texel: Texture::data as the reference holds it (S/Texture.hpp:18) */
+       ELEVEN_TEX_U8_SRGB   = 1,   /* 8-bit RGB; decoded through the 256-entry fastPow(x/255, 2.2) table (S/stb_image.h:127-136,1863) */
+       ELEVEN_TEX_U8_LINEAR = 2 }; /* 8-bit RGB; decoded through the fastPow(x/255, 1.0) table (not the identity!)      */
+
+/* Texture.hpp:14-34.  Row 0 is the first row of `data` exactly as the reference indexes it
+ * (LDR textures are flipped on load, S/Texture.hpp:49; the HDRI is not). */
+typedef struct ElevenTexture {
+    const void* data;
+    uint32_t format;          /* ELEVEN_TEX_* */
+    int32_t  width, height;
+    float    xTile, yTile, xOffset, yOffset;
+    uint32_t filter;          /* 0 = NO_FILTER (nearest), 1 = BILINEAR (S/Texture.hpp:10) */
+} ElevenTexture;
+
+/* PointLight.hpp:6-20 */
+typedef struct ElevenPointLight { float position[3]; float radiance[3]; } ElevenPointLight;
+
+typedef struct ElevenSceneDesc {
+    ElevenCamera            camera;
+    uint32_t                triCount;
+    const ElevenTri*        tris;              /* Scene::tris, S/Scene.hpp:28 */
+    uint32_t                objectCount;
+    const int32_t*          objectMaterial;    /* meshObjects[i].materialID, S/MeshObject.hpp:22 */
+    uint32_t                materialCount;
+    const ElevenMaterial*   materials;
+    uint32_t                textureCount;
+    const ElevenTexture*    textures;
+    ElevenTexture           hdri;              /* must be ELEVEN_TEX_F32_RGB; HDRI::texture, S/HDRI.hpp:14 */
+    uint32_t                pointLightCount;
+    const ElevenPointLight* pointLights;
+} ElevenSceneDesc;
+
+/* ---- results ------------------------------------------------------------ */
+
+/* One closest-hit record.  The reference's Hit (S/Hit.hpp:6-13) carries neither the
+ * triangle nor t,u,v; the parity contract (BASELINE.json north_star) is on these. */
+typedef struct ElevenHit {
+    int32_t tri;      /* index into ElevenSceneDesc::tris, -1 = miss */
+    float   t, u, v;  /* Moeller-Trumbore outputs, S/Tri.hpp:40-68    */
+    float   key;      /* |hit.position - ray.origin|, the reference's ordering key (S/BVH.hpp:170) */
+} ElevenHit;
+
+typedef struct ElevenStats {
+    uint64_t pixel_samples;      /* W*H*spp rendered by this context                        */
+    uint64_t rays_extension;     /* closest-hit rays traced                                  */
+    uint64_t rays_shadow_env;    /* environment NEE shadow rays                              */
+    uint64_t rays_shadow_light;  /* point-light NEE shadow rays                              */
+    uint64_t hit_bounces;        /* the reference's "paths": sum of dev_pathcount (S/kernel.cu:445) */
+    uint64_t nodes_visited;      /* BVH8 nodes fetched   (only with ELEVEN_FLAG_COUNTERS)    */
+    uint64_t tris_tested;        /* triangles intersected (only with ELEVEN_FLAG_COUNTERS)   */
+    uint64_t kernel_launches;    /* CUDA kernels launched by eleven_render so far            */
+    double   render_ms;          /* device time inside eleven_render (CUDA events)           */
+    double   trace_ms;           /* device time of the traversal kernels only                */
+    double   bvh_build_ms;       /* host wall time of the BVH8 build                         */
+    uint32_t bvh_nodes;          /* BVH8 node count                                          */
+    uint32_t bvh_tri_slots;      /* triangle slots in leaf order                             */
+    float    key_slack;          /* per-scene bound on |key - t| used for culling in HIT_KEY */
+    uint32_t samples_done;       /* per-pixel sample count of pixel 0 (getSamples)           */
+} ElevenStats;
+
+typedef struct ElevenCtx ElevenCtx;
+
+/* ---- entry points ------------------------------------------------------- */
+
+int  eleven_abi_version(void);
+const char* eleven_last_error(void);
+
+/* Creates a context on cfg->device.  Replaces the implicit global state + cudaSetDevice(0)
+ * of renderSetup (S/kernel.cu:46-49,604). */
+int  eleven_init(const ElevenConfig* cfg, ElevenCtx** out);
+void eleven_destroy(ElevenCtx* ctx);
+
+/* renderSetup (S/kernel.cu:566-661): build the acceleration structure, copy the scene,
+ * zero the film, seed the per-pixel RNG (setupKernel, S/kernel.cu:121-150). */
+int  eleven_scene_upload(ElevenCtx* ctx, const ElevenSceneDesc* scene);
+
+/* renderCuda (S/kernel.cu:665-686): add `spp` samples to every pixel; blocking. */
+int  eleven_render(ElevenCtx* ctx, int spp);
+
+/* getBuffers (S/kernel.cu:688-710): RGBA float, index W*(H-1-y)+x, A = 1; BEAUTY is the mean of
+ * per-sample radiance clamped to [0,10] (S/kernel.cu:447-463).  n_pixels must be W*H. */
+int  eleven_get_film(ElevenCtx* ctx, int pass, float* rgba, size_t n_pixels);
+int  eleven_get_pathcount(ElevenCtx* ctx, int32_t* out, size_t n_pixels);   /* dev_pathcount */
+int  eleven_get_samples(ElevenCtx* ctx);                                    /* getSamples, S/kernel.cu:712 */
+int  eleven_get_stats(ElevenCtx* ctx, ElevenStats* out);
+
+/* Zero film + counters and re-seed, keeping the uploaded scene (the reference has no such call:
+ * it is what re-running renderSetup's setupKernel would do). */
+int  eleven_film_reset(ElevenCtx* ctx);
+
+/* Test hook for the closest-hit contract: BVH::transverse (S/BVH.hpp:120-157) on a ray batch.
+ * rays = n * {ox,oy,oz,dx,dy,dz}; directions are normalised like Ray's ctor (S/Ray.hpp:14-18).
+ * Host pointers; copies are inside the call. */
+int  eleven_trace_closest(ElevenCtx* ctx, const float* rays, size_t n, ElevenHit* hits);
+/* Same, device pointers already resident (bench: inputs in HBM). `any_hit` != 0 traces
+ * occlusion only (hits[i].tri = -1 or the first triangle found). Returns device ms in *ms. */
+int  eleven_trace_device(ElevenCtx* ctx, const float* d_rays, size_t n, ElevenHit* d_hits,
+                         int any_hit, float* ms);
+
+/* Multi-GPU plumbing: the film lives as per-pixel SUMS; these expose it so the
+ * caller (one process per GPU) can all-reduce it with NCCL and resolve on the root. */
+int  eleven_film_sums_device(ElevenCtx* ctx, int pass, void** d_ptr, size_t* n_floats);
+int  eleven_film_counts_device(ElevenCtx* ctx, void** d_ptr, size_t* n_uints);
+int  eleven_device_alloc(ElevenCtx* ctx, size_t bytes, void** d_ptr);
+int  eleven_device_free(ElevenCtx* ctx, void* d_ptr);
+int  eleven_device_upload(ElevenCtx* ctx, void* d_dst, const void* h_src, size_t bytes);
+int  eleven_device_download(ElevenCtx* ctx, void* h_dst, const void* d_src, size_t bytes);
+
+/* Fused resolve: mean, alpha, optional 8-bit pack with the reference's output curve
+ * fastPow(clamp01(x), 1/2.2)*255 (S/main.cpp:156-158).  rgba8 is a HOST buffer of W*H*4 bytes. */
+int  eleven_resolve_rgba8(ElevenCtx* ctx, int pass, uint8_t* rgba8, size_t n_pixels);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ELEVEN_B200_H */
