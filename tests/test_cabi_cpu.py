@@ -1,0 +1,85 @@
+"""CPU-side checks of the boundary: the C-ABI library loads (without a GPU) and exports every symbol that
+include/eleven_b200.h declares; struct layouts agree between the header's users; no compute calls are made."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from tfg_pathtracer_b200 import _capi, scenes as S
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "eleven_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(eleven_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    assert os.path.exists(_capi.LIB_PATH), "build the extension first: python -c 'import __graft_entry__ as g; g.build()'"
+    lib = C.CDLL(_capi.LIB_PATH)
+    syms = header_symbols()
+    assert len(syms) >= 18
+    for s in syms:
+        assert hasattr(lib, s), "missing export %s" % s
+    assert sorted(_capi.EXPORTED_SYMBOLS) == syms
+    lib.eleven_abi_version.restype = C.c_int
+    assert lib.eleven_abi_version() == 1
+
+
+def test_struct_layouts_match_header():
+    prog = r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "eleven_b200.h"
+int main(void){
+ printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(ElevenConfig), sizeof(ElevenCamera), sizeof(ElevenTri), sizeof(ElevenMaterial),
+   sizeof(ElevenTexture), sizeof(ElevenSceneDesc), sizeof(ElevenHit), sizeof(ElevenStats), sizeof(ElevenPointLight));
+ printf("%zu %zu %zu\n", offsetof(ElevenSceneDesc, hdri), offsetof(ElevenSceneDesc, pointLights), offsetof(ElevenStats, render_ms));
+ return 0; }'''
+    exe = "/tmp/_layout_%d" % os.getpid()
+    subprocess.run(["gcc", "-x", "c", "-", "-I", os.path.join(ROOT, "include"), "-o", exe], input=prog.encode(), check=True)
+    out = subprocess.check_output([exe]).decode().split()
+    os.remove(exe)
+    got = list(map(int, out))
+    exp = [C.sizeof(_capi.ElevenConfig), C.sizeof(_capi.ElevenCamera), S.TRI_DT.itemsize, S.MAT_DT.itemsize, C.sizeof(_capi.ElevenTexture),
+           C.sizeof(_capi.ElevenSceneDesc), C.sizeof(_capi.ElevenHit), C.sizeof(_capi.ElevenStats), S.LIGHT_DT.itemsize,
+           _capi.ElevenSceneDesc.hdri.offset, _capi.ElevenSceneDesc.pointLights.offset, _capi.ElevenStats.render_ms.offset]
+    assert got == exp
+    assert S.CAM_DT.itemsize == C.sizeof(_capi.ElevenCamera) and _capi.HIT_DT.itemsize == C.sizeof(_capi.ElevenHit)
+
+
+def test_init_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from tfg_pathtracer_b200 import renderer as R
+    with pytest.raises(R.ElevenError):
+        R.Renderer()
+
+
+def test_scene_generators_and_codecs(tmp_path):
+    c = S.cornell_box(32, env_size=(8, 8))
+    assert len(c.tris) == 34 and c.tris["objectID"].max() == 4
+    k = S.clock_standin(tex_res=16, xres=32, yres=18, env_size=(32, 16))
+    assert [int((k.tris["objectID"] == i).sum()) for i in range(3)] == [8265, 5184, 111832]
+    assert len(k.textures) == 12
+    # container round trip
+    p = str(tmp_path / "s.flat")
+    S.save_flat(k, p)
+    k2 = S.load_flat(p)
+    assert (k2.tris == k.tris).all() and (k2.materials == k.materials).all() and (k2.hdri.data == k.hdri.data).all()
+    assert all((a.data == b.data).all() and a.format == b.format for a, b in zip(k.textures, k2.textures))
+    # codecs: what we write is what the reference's loaders decode (RGBE: exact float round trip; BMP: bytes)
+    rg = S.rgbe_encode(k.hdri.data)
+    S.write_hdr(str(tmp_path / "e.hdr"), rg)
+    assert (S.read_hdr(str(tmp_path / "e.hdr")) == rg).all()
+    assert (S.rgbe_decode(rg) == k.hdri.data).all()
+    S.write_bmp(str(tmp_path / "t.bmp"), k.textures[1].data)
+    assert (S.read_bmp(str(tmp_path / "t.bmp")) == k.textures[1].data).all()
+    d = S.write_reference_scene_dir(c, str(tmp_path / "cornell"), env_color=(0.01, 0.01, 0.01))
+    assert sorted(os.listdir(d)) == ["HDRI", "scene.json", "scene.mtl", "scene.obj", "textures"]

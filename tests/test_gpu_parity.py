@@ -1,0 +1,196 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle on the same inputs.
+
+Bars (BASELINE.json north_star):
+  * closest hit (triangle id, t, u, v, key): BIT-EXACT against the oracle's reference traversal, up to the documented
+    classes: equal-key ties (visit order) and reference slab-test misses (where the oracle's brute force agrees with us);
+  * image (rng = reference XORWOW, env = reference CDF search): >= 99.5 % of pixels within 1e-3 + 1e-3*|ref| on linear
+    BEAUTY (outliers = paths that diverged on a libm-ulp difference), first-hit AOVs to 1e-5, path counts equal on
+    >= 99.5 % of pixels;
+  * fast mode (counter RNG + alias table + dead-path termination): unbiased w.r.t. the oracle.
+"""
+import numpy as np
+import pytest
+
+import make_golden as MG
+import oracle_lib as O
+from tfg_pathtracer_b200 import renderer as R
+from tfg_pathtracer_b200 import scenes as S
+
+pytestmark = pytest.mark.gpu
+
+ABS_TOL, REL_TOL, PIXEL_FRACTION = 1e-3, 1e-3, 0.995
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+@pytest.fixture(scope="module")
+def scenes():
+    return MG.golden_scenes()
+
+
+def classify_hits(ours, ref, brute):
+    """Returns (exact, tie, slab_miss, bad) boolean masks."""
+    same_tri = ours["tri"] == ref["tri"]
+    exact = same_tri & ((ours["tri"] < 0) | ((bits(ours["t"]) == bits(ref["t"])) & (bits(ours["u"]) == bits(ref["u"])) &
+                                             (bits(ours["v"]) == bits(ref["v"])) & (bits(ours["key"]) == bits(ref["key"]))))
+    tie = ~exact & (ours["tri"] >= 0) & (ref["tri"] >= 0) & (bits(ours["key"]) == bits(ref["key"]))
+    same_as_brute = (ours["tri"] == brute["tri"]) & ((ours["tri"] < 0) | (bits(ours["t"]) == bits(brute["t"])))
+    brute_tie = (ours["tri"] >= 0) & (brute["tri"] >= 0) & (bits(ours["key"]) == bits(brute["key"]))
+    slab_miss = ~exact & ~tie & (same_as_brute | brute_tie)
+    bad = ~(exact | tie | slab_miss)
+    return exact, tie, slab_miss, bad
+
+
+@pytest.mark.parametrize("name", ["cornell", "clock", "grid"])
+def test_closest_hit_bit_exact(scenes, name):
+    sc = scenes[name]
+    orc = O.Oracle(sc)
+    rays = np.concatenate([MG.ray_batch(sc, 4096, 4096, 2048, seed=21), MG.ray_batch(sc)])
+    ref = orc.trace(rays, mode=0)
+    brute = orc.trace(rays, mode=1)
+    r = R.Renderer(**R.PARITY).render_setup(sc)
+    ours = r.trace_closest(rays)
+    exact, tie, slab, bad = classify_hits(ours, ref, brute)
+    assert bad.sum() == 0, "unclassified mismatches at rays %s" % np.nonzero(bad)[0][:10]
+    assert exact.mean() > 0.98, (exact.mean(), tie.sum(), slab.sum())
+    assert (ours["tri"] >= 0).sum() > 1000
+    r.close(); orc.close()
+
+
+@pytest.mark.parametrize("name", ["cornell", "clock"])
+def test_min_t_mode_differs_only_inside_key_slack(scenes, name):
+    sc = scenes[name]
+    rays = MG.ray_batch(sc, 4096, 2048, 1024, seed=5)
+    a = R.Renderer(**R.PARITY).render_setup(sc)
+    cfg = dict(R.PARITY); cfg["hit_mode"] = R.HIT_MIN_T
+    b = R.Renderer(**cfg).render_setup(sc)
+    ha, hb = a.trace_closest(rays), b.trace_closest(rays)
+    assert ((ha["tri"] >= 0) == (hb["tri"] >= 0)).all()
+    d = ha["tri"] != hb["tri"]
+    slack = a.stats()["key_slack"]
+    assert (np.abs(ha["t"][d] - hb["t"][d]) <= 2 * slack + 1e-5).all()
+    a.close(); b.close()
+
+
+def render_pair(sc, spp):
+    orc = O.Oracle(sc)
+    orc.render(spp)
+    r = R.Renderer(**R.PARITY).render_setup(sc)
+    r.render_cuda(spp)
+    return orc, r
+
+
+@pytest.mark.parametrize("name,spp", [("cornell", 8), ("clock", 4), ("grid", 4)])
+def test_image_matches_oracle_with_reference_rng(scenes, name, spp):
+    sc = scenes[name]
+    orc, r = render_pair(sc, spp)
+    bufs, pc = r.get_buffers()
+    ref = orc.film(0)
+    img = bufs[R.PASS_BEAUTY]
+    ok = (np.abs(img[..., :3] - ref[..., :3]) <= ABS_TOL + REL_TOL * np.abs(ref[..., :3])).all(-1)
+    assert ok.mean() >= PIXEL_FRACTION, "only %.4f of pixels within tolerance" % ok.mean()
+    assert (img[..., 3] == 1).all()
+    for p in (R.PASS_NORMAL, R.PASS_TANGENT, R.PASS_BITANGENT):
+        okp = (np.abs(bufs[p][..., :3] - orc.film(p)[..., :3]) <= 1e-5 + 1e-5 * np.abs(orc.film(p)[..., :3])).all(-1)
+        assert okp.mean() >= PIXEL_FRACTION, (p, okp.mean())
+    smp, opc = orc.counts()
+    assert (pc.astype(np.uint32) == opc).mean() >= PIXEL_FRACTION
+    assert r.get_samples() == int(smp[0]) == spp
+    st = r.stats()
+    oc = orc.ray_counts()
+    assert abs(int(st["rays_extension"]) - int(oc[0])) <= 0.002 * int(oc[0])
+    assert st["hit_bounces"] == int(pc.sum())
+    r.close(); orc.close()
+
+
+def test_progressive_render_equals_one_shot(scenes):
+    sc = scenes["cornell"]
+    a = R.Renderer(**R.PARITY).render_setup(sc); a.render_cuda(6)
+    b = R.Renderer(**R.PARITY).render_setup(sc); b.render_cuda(2); b.render_cuda(4)
+    assert (bits(a.film()) == bits(b.film())).all()
+    b.reset(); b.render_cuda(6)
+    assert (bits(a.film()) == bits(b.film())).all()
+    a.close(); b.close()
+
+
+def test_fast_mode_is_unbiased_and_split_invariant(scenes):
+    sc = scenes["cornell"]
+    orc = O.Oracle(sc); orc.render(64)
+    ref = orc.film(0)[..., :3]
+    r = R.Renderer(**R.FAST).render_setup(sc); r.render_cuda(256)
+    img = r.film()[..., :3]
+    assert abs(img.mean() - ref.mean()) / ref.mean() < 0.02
+    # blocks of 8x8 pixels average out the noise
+    H, W = img.shape[:2]
+    blk = lambda a: a[:H // 8 * 8, :W // 8 * 8].reshape(H // 8, 8, W // 8, 8, 3).mean((1, 3))
+    rel = np.abs(blk(img) - blk(ref)) / (blk(ref) + 0.02)
+    assert np.median(rel) < 0.05
+    # sample split: 2 contexts rendering the even/odd samples sum to the same film as 1 context
+    one = R.Renderer(**R.FAST).render_setup(sc); one.render_cuda(8)
+    parts = []
+    for g in range(2):
+        cfg = dict(R.FAST); cfg.update(sample_offset=g, sample_stride=2)
+        p = R.Renderer(**cfg).render_setup(sc); p.render_cuda(4)
+        parts.append(p.film()[..., :3] * 4); p.close()
+    np.testing.assert_allclose((parts[0] + parts[1]) / 8, one.film()[..., :3], rtol=1e-5, atol=1e-6)
+    one.close(); r.close(); orc.close()
+
+
+def test_env_alias_matches_cdf_distribution(scenes):
+    sc = scenes["clock"]
+    a = R.Renderer(rng_mode=R.RNG_FAST, env_mode=R.ENV_CDF, flags=0).render_setup(sc); a.render_cuda(96)
+    b = R.Renderer(rng_mode=R.RNG_FAST, env_mode=R.ENV_ALIAS, flags=0, seed=9).render_setup(sc); b.render_cuda(96)
+    ia, ib = a.film()[..., :3], b.film()[..., :3]
+    assert abs(ia.mean() - ib.mean()) / ia.mean() < 0.03
+    a.close(); b.close()
+
+
+def test_resolve_rgba8_uses_reference_output_curve(scenes):
+    sc = scenes["cornell"]
+    r = R.Renderer(**R.PARITY).render_setup(sc); r.render_cuda(2)
+    f = r.film()
+    out = r.resolve_rgba8()
+    x = np.clip(f, 0, 1).astype(np.float64)
+    exp = np.array([O.lib().orc_fastpow(float(v), 1.0 / 2.2) * 255 for v in x.ravel()[:4096]]).astype(np.uint8)
+    assert (out.ravel()[:4096] == exp).all()
+    r.close()
+
+
+def test_error_behaviour():
+    r = R.Renderer(**R.PARITY)
+    with pytest.raises(R.ElevenError):
+        r.render_cuda(1)                       # ELEVEN_ERR_STATE: render before upload
+    sc = S.cornell_box(16, env=(0, 0, 0), env_size=(8, 8))
+    with pytest.raises(R.ElevenError):
+        r.render_setup(sc)                     # black environment: the reference hangs (F10); we refuse
+    sc = S.cornell_box(16, env_size=(8, 8))
+    r.render_setup(sc)
+    with pytest.raises(R.ElevenError):
+        r.render_cuda(-1)
+    with pytest.raises(R.ElevenError):
+        R.Renderer(rng_mode=R.RNG_REFERENCE, flags=0, device=99)
+    r.close()
+
+
+def test_empty_and_degenerate_scenes():
+    sc = S.cornell_box(16, env_size=(8, 8))
+    sc.tris = sc.tris[:0]
+    r = R.Renderer(**R.PARITY).render_setup(sc)
+    hits = r.trace_closest(MG.ray_batch(S.cornell_box(16, env_size=(8, 8)), 64, 64, 0))
+    assert (hits["tri"] == -1).all()
+    r.render_cuda(2)
+    assert np.allclose(r.film()[..., :3], 0.01, atol=1e-6)     # every path escapes into the constant environment
+    assert r.trace_closest(np.zeros((0, 6), np.float32)).shape == (0,)
+    r.close()
+    # one degenerate (zero-area) triangle + one real one
+    sc = S.cornell_box(16, env_size=(8, 8))
+    sc.tris = sc.tris[:2].copy()
+    sc.tris["vertices"][0] = sc.tris["vertices"][0][0]
+    orc = O.Oracle(sc)
+    rays = MG.ray_batch(S.cornell_box(16, env_size=(8, 8)), 256, 256, 0)
+    r = R.Renderer(**R.PARITY).render_setup(sc)
+    exact, tie, slab, bad = classify_hits(r.trace_closest(rays), orc.trace(rays, 0), orc.trace(rays, 1))
+    assert bad.sum() == 0
+    r.close(); orc.close()

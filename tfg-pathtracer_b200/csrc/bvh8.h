@@ -1,0 +1,58 @@
+/*
+ * bvh8.h — compressed wide BVH (8-wide, 80-byte nodes) and its host builder.
+ *
+ * Replaces the reference's acceleration structure: an implicit complete binary tree of fixed depth 18
+ * (524 287 x 44-byte nodes whatever the scene, 57 % empty leaves at ClockCC0 scale) built by a
+ * recursive single-threaded CPU builder (S/BVH.hpp:187-330, divideSAH :373-460; S/ = reference
+ * src/tfg-pathtracer).  Here: top-down binned-SAH binary build (16 bins, in-place partition, task-parallel),
+ * greedy surface-area collapse to 8-wide nodes, octant-ordered child slots, quantised child boxes
+ * (layout after Ylitie, Karras, Laine: "Efficient Incoherent Ray Traversal on GPUs Through Compressed Wide
+ * BVHs", HPG 2017).  Triangles are re-laid out in leaf order as 48-byte records for 128-bit loads.
+ */
+#ifndef ELEVEN_BVH8_H
+#define ELEVEN_BVH8_H
+
+#include <stdint.h>
+#include <vector>
+#include "../../include/eleven_b200.h"
+
+namespace eleven {
+
+/* 80 bytes = 5 x 16-byte loads.
+ * child box i: lo = p + 2^e * qlo[i], hi = p + 2^e * qhi[i] (per axis).
+ * meta[i]: 0 = empty; internal child: 0b001xxxxx with xxxxx = 24 + slot; leaf: top 3 bits = unary triangle
+ * count (1 -> 001, 2 -> 011, 3 -> 111), low 5 bits = first triangle's offset from triBase (0..23). */
+struct alignas(16) Node8 {
+    float   px, py, pz;
+    uint8_t ex, ey, ez, imask;
+    uint32_t childBase, triBase;
+    uint8_t meta[8];
+    uint8_t qlox[8], qloy[8];
+    uint8_t qloz[8], qhix[8];
+    uint8_t qhiy[8], qhiz[8];
+};
+static_assert(sizeof(Node8) == 80, "Node8 must be 80 bytes");
+
+/* 48 bytes = 3 x float4.  e1 = v1 - v0 and e2 = v2 - v0 are the float32 differences the reference forms per hit
+ * test (S/Tri.hpp:42-43), precomputed once: identical bits, no per-test subtraction. */
+struct alignas(16) TriSlot {
+    float v0x, v0y, v0z, e1x;
+    float e1y, e1z, e2x, e2y;
+    float e2z; int32_t tri; int32_t material; uint32_t pad;
+};
+static_assert(sizeof(TriSlot) == 48, "TriSlot must be 48 bytes");
+
+struct Bvh8 {
+    std::vector<Node8>   nodes;       /* nodes[0] is the root */
+    std::vector<TriSlot> slots;       /* triangles in leaf order */
+    float  keySlack;                  /* bound on |reference key - t| over the scene (see build) */
+    float  boundsLo[3], boundsHi[3];
+    double buildMs;
+    uint32_t maxDepth;
+};
+
+/* Builds the BVH8 over `tris`.  triMaterial[i] = material id of triangle i (object -> material resolved). */
+void buildBvh8(const ElevenTri* tris, uint32_t n, const int32_t* triMaterial, Bvh8& out, int threads);
+
+} // namespace eleven
+#endif

@@ -1,0 +1,264 @@
+/*
+ * bvh8_build.cpp — host builder for the compressed 8-wide BVH (see bvh8.h).
+ *
+ * Replaces S/BVH.hpp:187-330 + divideSAH :373-460 (recursive, single-threaded, fixed depth 18, std::vector copies
+ * of 156-byte structs at every level).  Differences by design: adaptive depth, SAH leaf termination (<= 3
+ * triangles), in-place index partition, O(bins) sweep, task-parallel subtrees, wide collapse, quantisation.
+ */
+#include "bvh8.h"
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <future>
+#include <thread>
+
+namespace eleven {
+namespace {
+
+struct Box {
+    float lo[3], hi[3];
+    void reset() { for (int a = 0; a < 3; a++) { lo[a] = INFINITY; hi[a] = -INFINITY; } }
+    void grow(const Box& b) { for (int a = 0; a < 3; a++) { lo[a] = std::min(lo[a], b.lo[a]); hi[a] = std::max(hi[a], b.hi[a]); } }
+    void grow(const float* p) { for (int a = 0; a < 3; a++) { lo[a] = std::min(lo[a], p[a]); hi[a] = std::max(hi[a], p[a]); } }
+    float area() const {
+        float x = hi[0] - lo[0], y = hi[1] - lo[1], z = hi[2] - lo[2];
+        return (x < 0 || y < 0 || z < 0) ? 0.f : 2.f * (x * y + x * z + y * z);
+    }
+};
+
+struct Node2 { Box box; int left, right, first, count; };   // leaf iff count > 0
+
+static const int   BINS = 16;
+static const int   MAX_LEAF = 3;
+static const float COST_TRI = 1.0f, COST_NODE = 1.0f;
+
+struct Builder {
+    const ElevenTri* tris; uint32_t n;
+    std::vector<Box> tbox; std::vector<float> cen;   // cen[3*i+a]
+    std::vector<int> idx;
+    std::vector<Node2> nodes; std::atomic<int> nodeCount;
+    int threads; std::atomic<int> liveTasks;
+
+    int alloc() { return nodeCount.fetch_add(1); }
+
+    void build(int ni, int first, int count, int depth) {
+        Node2& N = nodes[ni];
+        Box b, cb; b.reset(); cb.reset();
+        for (int i = first; i < first + count; i++) { b.grow(tbox[idx[i]]); cb.grow(&cen[3 * idx[i]]); }
+        N.box = b; N.left = N.right = -1; N.first = first; N.count = count;
+        if (count <= 1) return;
+
+        // binned SAH over the three axes
+        float bestCost = INFINITY; int bestAxis = -1, bestSplit = -1;
+        for (int a = 0; a < 3; a++) {
+            float lo = cb.lo[a], ext = cb.hi[a] - cb.lo[a];
+            if (!(ext > 0)) continue;
+            Box bb[BINS]; int bc[BINS];
+            for (int k = 0; k < BINS; k++) { bb[k].reset(); bc[k] = 0; }
+            float scale = BINS / ext;
+            for (int i = first; i < first + count; i++) {
+                int t = idx[i];
+                int k = std::min(BINS - 1, std::max(0, (int)((cen[3 * t + a] - lo) * scale)));
+                bc[k]++; bb[k].grow(tbox[t]);
+            }
+            float rightArea[BINS]; int rightCount[BINS];
+            Box acc; acc.reset(); int c = 0;
+            for (int k = BINS - 1; k > 0; k--) { acc.grow(bb[k]); c += bc[k]; rightArea[k] = acc.area(); rightCount[k] = c; }
+            acc.reset(); c = 0;
+            for (int k = 1; k < BINS; k++) {
+                acc.grow(bb[k - 1]); c += bc[k - 1];
+                if (c == 0 || rightCount[k] == 0) continue;
+                float cost = acc.area() * c + rightArea[k] * rightCount[k];
+                if (cost < bestCost) { bestCost = cost; bestAxis = a; bestSplit = k; }
+            }
+        }
+        float leafCost = COST_TRI * count * b.area();
+        float splitCost = COST_NODE * b.area() + COST_TRI * bestCost;
+        if (count <= MAX_LEAF && (bestAxis < 0 || leafCost <= splitCost)) return;
+
+        int mid;
+        if (bestAxis >= 0) {
+            float lo = cb.lo[bestAxis], scale = BINS / (cb.hi[bestAxis] - cb.lo[bestAxis]);
+            int a = bestAxis, s = bestSplit;
+            int* p = std::partition(&idx[first], &idx[first] + count, [&](int t) {
+                int k = std::min(BINS - 1, std::max(0, (int)((cen[3 * t + a] - lo) * scale)));
+                return k < s;
+            });
+            mid = (int)(p - &idx[0]);
+        } else {
+            mid = first + count / 2;   // all centroids coincide: split by index
+        }
+        if (mid == first || mid == first + count) mid = first + count / 2;
+
+        int l = alloc(), r = alloc();
+        N.left = l; N.right = r; N.count = 0;
+        int lc = mid - first, rc = first + count - mid;
+        bool fork = threads > 1 && std::min(lc, rc) > 8192 && liveTasks.load() < threads - 1;
+        if (fork) {
+            liveTasks.fetch_add(1);
+            auto fut = std::async(std::launch::async, [=]() { build(l, first, lc, depth + 1); liveTasks.fetch_sub(1); });
+            build(r, mid, rc, depth + 1);
+            fut.get();
+        } else {
+            build(l, first, lc, depth + 1);
+            build(r, mid, rc, depth + 1);
+        }
+    }
+};
+
+static inline bool isLeaf2(const Node2& n) { return n.count > 0; }
+
+// largest power-of-two exponent e (biased by 127, stored in a byte) with 2^e * 255 >= extent
+static uint8_t quantExp(float extent) {
+    if (!(extent > 0)) return 0;
+    int e = (int)std::ceil(std::log2((double)extent / 255.0));
+    while (std::ldexp(255.0, e) < (double)extent) e++;
+    e = std::max(-126, std::min(127, e));
+    return (uint8_t)(e + 127);
+}
+
+} // namespace
+
+void buildBvh8(const ElevenTri* tris, uint32_t n, const int32_t* triMaterial, Bvh8& out, int threads) {
+    auto t0 = std::chrono::steady_clock::now();
+    out.nodes.clear(); out.slots.clear(); out.keySlack = 0; out.maxDepth = 0;
+    for (int a = 0; a < 3; a++) { out.boundsLo[a] = 0; out.boundsHi[a] = 0; }
+    if (threads < 1) threads = 1;
+
+    Builder B; B.tris = tris; B.n = n; B.threads = threads; B.liveTasks = 0;
+    B.tbox.resize(n); B.cen.resize(3 * (size_t)n); B.idx.resize(n);
+    Box scene; scene.reset();
+    double slack = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        Box b; b.reset();
+        for (int k = 0; k < 3; k++) b.grow(tris[i].vertices[k]);
+        B.tbox[i] = b; scene.grow(b);
+        for (int a = 0; a < 3; a++) B.cen[3 * (size_t)i + a] = 0.5f * (b.lo[a] + b.hi[a]);
+        B.idx[i] = (int)i;
+        // Bound on the shadow-terminator shift |shadingPosition - geomPosition| (S/Tri.hpp:81-89): shadingPosition is
+        // a convex combination of the projections p_i = P - dot(P - v_i, n_i) n_i, and dot(P - v_i, n_i) is linear in
+        // P over the triangle, so max |p_i - P| is attained at a vertex: max_{i,j} |dot(v_j - v_i, n_i)| * |n_i|.
+        for (int vi = 0; vi < 3; vi++) {
+            const float* nn = tris[i].normals[vi];
+            double nl = std::sqrt((double)nn[0] * nn[0] + (double)nn[1] * nn[1] + (double)nn[2] * nn[2]);
+            for (int vj = 0; vj < 3; vj++) {
+                if (vj == vi) continue;
+                double d = 0;
+                for (int a = 0; a < 3; a++) d += ((double)tris[i].vertices[vj][a] - tris[i].vertices[vi][a]) * nn[a];
+                slack = std::max(slack, std::fabs(d) * nl);
+            }
+        }
+    }
+    if (n == 0) { scene.lo[0] = scene.lo[1] = scene.lo[2] = 0; scene.hi[0] = scene.hi[1] = scene.hi[2] = 0; }
+    float ext = 0, mag = 0;
+    for (int a = 0; a < 3; a++) {
+        out.boundsLo[a] = scene.lo[a]; out.boundsHi[a] = scene.hi[a];
+        ext = std::max(ext, scene.hi[a] - scene.lo[a]);
+        mag = std::max(mag, std::max(std::fabs(scene.lo[a]), std::fabs(scene.hi[a])));
+    }
+    // pad triangle boxes so that float rounding in the slab test can never cull a triangle Moeller-Trumbore accepts
+    float pad = 4e-6f * std::max(ext, mag) + 1e-30f;
+    for (uint32_t i = 0; i < n; i++) for (int a = 0; a < 3; a++) { B.tbox[i].lo[a] -= pad; B.tbox[i].hi[a] += pad; }
+    out.keySlack = (float)(slack * 1.0001 + 1e-5 * std::max(ext, mag));
+
+    // ---- binary binned-SAH build ----------------------------------------------------------------
+    B.nodes.resize(std::max<size_t>(1, 2 * (size_t)n));
+    B.nodeCount = 1;
+    if (n > 0) B.build(0, 0, (int)n, 0);
+    else { B.nodes[0].box = scene; B.nodes[0].left = B.nodes[0].right = -1; B.nodes[0].first = 0; B.nodes[0].count = 0; }
+
+    // ---- collapse to 8-wide, breadth-first so that a node's internal children are contiguous ---------
+    struct Item { int n2; uint32_t n8; uint32_t depth; };
+    std::vector<Item> queue; queue.reserve(n / 4 + 16);
+    out.nodes.reserve(n / 3 + 16); out.slots.reserve(n);
+    out.nodes.emplace_back(); memset(&out.nodes[0], 0, sizeof(Node8));
+    queue.push_back({0, 0u, 1u});
+    for (size_t qi = 0; qi < queue.size(); qi++) {
+        Item it = queue[qi];
+        out.maxDepth = std::max(out.maxDepth, it.depth);
+        const Node2& root = B.nodes[it.n2];
+        int ch[8]; int nc = 0;
+        if (isLeaf2(root) || root.left < 0) { if (root.count > 0) ch[nc++] = it.n2; }
+        else { ch[nc++] = root.left; ch[nc++] = root.right; }
+        while (nc < 8) {                                   // open the internal child with the largest area
+            int best = -1; float bestA = -1;
+            for (int i = 0; i < nc; i++) { const Node2& c = B.nodes[ch[i]]; if (!isLeaf2(c)) { float a = c.box.area(); if (a > bestA) { bestA = a; best = i; } } }
+            if (best < 0) break;
+            const Node2& c = B.nodes[ch[best]];
+            ch[best] = c.left; ch[nc++] = c.right;
+        }
+        // octant-ordered slots: slot s "lies" in direction ((s&4)?+:-, (s&2)?+:-, (s&1)?+:-) from the node centre
+        Box nb = root.box;
+        float cx[3] = {0.5f * (nb.lo[0] + nb.hi[0]), 0.5f * (nb.lo[1] + nb.hi[1]), 0.5f * (nb.lo[2] + nb.hi[2])};
+        float cost[8][8]; int slotOf[8]; bool cUsed[8] = {false}, sUsed[8] = {false};
+        for (int c = 0; c < nc; c++) {
+            const Box& cb = B.nodes[ch[c]].box;
+            float d[3] = {0.5f * (cb.lo[0] + cb.hi[0]) - cx[0], 0.5f * (cb.lo[1] + cb.hi[1]) - cx[1], 0.5f * (cb.lo[2] + cb.hi[2]) - cx[2]};
+            for (int s = 0; s < 8; s++) cost[c][s] = ((s & 4) ? d[0] : -d[0]) + ((s & 2) ? d[1] : -d[1]) + ((s & 1) ? d[2] : -d[2]);
+        }
+        for (int k = 0; k < nc; k++) {
+            int bc = -1, bs = -1; float bv = -INFINITY;
+            for (int c = 0; c < nc; c++) if (!cUsed[c]) for (int s = 0; s < 8; s++) if (!sUsed[s] && cost[c][s] > bv) { bv = cost[c][s]; bc = c; bs = s; }
+            cUsed[bc] = true; sUsed[bs] = true; slotOf[bc] = bs;
+        }
+        int childAt[8]; for (int s = 0; s < 8; s++) childAt[s] = -1;
+        for (int c = 0; c < nc; c++) childAt[slotOf[c]] = ch[c];
+
+        Node8 N; memset(&N, 0, sizeof N);
+        N.px = nb.lo[0]; N.py = nb.lo[1]; N.pz = nb.lo[2];
+        N.ex = quantExp(nb.hi[0] - nb.lo[0]); N.ey = quantExp(nb.hi[1] - nb.lo[1]); N.ez = quantExp(nb.hi[2] - nb.lo[2]);
+        N.childBase = (uint32_t)out.nodes.size(); N.triBase = (uint32_t)out.slots.size();
+        const uint8_t ebits[3] = {N.ex, N.ey, N.ez};
+        uint8_t* qlo[3] = {N.qlox, N.qloy, N.qloz}; uint8_t* qhi[3] = {N.qhix, N.qhiy, N.qhiz};
+        uint32_t triOff = 0;
+        for (int s = 0; s < 8; s++) {
+            int c2 = childAt[s];
+            if (c2 < 0) continue;
+            const Node2& c = B.nodes[c2];
+            for (int a = 0; a < 3; a++) {
+                if (ebits[a] == 0) { qlo[a][s] = 0; qhi[a][s] = 0; continue; }
+                double sc = std::ldexp(1.0, (int)ebits[a] - 127), p = (&N.px)[a];
+                int lo = (int)std::floor(((double)c.box.lo[a] - p) / sc), hi = (int)std::ceil(((double)c.box.hi[a] - p) / sc);
+                lo = std::max(0, std::min(255, lo)); hi = std::max(0, std::min(255, hi));
+                // make sure the float decode the kernel performs is conservative
+                float scf = (float)sc, pf = (&N.px)[a];
+                while (lo > 0 && pf + (float)lo * scf > c.box.lo[a]) lo--;
+                while (hi < 255 && pf + (float)hi * scf < c.box.hi[a]) hi++;
+                qlo[a][s] = (uint8_t)lo; qhi[a][s] = (uint8_t)hi;
+            }
+            if (isLeaf2(c)) {
+                uint32_t cnt = (uint32_t)c.count;               // <= 3
+                N.meta[s] = (uint8_t)((((1u << cnt) - 1u) << 5) | triOff);
+                for (uint32_t k = 0; k < cnt; k++) {
+                    int t = B.idx[c.first + k];
+                    const ElevenTri& T = tris[t];
+                    TriSlot S;
+                    S.v0x = T.vertices[0][0]; S.v0y = T.vertices[0][1]; S.v0z = T.vertices[0][2];
+                    S.e1x = T.vertices[1][0] - T.vertices[0][0]; S.e1y = T.vertices[1][1] - T.vertices[0][1]; S.e1z = T.vertices[1][2] - T.vertices[0][2];
+                    S.e2x = T.vertices[2][0] - T.vertices[0][0]; S.e2y = T.vertices[2][1] - T.vertices[0][1]; S.e2z = T.vertices[2][2] - T.vertices[0][2];
+                    S.tri = t; S.material = triMaterial ? triMaterial[t] : 0; S.pad = 0;
+                    out.slots.push_back(S);
+                }
+                triOff += cnt;
+            } else {
+                N.meta[s] = (uint8_t)((1u << 5) | (24u + (uint32_t)s));
+                N.imask |= (uint8_t)(1u << s);
+            }
+        }
+        // internal children: contiguous, ascending slot order (rank = popcount of imask below the slot)
+        for (int s = 0; s < 8; s++) {
+            int c2 = childAt[s];
+            if (c2 < 0 || isLeaf2(B.nodes[c2])) continue;
+            uint32_t id = (uint32_t)out.nodes.size();
+            out.nodes.emplace_back(); memset(&out.nodes.back(), 0, sizeof(Node8));
+            queue.push_back({c2, id, it.depth + 1});
+        }
+        out.nodes[it.n8] = N;
+    }
+    out.buildMs = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+}
+
+} // namespace eleven

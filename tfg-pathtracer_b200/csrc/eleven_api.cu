@@ -1,0 +1,527 @@
+/*
+ * eleven_api.cu — the C ABI of include/eleven_b200.h: context, scene upload, wave scheduling, film read-back.
+ *
+ * Replaces the host half of S/kernel.cu (renderSetup :566-661, renderCuda :665-686, getBuffers :688-710,
+ * getSamples :712-724; S/ = reference src/tfg-pathtracer) with a context object (no globals, no fixed
+ * 1920x1080 symbols, S/kernel.cu:41-47), checked CUDA calls and zero host synchronisations inside a render call.
+ */
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/eleven_b200.h"
+#include "bvh8.h"
+#include "kernels.cuh"
+
+using namespace eleven;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+#define CK(call)                                                                                           \
+    do {                                                                                                   \
+        cudaError_t e_ = (call);                                                                           \
+        if (e_ != cudaSuccess) {                                                                           \
+            return fail(ELEVEN_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_) + " (" + __FILE__ + ":" + std::to_string(__LINE__) + ")"); \
+        }                                                                                                  \
+    } while (0)
+
+struct ElevenCtx {
+    ElevenConfig cfg;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<void*> sceneAllocs, waveAllocs;
+    DevScene scene;
+    WaveState W;
+    RenderParams P;
+    bool haveScene = false;
+    uint32_t nPixels = 0, width = 0, height = 0;
+    uint32_t samplesRendered = 0;
+    int numSMs = 148;
+    uint32_t* d_seqMat = nullptr;
+    float4* d_resolve = nullptr;
+    uint32_t* d_workCounter = nullptr;
+    ElevenStats stats;
+};
+
+extern "C" int eleven_abi_version(void) { return ELEVEN_ABI_VERSION; }
+extern "C" const char* eleven_last_error(void) { return g_err.c_str(); }
+
+template <typename T>
+static int devAlloc(std::vector<void*>& list, T** p, size_t count) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T));
+    if (e != cudaSuccess) return fail(ELEVEN_ERR_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    list.push_back(q); *p = (T*)q; return ELEVEN_OK;
+}
+template <typename T>
+static int devUpload(std::vector<void*>& list, const T** p, const T* host, size_t count) {
+    T* q = nullptr;
+    int rc = devAlloc(list, &q, count); if (rc) return rc;
+    if (count) CK(cudaMemcpy(q, host, count * sizeof(T), cudaMemcpyHostToDevice));
+    *p = q; return ELEVEN_OK;
+}
+static void freeAll(std::vector<void*>& list) { for (void* p : list) cudaFree(p); list.clear(); }
+
+extern "C" int eleven_init(const ElevenConfig* cfg, ElevenCtx** out) {
+    if (!cfg || !out) return fail(ELEVEN_ERR_ARG, "eleven_init: null argument");
+    if (cfg->rng_mode > 1 || cfg->env_mode > 1 || cfg->hit_mode > 1) return fail(ELEVEN_ERR_ARG, "eleven_init: bad mode");
+    if ((cfg->flags & ELEVEN_FLAG_TERMINATE_DEAD_PATHS) && cfg->rng_mode == ELEVEN_RNG_REFERENCE)
+        return fail(ELEVEN_ERR_ARG, "eleven_init: dead-path termination changes the XORWOW stream; use it with ELEVEN_RNG_FAST only");
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(ELEVEN_ERR_ARG, "eleven_init: no such CUDA device");
+    CK(cudaSetDevice(cfg->device));
+    ElevenCtx* c = new ElevenCtx();
+    c->cfg = *cfg;
+    if (c->cfg.max_bounces == 0) c->cfg.max_bounces = 5;
+    if (c->cfg.sample_stride == 0) c->cfg.sample_stride = 1;
+    memset(&c->scene, 0, sizeof c->scene); memset(&c->W, 0, sizeof c->W); memset(&c->stats, 0, sizeof c->stats);
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, cfg->device));
+    c->numSMs = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&c->ev0)); CK(cudaEventCreate(&c->ev1));
+    *out = c;
+    return ELEVEN_OK;
+}
+
+extern "C" void eleven_destroy(ElevenCtx* c) {
+    if (!c) return;
+    cudaSetDevice(c->cfg.device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    freeAll(c->sceneAllocs); freeAll(c->waveAllocs);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+// ---- host-side preparation ---------------------------------------------------------------------------------------
+// stb_image's patched LDR decode (S/stb_image.h:127-136,1863): published algorithm (Ankerl's approximate pow)
+static double fastPowHost(double a, double b) {
+    union { double d; int32_t x[2]; } u; u.d = a;
+    u.x[1] = (int32_t)(b * (u.x[1] - 1072632447) + 1072632447);
+    u.x[0] = 0;
+    return u.d;
+}
+static void buildLut(float* lut512) {
+    for (int i = 0; i < 256; i++) {
+        lut512[i] = (float)(fastPowHost((float)i / 255.0f, 2.2f) * 1.0f);
+        lut512[256 + i] = (float)(fastPowHost((float)i / 255.0f, 1.0f) * 1.0f);
+    }
+}
+// XORWOW sequence-skip matrices: step^(2^67 * 2^k), k = 0..23, by repeated squaring over GF(2) (see k_rngInit)
+static void xorwowStepHost(uint32_t v[5]) {
+    uint32_t t = v[0] ^ (v[0] >> 2);
+    v[0] = v[1]; v[1] = v[2]; v[2] = v[3]; v[3] = v[4];
+    v[4] = (v[4] ^ (v[4] << 4)) ^ (t ^ (t << 1));
+}
+struct BitMat { uint32_t col[160][5]; };
+static void matVecHost(const BitMat& m, const uint32_t in[5], uint32_t out[5]) {
+    uint32_t r[5] = {0, 0, 0, 0, 0};
+    for (int w = 0; w < 5; w++) for (int b = 0; b < 32; b++) if (in[w] & (1u << b)) for (int k = 0; k < 5; k++) r[k] ^= m.col[w * 32 + b][k];
+    for (int k = 0; k < 5; k++) out[k] = r[k];
+}
+static void matMulHost(const BitMat& a, const BitMat& b, BitMat& out) { BitMat r; for (int j = 0; j < 160; j++) matVecHost(a, b.col[j], r.col[j]); out = r; }
+static void buildSeqMats(std::vector<uint32_t>& flat, int count) {
+    BitMat m;
+    for (int j = 0; j < 160; j++) { uint32_t v[5] = {0, 0, 0, 0, 0}; v[j / 32] = 1u << (j % 32); xorwowStepHost(v); for (int k = 0; k < 5; k++) m.col[j][k] = v[k]; }
+    for (int i = 0; i < 67; i++) matMulHost(m, m, m);
+    flat.resize((size_t)count * 800);
+    for (int k = 0; k < count; k++) {
+        memcpy(&flat[(size_t)k * 800], m.col, 800 * 4);
+        matMulHost(m, m, m);
+    }
+}
+
+static int uploadTexture(ElevenCtx* c, const ElevenTexture& t, DevTex& out, bool hdri) {
+    if (!t.data || t.width <= 0 || t.height <= 0) return fail(ELEVEN_ERR_ARG, "texture: null data or bad size");
+    if (t.format > ELEVEN_TEX_U8_LINEAR) return fail(ELEVEN_ERR_ARG, "texture: unknown format");
+    if (hdri && t.format != ELEVEN_TEX_F32_RGB) return fail(ELEVEN_ERR_ARG, "hdri must be ELEVEN_TEX_F32_RGB");
+    const size_t n = (size_t)t.width * t.height;
+    out.width = t.width; out.height = t.height; out.xTile = t.xTile; out.yTile = t.yTile; out.xOffset = t.xOffset; out.yOffset = t.yOffset;
+    out.format = t.format; out.filter = t.filter;
+    if (t.format == ELEVEN_TEX_F32_RGB) {
+        std::vector<float4> tmp(n);
+        const float* s = (const float*)t.data;
+        for (size_t i = 0; i < n; i++) tmp[i] = make_float4(s[3 * i], s[3 * i + 1], s[3 * i + 2], (s[3 * i] + s[3 * i + 1]) + s[3 * i + 2]);
+        const float4* d = nullptr; int rc = devUpload(c->sceneAllocs, &d, tmp.data(), n); if (rc) return rc;
+        out.data = d;
+    } else {
+        std::vector<uchar4> tmp(n);
+        const uint8_t* s = (const uint8_t*)t.data;
+        for (size_t i = 0; i < n; i++) tmp[i] = make_uchar4(s[3 * i], s[3 * i + 1], s[3 * i + 2], 255);
+        const uchar4* d = nullptr; int rc = devUpload(c->sceneAllocs, &d, tmp.data(), n); if (rc) return rc;
+        out.data = d;
+    }
+    return ELEVEN_OK;
+}
+
+static int allocWave(ElevenCtx* c) {
+    freeAll(c->waveAllocs);
+    WaveState& W = c->W; memset(&W, 0, sizeof W);
+    const size_t n = c->nPixels; W.nPixels = c->nPixels;
+    int rc = 0;
+#define A(field, type) if ((rc = devAlloc(c->waveAllocs, &W.field, n))) return rc;
+    A(rayO, float4) A(rayD, float4) A(thr, float4) A(rad, float4) A(hit, float4) A(aovN, float4) A(aovT, float4) A(aovB, float4)
+    A(depth, uint32_t) A(rng, Xorwow)
+    A(neeEnvDir, float4) A(neeEnvC, float4) A(neeLightDir, float4) A(neeLightC, float4) A(neeBrdfC, float4) A(neePos, float4) A(neeThrMul, float4)
+    A(qCur, uint32_t) A(qNext, uint32_t) A(qNee, uint32_t)
+    A(filmBeauty, float4) A(filmNormal, float4) A(filmTangent, float4) A(filmBitangent, float4) A(filmCount, uint32_t) A(pathCount, uint32_t)
+#undef A
+    if ((rc = devAlloc(c->waveAllocs, &W.cnt, CNT_COUNT))) return rc;
+    if ((rc = devAlloc(c->waveAllocs, &W.stats, ST_COUNT))) return rc;
+    if ((rc = devAlloc(c->waveAllocs, &c->d_resolve, n))) return rc;
+    if ((rc = devAlloc(c->waveAllocs, &c->d_workCounter, 4))) return rc;
+    CK(cudaMemsetAsync(W.cnt, 0, CNT_COUNT * sizeof(uint32_t), c->stream));
+    CK(cudaMemsetAsync(W.stats, 0, ST_COUNT * sizeof(unsigned long long), c->stream));
+    return ELEVEN_OK;
+}
+
+static int resetFilm(ElevenCtx* c) {
+    const uint32_t n = c->nPixels;
+    k_filmReset<<<(n + 255) / 256, 256, 0, c->stream>>>(c->W);
+    if (c->cfg.rng_mode == ELEVEN_RNG_REFERENCE)
+        k_rngInit<<<(n + 127) / 128, 128, 0, c->stream>>>(c->W.rng, c->d_seqMat, n);
+    CK(cudaMemsetAsync(c->W.stats, 0, ST_COUNT * sizeof(unsigned long long), c->stream));
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->stream));
+    c->samplesRendered = 0;
+    c->stats.render_ms = 0; c->stats.trace_ms = 0; c->stats.kernel_launches = 0; c->stats.pixel_samples = 0;
+    return ELEVEN_OK;
+}
+
+extern "C" int eleven_scene_upload(ElevenCtx* c, const ElevenSceneDesc* d) {
+    if (!c || !d) return fail(ELEVEN_ERR_ARG, "eleven_scene_upload: null argument");
+    if (d->camera.xRes == 0 || d->camera.yRes == 0) return fail(ELEVEN_ERR_ARG, "camera resolution is zero");
+    if (d->triCount && !d->tris) return fail(ELEVEN_ERR_ARG, "tris is null");
+    if (d->materialCount == 0 || !d->materials) return fail(ELEVEN_ERR_ARG, "at least one material is required");
+    if (d->objectCount == 0 || !d->objectMaterial) return fail(ELEVEN_ERR_ARG, "objectMaterial is required");
+    CK(cudaSetDevice(c->cfg.device));
+    freeAll(c->sceneAllocs);
+    c->d_seqMat = nullptr;
+    c->haveScene = false;
+    DevScene& S = c->scene; memset(&S, 0, sizeof S);
+    int rc;
+
+    // triangles -> per-triangle material, BVH8, shading records
+    std::vector<int32_t> triMat(d->triCount);
+    for (uint32_t i = 0; i < d->triCount; i++) {
+        const int32_t o = d->tris[i].objectID;
+        if (o < 0 || (uint32_t)o >= d->objectCount) return fail(ELEVEN_ERR_ARG, "triangle objectID out of range");
+        const int32_t m = d->objectMaterial[o];
+        if (m < 0 || (uint32_t)m >= d->materialCount) return fail(ELEVEN_ERR_ARG, "object material out of range");
+        triMat[i] = m;
+    }
+    Bvh8 bvh;
+    buildBvh8(d->tris, d->triCount, triMat.data(), bvh, (int)std::max(1u, std::thread::hardware_concurrency()));
+    if (bvh.maxDepth >= EL_STACK) return fail(ELEVEN_ERR_UNSUPPORTED, "BVH deeper than the traversal stack");
+    c->stats.bvh_build_ms = bvh.buildMs; c->stats.bvh_nodes = (uint32_t)bvh.nodes.size(); c->stats.bvh_tri_slots = (uint32_t)bvh.slots.size();
+    c->stats.key_slack = bvh.keySlack;
+    if ((rc = devUpload(c->sceneAllocs, &S.nodes, (const float4*)bvh.nodes.data(), bvh.nodes.size() * 5))) return rc;
+    if ((rc = devUpload(c->sceneAllocs, &S.slots, (const float4*)bvh.slots.data(), bvh.slots.size() * 3))) return rc;
+    S.nodeCount = d->triCount ? (uint32_t)bvh.nodes.size() : 0u; S.triCount = d->triCount; S.keySlack = bvh.keySlack;
+    {
+        std::vector<float> st((size_t)d->triCount * 36);
+        for (uint32_t i = 0; i < d->triCount; i++) {
+            const ElevenTri& T = d->tris[i]; float* o = &st[(size_t)i * 36];
+            memcpy(o, T.vertices, 36); memcpy(o + 9, T.normals, 36); memcpy(o + 18, T.tangents, 36);
+            o[27] = T.tangentsSign;
+            o[28] = T.uv[0][0]; o[29] = T.uv[0][1]; o[30] = T.uv[1][0]; o[31] = T.uv[1][1]; o[32] = T.uv[2][0]; o[33] = T.uv[2][1];
+            memcpy(o + 34, &T.objectID, 4); o[35] = 0.f;
+        }
+        if ((rc = devUpload(c->sceneAllocs, &S.shadeTris, (const float4*)st.data(), (size_t)d->triCount * 9))) return rc;
+    }
+    if ((rc = devUpload(c->sceneAllocs, &S.objectMaterial, d->objectMaterial, d->objectCount))) return rc;
+    static_assert(sizeof(DevMaterial) == sizeof(ElevenMaterial), "material layout");
+    for (uint32_t i = 0; i < d->materialCount; i++) {
+        const ElevenMaterial& m = d->materials[i];
+        const int32_t ids[5] = {m.albedoTextureID, m.emissionTextureID, m.roughnessTextureID, m.metallicTextureID, m.normalTextureID};
+        for (int k = 0; k < 5; k++) if (ids[k] >= (int32_t)d->textureCount) return fail(ELEVEN_ERR_ARG, "material texture id out of range");
+    }
+    if ((rc = devUpload(c->sceneAllocs, &S.materials, (const DevMaterial*)d->materials, d->materialCount))) return rc;
+    std::vector<DevTex> texs(d->textureCount);
+    for (uint32_t i = 0; i < d->textureCount; i++) if ((rc = uploadTexture(c, d->textures[i], texs[i], false))) return rc;
+    if ((rc = devUpload(c->sceneAllocs, &S.textures, texs.data(), texs.size()))) return rc;
+    float lut[512]; buildLut(lut);
+    if ((rc = devUpload(c->sceneAllocs, &S.lut, lut, 512))) return rc;
+
+    // environment: float4 texels + the reference's float CDF (S/HDRI.hpp:107-128) + alias table over its increments
+    if ((rc = uploadTexture(c, d->hdri, S.hdri, true))) return rc;
+    {
+        const int EW = d->hdri.width, EH = d->hdri.height; const size_t n = (size_t)EW * EH;
+        const float* src = (const float*)d->hdri.data;
+        auto texel = [&](int x, int y) -> size_t {          // Texture::getValueFromCoordinates addressing, S/Texture.hpp:95-108
+            x = (int)(d->hdri.xTile * (x + d->hdri.xOffset * EW)) % EW;
+            y = (int)(d->hdri.yTile * (y + d->hdri.yOffset * EH)) % EH;
+            long long idx = (long long)y * EW + x; if (idx < 0) idx = 0; if (idx >= (long long)n) idx = (long long)n - 1;
+            return (size_t)idx;
+        };
+        float sum = 0;
+        for (int j = 0; j < EH; j++) for (int i = 0; i < EW; i++) { const float* p = src + 3 * texel(i, j); sum += p[0] + p[1] + p[2]; }
+        if (!(sum > 0)) return fail(ELEVEN_ERR_ARG, "environment has zero total radiance (the reference hangs on it, SURVEY F10)");
+        std::vector<float> cdf(n + 1); cdf[0] = 0; size_t k = 0;
+        for (int j = 0; j < EH; j++) for (int i = 0; i < EW; i++) { const float* p = src + 3 * texel(i, j); cdf[k + 1] = cdf[k] + (p[0] + p[1] + p[2]) / sum; k++; }
+        S.radianceSum = sum;
+        if ((rc = devUpload(c->sceneAllocs, &S.cdf, cdf.data(), n + 1))) return rc;
+        // Walker/Vose alias table over P_i = cdf[i+1]-cdf[i]: the reference's *effective* texel distribution
+        std::vector<AliasEntry> alias(n);
+        std::vector<double> p(n); double tot = 0;
+        for (size_t i = 0; i < n; i++) { p[i] = std::max(0.0, (double)cdf[i + 1] - (double)cdf[i]); tot += p[i]; }
+        std::vector<uint32_t> small, large; small.reserve(n); large.reserve(n);
+        for (size_t i = 0; i < n; i++) { p[i] = p[i] * (double)n / tot; (p[i] < 1.0 ? small : large).push_back((uint32_t)i); }
+        while (!small.empty() && !large.empty()) {
+            const uint32_t s = small.back(), l = large.back(); small.pop_back();
+            alias[s].prob = (float)p[s]; alias[s].alias = l;
+            p[l] = (p[l] + p[s]) - 1.0;
+            if (p[l] < 1.0) { large.pop_back(); small.push_back(l); }
+        }
+        for (uint32_t i : large) { alias[i].prob = 1.0f; alias[i].alias = i; }
+        for (uint32_t i : small) { alias[i].prob = 1.0f; alias[i].alias = i; }
+        if ((rc = devUpload(c->sceneAllocs, &S.alias, alias.data(), n))) return rc;
+    }
+    S.lightCount = d->pointLightCount;
+    if ((rc = devUpload(c->sceneAllocs, &S.lights, (const float*)d->pointLights, (size_t)d->pointLightCount * 6))) return rc;
+    static_assert(sizeof(DevCamera) == sizeof(ElevenCamera), "camera layout");
+    memcpy(&S.cam, &d->camera, sizeof(DevCamera));
+
+    c->width = d->camera.xRes; c->height = d->camera.yRes;
+    const uint32_t nPix = c->width * c->height;
+    if (nPix != c->nPixels || !c->W.rayO) { c->nPixels = nPix; if ((rc = allocWave(c))) return rc; }
+    if (c->cfg.rng_mode == ELEVEN_RNG_REFERENCE && !c->d_seqMat) {
+        std::vector<uint32_t> flat; buildSeqMats(flat, 32);
+        const uint32_t* p = nullptr;
+        if ((rc = devUpload(c->sceneAllocs, &p, flat.data(), flat.size()))) return rc;
+        c->d_seqMat = (uint32_t*)p;
+    }
+    // per-render constants
+    RenderParams& P = c->P; memset(&P, 0, sizeof P);
+    P.rngMode = c->cfg.rng_mode; P.envMode = c->cfg.env_mode; P.hitMode = c->cfg.hit_mode; P.maxBounces = c->cfg.max_bounces; P.flags = c->cfg.flags;
+    P.seedLo = (uint32_t)c->cfg.seed; P.seedHi = (uint32_t)(c->cfg.seed >> 32);
+    {   // rotation *= PI/180.0 in float, then sin/cos (S/kernel.cu:299-306)
+        const float k = (float)((double)EL_PI / 180.0);
+        const float rx = d->camera.rotation[0] * k, ry = d->camera.rotation[1] * k, rz = d->camera.rotation[2] * k;
+        P.rot.sx = sinf(rx); P.rot.cx = cosf(rx); P.rot.sy = sinf(ry); P.rot.cy = cosf(ry); P.rot.sz = sinf(rz); P.rot.cz = cosf(rz);
+    }
+    c->haveScene = true;
+    return resetFilm(c);
+}
+
+extern "C" int eleven_film_reset(ElevenCtx* c) {
+    if (!c || !c->haveScene) return fail(ELEVEN_ERR_STATE, "eleven_film_reset: no scene uploaded");
+    CK(cudaSetDevice(c->cfg.device));
+    return resetFilm(c);
+}
+
+template <bool COUNT>
+static void launchExtend(ElevenCtx* c, int grid) {
+    if (c->cfg.hit_mode == ELEVEN_HIT_KEY) k_extend<TRACE_CLOSEST_KEY, COUNT><<<grid, 128, 0, c->stream>>>(c->W, c->scene);
+    else k_extend<TRACE_CLOSEST_T, COUNT><<<grid, 128, 0, c->stream>>>(c->W, c->scene);
+}
+template <bool COUNT>
+static void launchConnect(ElevenCtx* c, int grid) {
+    if (c->cfg.hit_mode == ELEVEN_HIT_KEY) k_connect<ELEVEN_HIT_KEY, COUNT><<<grid, 128, 0, c->stream>>>(c->W, c->scene, c->P);
+    else k_connect<ELEVEN_HIT_MIN_T, COUNT><<<grid, 128, 0, c->stream>>>(c->W, c->scene, c->P);
+}
+
+extern "C" int eleven_render(ElevenCtx* c, int spp) {
+    if (!c) return fail(ELEVEN_ERR_ARG, "eleven_render: null context");
+    if (!c->haveScene) return fail(ELEVEN_ERR_STATE, "eleven_render: no scene uploaded");
+    if (spp < 0) return fail(ELEVEN_ERR_ARG, "eleven_render: negative sample count");
+    CK(cudaSetDevice(c->cfg.device));
+    const uint32_t n = c->nPixels;
+    const int gridPix = (int)((n + 255) / 256);
+    const int gridPersist = c->numSMs * 8;             // 148 SMs x 8 CTAs of 128 threads: a multiple of the SM count
+    const bool count = (c->cfg.flags & ELEVEN_FLAG_COUNTERS) != 0;
+    CK(cudaEventRecord(c->ev0, c->stream));
+    for (int s = 0; s < spp; s++) {
+        c->P.sampleIndex = c->cfg.sample_offset + c->samplesRendered * c->cfg.sample_stride;
+        k_raygen<<<gridPix, 256, 0, c->stream>>>(c->W, c->scene, c->P);
+        for (uint32_t b = 0; b < c->cfg.max_bounces; b++) {
+            if (count) launchExtend<true>(c, gridPersist); else launchExtend<false>(c, gridPersist);
+            k_shade<<<gridPersist, 128, 0, c->stream>>>(c->W, c->scene, c->P);
+            k_advance<<<1, 32, 0, c->stream>>>(c->W, c->scene.lightCount, 0);
+            if (count) launchConnect<true>(c, gridPersist); else launchConnect<false>(c, gridPersist);
+            k_advance<<<1, 32, 0, c->stream>>>(c->W, c->scene.lightCount, 1);
+            c->stats.kernel_launches += 5;
+        }
+        k_accumulate<<<gridPix, 256, 0, c->stream>>>(c->W);
+        c->stats.kernel_launches += 2;
+        c->samplesRendered++;
+    }
+    CK(cudaEventRecord(c->ev1, c->stream));
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->stream));
+    float ms = 0; CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    c->stats.render_ms += ms;
+    c->stats.pixel_samples += (uint64_t)n * (uint64_t)spp;
+    return ELEVEN_OK;
+}
+
+static float4* filmPass(ElevenCtx* c, int pass) {
+    switch (pass) {
+        case ELEVEN_PASS_BEAUTY: return c->W.filmBeauty;
+        case ELEVEN_PASS_NORMAL: return c->W.filmNormal;
+        case ELEVEN_PASS_TANGENT: return c->W.filmTangent;
+        case ELEVEN_PASS_BITANGENT: return c->W.filmBitangent;
+        default: return nullptr;
+    }
+}
+
+extern "C" int eleven_get_film(ElevenCtx* c, int pass, float* rgba, size_t nPixels) {
+    if (!c || !rgba) return fail(ELEVEN_ERR_ARG, "eleven_get_film: null argument");
+    if (!c->haveScene) return fail(ELEVEN_ERR_STATE, "eleven_get_film: no scene uploaded");
+    if (nPixels != c->nPixels) return fail(ELEVEN_ERR_ARG, "eleven_get_film: n_pixels must be W*H");
+    float4* src = filmPass(c, pass);
+    if (!src) return fail(ELEVEN_ERR_UNSUPPORTED, "eleven_get_film: pass not produced on the device (DENOISE is a host-side OIDN pass in the reference)");
+    CK(cudaSetDevice(c->cfg.device));
+    k_resolve<<<(c->nPixels + 255) / 256, 256, 0, c->stream>>>(src, c->W.filmCount, c->d_resolve, c->nPixels);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(rgba, c->d_resolve, (size_t)c->nPixels * 16, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return ELEVEN_OK;
+}
+
+extern "C" int eleven_resolve_rgba8(ElevenCtx* c, int pass, uint8_t* rgba8, size_t nPixels) {
+    if (!c || !rgba8) return fail(ELEVEN_ERR_ARG, "eleven_resolve_rgba8: null argument");
+    if (!c->haveScene) return fail(ELEVEN_ERR_STATE, "eleven_resolve_rgba8: no scene uploaded");
+    if (nPixels != c->nPixels) return fail(ELEVEN_ERR_ARG, "eleven_resolve_rgba8: n_pixels must be W*H");
+    float4* src = filmPass(c, pass);
+    if (!src) return fail(ELEVEN_ERR_UNSUPPORTED, "eleven_resolve_rgba8: pass not available");
+    CK(cudaSetDevice(c->cfg.device));
+    k_resolve8<<<(c->nPixels + 255) / 256, 256, 0, c->stream>>>(src, c->W.filmCount, (uchar4*)c->d_resolve, c->nPixels);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(rgba8, c->d_resolve, (size_t)c->nPixels * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return ELEVEN_OK;
+}
+
+extern "C" int eleven_get_pathcount(ElevenCtx* c, int32_t* out, size_t nPixels) {
+    if (!c || !out) return fail(ELEVEN_ERR_ARG, "eleven_get_pathcount: null argument");
+    if (!c->haveScene) return fail(ELEVEN_ERR_STATE, "eleven_get_pathcount: no scene uploaded");
+    if (nPixels != c->nPixels) return fail(ELEVEN_ERR_ARG, "eleven_get_pathcount: n_pixels must be W*H");
+    CK(cudaSetDevice(c->cfg.device));
+    CK(cudaMemcpyAsync(out, c->W.pathCount, (size_t)c->nPixels * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return ELEVEN_OK;
+}
+
+extern "C" int eleven_get_samples(ElevenCtx* c) {
+    if (!c || !c->haveScene) return fail(ELEVEN_ERR_STATE, "eleven_get_samples: no scene uploaded");
+    uint32_t v = 0;
+    if (cudaSetDevice(c->cfg.device) != cudaSuccess) return fail(ELEVEN_ERR_CUDA, "cudaSetDevice");
+    if (cudaMemcpyAsync(&v, c->W.filmCount, 4, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) return fail(ELEVEN_ERR_CUDA, "cudaMemcpyAsync");
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) return fail(ELEVEN_ERR_CUDA, "cudaStreamSynchronize");
+    return (int)v;
+}
+
+extern "C" int eleven_get_stats(ElevenCtx* c, ElevenStats* out) {
+    if (!c || !out) return fail(ELEVEN_ERR_ARG, "eleven_get_stats: null argument");
+    if (c->haveScene) {
+        CK(cudaSetDevice(c->cfg.device));
+        unsigned long long st[ST_COUNT];
+        CK(cudaMemcpyAsync(st, c->W.stats, sizeof st, cudaMemcpyDeviceToHost, c->stream));
+        std::vector<uint32_t> pc(c->nPixels);
+        CK(cudaMemcpyAsync(pc.data(), c->W.pathCount, (size_t)c->nPixels * 4, cudaMemcpyDeviceToHost, c->stream));
+        uint32_t s0 = 0;
+        CK(cudaMemcpyAsync(&s0, c->W.filmCount, 4, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        c->stats.rays_extension = st[ST_RAYS_EXT]; c->stats.rays_shadow_env = st[ST_RAYS_ENV]; c->stats.rays_shadow_light = st[ST_RAYS_LIGHT];
+        c->stats.nodes_visited = st[ST_NODES]; c->stats.tris_tested = st[ST_TRIS];
+        uint64_t hb = 0; for (uint32_t v : pc) hb += v;
+        c->stats.hit_bounces = hb; c->stats.samples_done = s0;
+    }
+    *out = c->stats;
+    return ELEVEN_OK;
+}
+
+// ---- closest-hit test hook / bench ---------------------------------------------------------------------------------
+extern "C" int eleven_trace_device(ElevenCtx* c, const float* d_rays, size_t n, ElevenHit* d_hits, int anyHit, float* ms) {
+    if (!c || !d_rays || !d_hits) return fail(ELEVEN_ERR_ARG, "eleven_trace_device: null argument");
+    if (!c->haveScene) return fail(ELEVEN_ERR_STATE, "eleven_trace_device: no scene uploaded");
+    if (n > 0xfffffff0ull) return fail(ELEVEN_ERR_ARG, "eleven_trace_device: too many rays");
+    CK(cudaSetDevice(c->cfg.device));
+    const int grid = c->numSMs * 8;
+    const bool count = (c->cfg.flags & ELEVEN_FLAG_COUNTERS) != 0;
+    CK(cudaMemsetAsync(c->d_workCounter, 0, 4, c->stream));
+    CK(cudaEventRecord(c->ev0, c->stream));
+    const uint32_t nn = (uint32_t)n;
+    if (anyHit) {
+        if (count) k_traceBatch<TRACE_ANY, true><<<grid, 128, 0, c->stream>>>(d_rays, nn, d_hits, c->scene, c->d_workCounter, c->W.stats);
+        else k_traceBatch<TRACE_ANY, false><<<grid, 128, 0, c->stream>>>(d_rays, nn, d_hits, c->scene, c->d_workCounter, c->W.stats);
+    } else if (c->cfg.hit_mode == ELEVEN_HIT_KEY) {
+        if (count) k_traceBatch<TRACE_CLOSEST_KEY, true><<<grid, 128, 0, c->stream>>>(d_rays, nn, d_hits, c->scene, c->d_workCounter, c->W.stats);
+        else k_traceBatch<TRACE_CLOSEST_KEY, false><<<grid, 128, 0, c->stream>>>(d_rays, nn, d_hits, c->scene, c->d_workCounter, c->W.stats);
+    } else {
+        if (count) k_traceBatch<TRACE_CLOSEST_T, true><<<grid, 128, 0, c->stream>>>(d_rays, nn, d_hits, c->scene, c->d_workCounter, c->W.stats);
+        else k_traceBatch<TRACE_CLOSEST_T, false><<<grid, 128, 0, c->stream>>>(d_rays, nn, d_hits, c->scene, c->d_workCounter, c->W.stats);
+    }
+    CK(cudaEventRecord(c->ev1, c->stream));
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->stream));
+    float t = 0; CK(cudaEventElapsedTime(&t, c->ev0, c->ev1));
+    c->stats.trace_ms += t; c->stats.kernel_launches += 1;
+    if (ms) *ms = t;
+    return ELEVEN_OK;
+}
+
+extern "C" int eleven_trace_closest(ElevenCtx* c, const float* rays, size_t n, ElevenHit* hits) {
+    if (!c || (n && (!rays || !hits))) return fail(ELEVEN_ERR_ARG, "eleven_trace_closest: null argument");
+    if (!c->haveScene) return fail(ELEVEN_ERR_STATE, "eleven_trace_closest: no scene uploaded");
+    if (n == 0) return ELEVEN_OK;
+    CK(cudaSetDevice(c->cfg.device));
+    float* d_rays = nullptr; ElevenHit* d_hits = nullptr;
+    CK(cudaMalloc(&d_rays, n * 24));
+    cudaError_t e = cudaMalloc(&d_hits, n * sizeof(ElevenHit));
+    if (e != cudaSuccess) { cudaFree(d_rays); return fail(ELEVEN_ERR_NOMEM, "cudaMalloc hits"); }
+    int rc = ELEVEN_OK;
+    if (cudaMemcpyAsync(d_rays, rays, n * 24, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) rc = fail(ELEVEN_ERR_CUDA, "H2D rays");
+    if (!rc) rc = eleven_trace_device(c, d_rays, n, d_hits, 0, nullptr);
+    if (!rc && cudaMemcpyAsync(hits, d_hits, n * sizeof(ElevenHit), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) rc = fail(ELEVEN_ERR_CUDA, "D2H hits");
+    if (!rc && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = fail(ELEVEN_ERR_CUDA, "sync");
+    cudaFree(d_rays); cudaFree(d_hits);
+    return rc;
+}
+
+// ---- device plumbing for the one-process-per-GPU driver ------------------------------------------------------------------
+extern "C" int eleven_film_sums_device(ElevenCtx* c, int pass, void** p, size_t* nFloats) {
+    if (!c || !p || !nFloats) return fail(ELEVEN_ERR_ARG, "eleven_film_sums_device: null argument");
+    if (!c->haveScene) return fail(ELEVEN_ERR_STATE, "eleven_film_sums_device: no scene uploaded");
+    float4* src = filmPass(c, pass);
+    if (!src) return fail(ELEVEN_ERR_UNSUPPORTED, "eleven_film_sums_device: pass not available");
+    *p = src; *nFloats = (size_t)c->nPixels * 4; return ELEVEN_OK;
+}
+extern "C" int eleven_film_counts_device(ElevenCtx* c, void** p, size_t* n) {
+    if (!c || !p || !n) return fail(ELEVEN_ERR_ARG, "eleven_film_counts_device: null argument");
+    if (!c->haveScene) return fail(ELEVEN_ERR_STATE, "eleven_film_counts_device: no scene uploaded");
+    *p = c->W.filmCount; *n = c->nPixels; return ELEVEN_OK;
+}
+extern "C" int eleven_device_alloc(ElevenCtx* c, size_t bytes, void** p) {
+    if (!c || !p) return fail(ELEVEN_ERR_ARG, "eleven_device_alloc: null argument");
+    CK(cudaSetDevice(c->cfg.device));
+    cudaError_t e = cudaMalloc(p, std::max<size_t>(bytes, 1));
+    if (e != cudaSuccess) return fail(ELEVEN_ERR_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    return ELEVEN_OK;
+}
+extern "C" int eleven_device_free(ElevenCtx* c, void* p) {
+    if (!c) return fail(ELEVEN_ERR_ARG, "eleven_device_free: null context");
+    CK(cudaSetDevice(c->cfg.device)); CK(cudaFree(p)); return ELEVEN_OK;
+}
+extern "C" int eleven_device_upload(ElevenCtx* c, void* d, const void* h, size_t bytes) {
+    if (!c || !d || !h) return fail(ELEVEN_ERR_ARG, "eleven_device_upload: null argument");
+    CK(cudaSetDevice(c->cfg.device));
+    CK(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, c->stream)); CK(cudaStreamSynchronize(c->stream)); return ELEVEN_OK;
+}
+extern "C" int eleven_device_download(ElevenCtx* c, void* h, const void* d, size_t bytes) {
+    if (!c || !d || !h) return fail(ELEVEN_ERR_ARG, "eleven_device_download: null argument");
+    CK(cudaSetDevice(c->cfg.device));
+    CK(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, c->stream)); CK(cudaStreamSynchronize(c->stream)); return ELEVEN_OK;
+}

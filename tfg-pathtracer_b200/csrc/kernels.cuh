@@ -1,0 +1,452 @@
+/*
+ * kernels.cuh — the wavefront path-tracing pipeline (device kernels).
+ *
+ * Replaces the reference's megakernel `renderingKernel` (S/kernel.cu:369-481: one thread = one pixel-sample,
+ * 188 registers, 2.8 KB of local stack, one launch + one host sync per sample) by a queue-driven pipeline whose
+ * stages are separate persistent kernels:
+ *
+ *   raygen  -> [ extend -> shade -> connect ] x maxBounces -> accumulate
+ *
+ *   raygen      camera ray with jitter + thin lens (calculateCameraRay, S/kernel.cu:260-337)
+ *   extend      closest hit over the BVH8 (throwRay/BVH::transverse, S/kernel.cu:152, S/BVH.hpp:120)
+ *   shade       hit attributes, material + texture fetch, DisneySample/Eval/Pdf, NEE set-up (generateHitData,
+ *               calculateBounce, shade, hdriLight, pointLight: S/kernel.cu:54-119,175-258,339-367)
+ *   connect     shadow rays + the balance-heuristic MIS combination (S/kernel.cu:246-248,192-197,351-357)
+ *   accumulate  clamp, NaN rejection, film sums (S/kernel.cu:445-480)
+ *
+ * One path per pixel per wave, path id == film index, so film updates need no atomics.  Queues hold path ids;
+ * their counts live on the device and every kernel is a persistent grid that fetches 32-ray batches per warp with
+ * one atomicAdd ("warp-level work fetch"), so a whole wave is enqueued without a single host synchronisation.
+ */
+#pragma once
+#include "shading.cuh"
+
+namespace eleven {
+
+enum { CNT_CUR = 0, CNT_NEXT = 1, CNT_NEE = 2, CNT_WORK_TRACE = 3, CNT_WORK_SHADE = 4, CNT_WORK_CONNECT = 5, CNT_WORK_SORT = 6, CNT_COUNT = 16 };
+enum { ST_RAYS_EXT = 0, ST_RAYS_ENV = 1, ST_RAYS_LIGHT = 2, ST_NODES = 3, ST_TRIS = 4, ST_COUNT = 8 };
+
+struct WaveState {
+    // per path (index = film index)
+    float4* rayO; float4* rayD;          // origin / normalised direction
+    float4* thr;  float4* rad;           // throughput ("reduction"), accumulated radiance ("light")
+    float4* hit;                         // tri (as int bits), t, u, v
+    float4* aovN; float4* aovT; float4* aovB;
+    uint32_t* depth;                     // number of hit bounces so far ("i")
+    Xorwow* rng;                         // per-pixel XORWOW state, persistent across samples (reference mode)
+    // NEE records written by shade, consumed by connect
+    float4* neeEnvDir;                   // w_e.xyz, p_e
+    float4* neeEnvC;                     // C_e.xyz, p_b
+    float4* neeLightDir;                 // w_l.xyz, dist
+    float4* neeLightC;                   // C_p.xyz, p_p
+    float4* neeBrdfC;                    // C_b.xyz, -
+    float4* neePos;                      // hit position P
+    float4* neeThrMul;                   // f*cos/p_b (throughput update factor)
+    // queues
+    uint32_t* qCur; uint32_t* qNext; uint32_t* qNee;
+    uint32_t* cnt;                       // CNT_*
+    unsigned long long* stats;           // ST_*
+    // film: per-pixel sums + counts
+    float4* filmBeauty; float4* filmNormal; float4* filmTangent; float4* filmBitangent;
+    uint32_t* filmCount; uint32_t* pathCount;
+    uint32_t nPixels;
+};
+
+struct RenderParams {
+    uint32_t rngMode, envMode, hitMode, maxBounces, flags;
+    uint32_t sampleIndex;                // global index of the sample this wave renders (fast rng)
+    uint32_t seedLo, seedHi;
+    CamRot rot;
+};
+
+__device__ __forceinline__ uint32_t warpFetch(uint32_t* counter, uint32_t lane) {
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(counter, 32u);
+    return __shfl_sync(0xffffffffu, base, 0);
+}
+
+// ---- XORWOW per-pixel seeding: curand_init(0, idx, 0) (S/kernel.cu:140) --------------------------------------
+// seqMat[k] = step^(2^67 * 2^k) as 160 columns x 5 words (built on the host by repeated squaring over GF(2)).
+__global__ void k_rngInit(Xorwow* __restrict__ rng, const uint32_t* __restrict__ seqMat, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t v[5];
+    const uint32_t s0 = 0u ^ 0xaad26b49u, s1 = 0u ^ 0xf7dcefddu;          // seed 0 (curand_kernel.h:780-791)
+    const uint32_t t0 = 1099087573u * s0, t1 = 2591861531u * s1;
+    const uint32_t d = 6615241u + t1 + t0;
+    v[0] = 123456789u + t0; v[1] = 362436069u ^ t0; v[2] = 521288629u + t1; v[3] = 88675123u ^ t1; v[4] = 5783321u + t0;
+    for (uint32_t k = 0; (i >> k) != 0u; k++) {
+        if (!((i >> k) & 1u)) continue;
+        const uint32_t* M = seqMat + (size_t)k * 800;
+        uint32_t r[5] = {0u, 0u, 0u, 0u, 0u};
+        for (int w = 0; w < 5; w++) {
+            uint32_t bitsLeft = v[w];
+            while (bitsLeft) {
+                const int b = __ffs(bitsLeft) - 1; bitsLeft &= bitsLeft - 1;
+                const uint32_t* c = M + (w * 32 + b) * 5;
+                r[0] ^= __ldg(c); r[1] ^= __ldg(c + 1); r[2] ^= __ldg(c + 2); r[3] ^= __ldg(c + 3); r[4] ^= __ldg(c + 4);
+            }
+        }
+        for (int w = 0; w < 5; w++) v[w] = r[w];
+    }
+    Xorwow s; s.v0 = v[0]; s.v1 = v[1]; s.v2 = v[2]; s.v3 = v[3]; s.v4 = v[4]; s.d = d;
+    rng[i] = s;
+}
+
+__global__ void k_filmReset(WaveState W) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= W.nPixels) return;
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    W.filmBeauty[i] = z; W.filmNormal[i] = z; W.filmTangent[i] = z; W.filmBitangent[i] = z;
+    W.filmCount[i] = 0u; W.pathCount[i] = 0u;
+}
+
+// fast-mode uniforms: 4 per call, keyed by (pixel, sample, dimension block)
+__device__ __forceinline__ uint4 fastBits(const RenderParams& P, uint32_t pixel, uint32_t block) {
+    return philox4x32(make_uint4(pixel, P.sampleIndex, block, 0x11e7e0u), make_uint2(P.seedLo, P.seedHi));
+}
+
+// ---- raygen ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_raygen(WaveState W, const __grid_constant__ DevScene S, const __grid_constant__ RenderParams P) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= W.nPixels) return;
+    const uint32_t Wd = S.cam.xRes, Hd = S.cam.yRes;
+    const int x = (int)(i % Wd), y = (int)(Hd - 1u - i / Wd);        // film index = W*(H-1-y)+x (S/kernel.cu:378)
+    float r1, r2, r3, r4, r5;
+    if (P.rngMode == ELEVEN_RNG_REFERENCE) {
+        Xorwow s = W.rng[i];
+        r1 = xorwowUniform(s); r2 = xorwowUniform(s); r3 = xorwowUniform(s); r4 = xorwowUniform(s); r5 = xorwowUniform(s);
+        W.rng[i] = s;
+    } else {
+        const uint4 a = fastBits(P, i, 0u);
+        r1 = u32ToUniform(a.x); r2 = u32ToUniform(a.y); r3 = u32ToUniform(a.z); r4 = u32ToUniform(a.w);
+        r5 = S.cam.bokeh ? u32ToUniform(fastBits(P, i, 1u).x) : 0.5f;
+    }
+    const Ray ray = cameraRay(S.cam, P.rot, x, y, r1, r2, r3, r4, r5);
+    W.rayO[i] = make_float4(ray.o.x, ray.o.y, ray.o.z, 0.f);
+    W.rayD[i] = make_float4(ray.d.x, ray.d.y, ray.d.z, 0.f);
+    W.thr[i] = make_float4(1.f, 1.f, 1.f, 0.f);
+    W.rad[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    W.aovN[i] = z; W.aovT[i] = z; W.aovB[i] = z;
+    W.depth[i] = 0u;
+    W.qCur[i] = i;
+    if (i == 0) {
+        W.cnt[CNT_CUR] = W.nPixels; W.cnt[CNT_NEXT] = 0u; W.cnt[CNT_NEE] = 0u;
+        W.cnt[CNT_WORK_TRACE] = 0u; W.cnt[CNT_WORK_SHADE] = 0u; W.cnt[CNT_WORK_CONNECT] = 0u;
+    }
+}
+
+// ---- extend: closest hit for every queued path ---------------------------------------------------------------
+template <int MODE, bool COUNT>
+__global__ void __launch_bounds__(128) k_extend(WaveState W, const __grid_constant__ DevScene S) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t n = W.cnt[CNT_CUR];
+    TraceCounters tc; tc.nodes = 0; tc.tris = 0;
+    for (;;) {
+        const uint32_t base = warpFetch(&W.cnt[CNT_WORK_TRACE], lane);
+        if (base >= n) break;
+        const uint32_t qi = base + lane;
+        if (qi < n) {
+            const uint32_t pid = W.qCur[qi];
+            const float4 o = W.rayO[pid], d = W.rayD[pid];
+            Ray ray; ray.o = f3(o.x, o.y, o.z); ray.d = f3(d.x, d.y, d.z);
+            HitRec h;
+            traverse<MODE, COUNT>(S, ray, INFINITY, h, &tc);
+            W.hit[pid] = make_float4(__int_as_float(h.tri), h.t, h.u, h.v);
+        }
+    }
+    if (COUNT) { atomicAdd(&W.stats[ST_NODES], (unsigned long long)tc.nodes); atomicAdd(&W.stats[ST_TRIS], (unsigned long long)tc.tris); }
+}
+
+// ---- shade -----------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void appendWarpAggregated(uint32_t* q, uint32_t* counter, bool pred, uint32_t value) {
+    const uint32_t mask = __ballot_sync(0xffffffffu, pred);   // called by all 32 lanes of the warp
+    if (!pred) return;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t leader = __ffs(mask) - 1u;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(mask));
+    base = __shfl_sync(mask, base, leader);
+    q[base + __popc(mask & ((1u << lane) - 1u))] = value;
+}
+
+__global__ void __launch_bounds__(128) k_shade(WaveState W, const __grid_constant__ DevScene S, const __grid_constant__ RenderParams P) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t n = W.cnt[CNT_CUR];
+    for (;;) {
+        const uint32_t base = warpFetch(&W.cnt[CNT_WORK_SHADE], lane);
+        if (base >= n) break;
+        const uint32_t qi = base + lane;
+        bool toNee = false, toNext = false;
+        uint32_t pid = 0;
+        if (qi < n) {
+            pid = W.qCur[qi];
+            const float4 hv = W.hit[pid];
+            const int tri = __float_as_int(hv.x);
+            const float4 o4 = W.rayO[pid], d4 = W.rayD[pid];
+            Ray ray; ray.o = f3(o4.x, o4.y, o4.z); ray.d = f3(d4.x, d4.y, d4.z);
+            const float4 thr4 = W.thr[pid];
+            const F3 thr = f3(thr4.x, thr4.y, thr4.z);
+            if (tri < 0) {
+                // escaped: light += env(dir) * reduction (S/kernel.cu:414-419)
+                const F3 e = envLookup(S, ray.d);
+                float4 r = W.rad[pid];
+                r.x += e.x * thr.x; r.y += e.y * thr.y; r.z += e.z * thr.z;
+                W.rad[pid] = r;
+            } else {
+                const uint32_t depth = W.depth[pid];
+                // --- hit attributes: Tri::hit's second half (S/Tri.hpp:70-157), exact arithmetic -----------------
+                const float t = hv.y, u = hv.z, v = hv.w;
+                const float4* tp = S.shadeTris + (size_t)tri * 9;
+                const float4 q4 = __ldg(tp + 4), q5 = __ldg(tp + 5), q6 = __ldg(tp + 6), q7 = __ldg(tp + 7), q8 = __ldg(tp + 8);
+                const TriGeom g = loadTriGeom(S.shadeTris, tri);
+                F3 N;
+                const F3 Pp = hitPosition(ray, g, t, u, v, N);
+                const F3 t0 = f3(q4.z, q4.w, q5.x), t1 = f3(q5.y, q5.z, q5.w), t2 = f3(q6.x, q6.y, q6.z);
+                const F3 T = baryLerp(t0, t1, t2, u, v);
+                const float sign = q6.w;
+                const F3 nxt = ex::cross(N, T);
+                const F3 B = f3(ex::mul(nxt.x, sign), ex::mul(nxt.y, sign), ex::mul(nxt.z, sign));
+                const F3 uv0 = f3(q7.x, q7.y, 0.f), uv1 = f3(q7.z, q7.w, 0.f), uv2 = f3(q8.x, q8.y, 0.f);
+                const F3 tUV = baryLerp(uv0, uv1, uv2, u, v);
+                const int objectID = __float_as_int(q8.z);
+                const DevMaterial& m = S.materials[S.objectMaterial[objectID]];
+                HitData hd;
+                generateHitData(S, m, hd, N, T, B, tUV.x, tUV.y);
+
+                // --- random numbers: 3 for the bounce, 3 for shade of which only the first is used
+                float b1, b2, b3, s1; uint32_t aliasBitsA = 0, aliasBitsB = 0, lightBits = 0;
+                if (P.rngMode == ELEVEN_RNG_REFERENCE) {
+                    Xorwow s = W.rng[pid];
+                    b1 = xorwowUniform(s); b2 = xorwowUniform(s); b3 = xorwowUniform(s);
+                    s1 = xorwowUniform(s); xorwowNext(s); xorwowNext(s);
+                    W.rng[pid] = s;
+                } else {
+                    const uint4 a = fastBits(P, pid, 2u + 2u * depth);
+                    b1 = u32ToUniform(a.x); b2 = u32ToUniform(a.y); b3 = u32ToUniform(a.z); s1 = u32ToUniform(a.w);
+                    const uint4 c = fastBits(P, pid, 3u + 2u * depth);
+                    aliasBitsA = c.x; aliasBitsB = c.y; lightBits = c.z;
+                }
+                const BrdfFrame bf = makeBrdfFrame(hd, ray.d);
+                const F3 L = disneySample(hd, bf, b1, b2, b3);
+                const F3 fB = disneyEval(hd, bf, L);
+                const float pB = disneyPdf(hd, bf, L);
+
+                // --- environment NEE set-up (hdriLight, S/kernel.cu:236-256) -----------------------------------
+                const int EW = S.hdri.width, EH = S.hdri.height;
+                int texel;
+                if (P.envMode == ELEVEN_ENV_CDF) texel = cdfSearch(S.cdf, s1, EW * EH);
+                else {
+                    const uint32_t nT = (uint32_t)(EW * EH);
+                    const uint32_t k = P.rngMode == ELEVEN_RNG_REFERENCE ? min(nT - 1u, (uint32_t)(s1 * (float)nT)) : __umulhi(aliasBitsA, nT);
+                    const float xi = P.rngMode == ELEVEN_RNG_REFERENCE ? s1 * (float)nT - floorf(s1 * (float)nT) : u32ToUniform(aliasBitsB);
+                    const AliasEntry ae = S.alias[k];
+                    texel = xi <= ae.prob ? (int)k : (int)ae.alias;
+                }
+                const float sx = (float)(texel % EW), sy = (float)(texel / EW);
+                const float nu = sx / (float)EW, nv = sy / (float)EH;
+                float iu, iv; inverseTransformUV(S.hdri, nu, nv, iu, iv);
+                const F3 rsm = normalized(reverseSphericalMapping(iu, iv));
+                const F3 wE = f3(-rsm.x, -rsm.y, -rsm.z);
+                const float4 ev = envTexelRaw(S.hdri, (int)(iu * EW), (int)(iv * EH));
+                const float pE = hdriPdf(S, (int)(iu * EW), (int)(iv * EH));
+                const F3 fE = disneyEval(hd, bf, wE);
+                const float cE = fabsf(dot(wE, hd.normal));
+                const F3 CE = f3(fE.x * cE * ev.x / pE, fE.y * cE * ev.y / pE, fE.z * cE * ev.z / pE);
+
+                // --- point-light NEE set-up (pointLight, S/kernel.cu:175-205) -----------------------------------
+                F3 wL = f3(0.f), CP = f3(0.f); float dist = 0.f, pP = 0.f;
+                if (S.lightCount > 0) {
+                    pP = (float)((double)(float)S.lightCount / (2.0 * (double)EL_PI));
+                    int li = P.rngMode == ELEVEN_RNG_REFERENCE ? (int)((float)S.lightCount * s1) : (int)__umulhi(lightBits, S.lightCount);
+                    if (li >= (int)S.lightCount) li = (int)S.lightCount - 1;
+                    const float* lp = S.lights + 6 * li;
+                    const F3 lpos = f3(lp[0], lp[1], lp[2]), lrad = f3(lp[3], lp[4], lp[5]);
+                    wL = normalized(lpos - Pp);
+                    dist = length(lpos - Pp);
+                    const F3 val = lrad / (dist * dist);
+                    const F3 fL = disneyEval(hd, bf, wL);
+                    const float cL = fabsf(dot(wL, hd.normal));
+                    CP = f3(val.x * fL.x * cL / pP, val.y * fL.y * cL / pP, val.z * fL.z * cL / pP);
+                }
+                // --- emission through the BRDF strategy + throughput factor (shade, S/kernel.cu:349,357) ------------
+                const float cB = fabsf(dot(L, hd.normal));
+                const F3 mulB = f3(fB.x * cB / pB, fB.y * cB / pB, fB.z * cB / pB);
+                const F3 CB = hd.emission * mulB;
+
+                W.neeEnvDir[pid] = make_float4(wE.x, wE.y, wE.z, pE);
+                W.neeEnvC[pid] = make_float4(CE.x, CE.y, CE.z, pB);
+                if (S.lightCount > 0) {
+                    W.neeLightDir[pid] = make_float4(wL.x, wL.y, wL.z, dist);
+                    W.neeLightC[pid] = make_float4(CP.x, CP.y, CP.z, pP);
+                }
+                W.neeBrdfC[pid] = make_float4(CB.x, CB.y, CB.z, 0.f);
+                W.neePos[pid] = make_float4(Pp.x, Pp.y, Pp.z, 0.f);
+                W.neeThrMul[pid] = make_float4(mulB.x, mulB.y, mulB.z, 0.f);
+                if (depth == 0) {                                   // first-hit AOVs (S/kernel.cu:436-440)
+                    W.aovN[pid] = make_float4(N.x, N.y, N.z, 0.f);
+                    W.aovT[pid] = make_float4(T.x, T.y, T.z, 0.f);
+                    W.aovB[pid] = make_float4(B.x, B.y, B.z, 0.f);
+                }
+                // next ray: Ray(P + L*0.001, L) (S/kernel.cu:442)
+                const Ray nr = makeRay(ex::madd(Pp, L, 0.001f), L);
+                W.rayO[pid] = make_float4(nr.o.x, nr.o.y, nr.o.z, 0.f);
+                W.rayD[pid] = make_float4(nr.d.x, nr.d.y, nr.d.z, 0.f);
+                W.depth[pid] = depth + 1u;
+                toNee = true;
+                toNext = depth + 1u < P.maxBounces;
+                if ((P.flags & ELEVEN_FLAG_TERMINATE_DEAD_PATHS) && toNext) {
+                    // throughput after this bounce is thr * mulB: exactly zero means no later bounce can contribute
+                    const F3 nt = thr * mulB;
+                    if (nt.x == 0.f && nt.y == 0.f && nt.z == 0.f) toNext = false;
+                }
+            }
+        }
+        appendWarpAggregated(W.qNee, &W.cnt[CNT_NEE], toNee, pid);
+        appendWarpAggregated(W.qNext, &W.cnt[CNT_NEXT], toNext, pid);
+    }
+}
+
+// ---- connect: shadow rays + MIS ------------------------------------------------------------------------------------
+template <int HITMODE, bool COUNT>
+__global__ void __launch_bounds__(128) k_connect(WaveState W, const __grid_constant__ DevScene S, const __grid_constant__ RenderParams P) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t n = W.cnt[CNT_NEE];
+    TraceCounters tc; tc.nodes = 0; tc.tris = 0;
+    for (;;) {
+        const uint32_t base = warpFetch(&W.cnt[CNT_WORK_CONNECT], lane);
+        if (base >= n) break;
+        const uint32_t qi = base + lane;
+        if (qi >= n) continue;
+        const uint32_t pid = W.qNee[qi];
+        const float4 pos4 = W.neePos[pid];
+        const F3 Pp = f3(pos4.x, pos4.y, pos4.z);
+        const float4 ed = W.neeEnvDir[pid], ec = W.neeEnvC[pid];
+        const float pB = ec.w;
+        float pE = ed.w;
+        F3 CE = f3(ec.x, ec.y, ec.z);
+        HitRec h;
+        {   // environment shadow ray: any valid hit occludes (S/kernel.cu:246-248)
+            const F3 w = f3(ed.x, ed.y, ed.z);
+            const Ray sr = makeRay(ex::madd(Pp, w, 0.001f), w);
+            if (traverse<TRACE_ANY, COUNT>(S, sr, INFINITY, h, &tc)) { pE = 0.f; CE = f3(0.f); }   // hdriPdf defined as 0 when occluded
+        }
+        float pP = 0.f; F3 CP = f3(0.f);
+        if (S.lightCount > 0) {
+            const float4 ld = W.neeLightDir[pid], lc = W.neeLightC[pid];
+            pP = lc.w; CP = f3(lc.x, lc.y, lc.z);
+            const F3 w = f3(ld.x, ld.y, ld.z);
+            const float dist = ld.w;
+            const Ray sr = makeRay(ex::madd(Pp, w, 0.001f), w);
+            bool occluded;
+            if (HITMODE == ELEVEN_HIT_KEY) {
+                // the reference takes the closest hit and compares |hit.position - point| with the light distance (S/kernel.cu:193-197)
+                occluded = false;
+                if (traverse<TRACE_CLOSEST_KEY, COUNT>(S, sr, INFINITY, h, &tc)) {
+                    const TriGeom g = loadTriGeom(S.shadeTris, h.tri);
+                    F3 sn;
+                    const F3 hp = hitPosition(sr, g, h.t, h.u, h.v, sn);
+                    occluded = length(hp - Pp) < dist;
+                }
+            } else {
+                occluded = traverse<TRACE_ANY, COUNT>(S, sr, dist - 0.001f, h, &tc);
+            }
+            if (occluded) CP = f3(0.f);
+        }
+        const float4 bc = W.neeBrdfC[pid];
+        const float sum = pE + pP + pB;
+        const float w1 = pE / sum, w2 = pP / sum, w3 = pB / sum;
+        const float4 thr4 = W.thr[pid];
+        const F3 thr = f3(thr4.x, thr4.y, thr4.z);
+        const F3 mix = f3(w1 * CE.x + w2 * CP.x + w3 * bc.x, w1 * CE.y + w2 * CP.y + w3 * bc.y, w1 * CE.z + w2 * CP.z + w3 * bc.z);
+        float4 r = W.rad[pid];
+        r.x += thr.x * mix.x; r.y += thr.y * mix.y; r.z += thr.z * mix.z;
+        W.rad[pid] = r;
+        const float4 tm = W.neeThrMul[pid];
+        W.thr[pid] = make_float4(thr.x * tm.x, thr.y * tm.y, thr.z * tm.z, 0.f);
+    }
+    if (COUNT) { atomicAdd(&W.stats[ST_NODES], (unsigned long long)tc.nodes); atomicAdd(&W.stats[ST_TRIS], (unsigned long long)tc.tris); }
+}
+
+// ---- queue bookkeeping between bounces (single thread) ---------------------------------------------------------------
+__global__ void k_advance(WaveState W, uint32_t lights, int phase) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (phase == 0) {            // after extend+shade: account rays, arm connect
+        W.stats[ST_RAYS_EXT] += W.cnt[CNT_CUR];
+        W.stats[ST_RAYS_ENV] += W.cnt[CNT_NEE];
+        if (lights) W.stats[ST_RAYS_LIGHT] += W.cnt[CNT_NEE];
+        W.cnt[CNT_WORK_CONNECT] = 0u;
+    } else {                     // after connect: next bounce
+        W.cnt[CNT_CUR] = W.cnt[CNT_NEXT]; W.cnt[CNT_NEXT] = 0u; W.cnt[CNT_NEE] = 0u;
+        W.cnt[CNT_WORK_TRACE] = 0u; W.cnt[CNT_WORK_SHADE] = 0u;
+    }
+}
+
+// ---- accumulate (S/kernel.cu:445-480) with sums instead of running means -------------------------------------------------
+__global__ void __launch_bounds__(256) k_accumulate(WaveState W) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= W.nPixels) return;
+    W.pathCount[i] += W.depth[i];
+    float4 r = W.rad[i];
+    r.x = clampf_(r.x, 0.f, 10.f); r.y = clampf_(r.y, 0.f, 10.f); r.z = clampf_(r.z, 0.f, 10.f);
+    if (!isnan(r.x) && !isnan(r.y) && !isnan(r.z)) {
+        float4 b = W.filmBeauty[i]; b.x += r.x; b.y += r.y; b.z += r.z; W.filmBeauty[i] = b;
+        const float4 n = W.aovN[i], t = W.aovT[i], bt = W.aovB[i];
+        float4 a = W.filmNormal[i]; a.x += n.x; a.y += n.y; a.z += n.z; W.filmNormal[i] = a;
+        a = W.filmTangent[i]; a.x += t.x; a.y += t.y; a.z += t.z; W.filmTangent[i] = a;
+        a = W.filmBitangent[i]; a.x += bt.x; a.y += bt.y; a.z += bt.z; W.filmBitangent[i] = a;
+        W.filmCount[i] += 1u;
+    }
+}
+
+// film read-back: mean, alpha = 1 (S/kernel.cu:137,461-463)
+__global__ void k_resolve(const float4* __restrict__ sums, const uint32_t* __restrict__ counts, float4* __restrict__ out, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 s = sums[i]; const uint32_t c = counts[i];
+    const float inv = c ? 1.0f / (float)c : 0.f;
+    out[i] = make_float4(s.x * inv, s.y * inv, s.z * inv, 1.0f);
+}
+// fused resolve -> 8-bit with the reference's output curve fastPow(clamp01(x), 1/2.2)*255 (S/main.cpp:156-158, S/PostProcessing.cpp:30-33)
+__device__ __forceinline__ double fastPowDev(double a, double b) {
+    int hi = __double2hiint(a);
+    hi = (int)(b * (double)(hi - 1072632447) + 1072632447.0);
+    return __hiloint2double(hi, 0);
+}
+__global__ void k_resolve8(const float4* __restrict__ sums, const uint32_t* __restrict__ counts, uchar4* __restrict__ out, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 s = sums[i]; const uint32_t c = counts[i];
+    const float inv = c ? 1.0f / (float)c : 0.f;
+    const float v[4] = {s.x * inv, s.y * inv, s.z * inv, 1.0f};
+    unsigned char o[4];
+    for (int k = 0; k < 4; k++) {
+        const float x = clampf_(v[k], 0.f, 1.f);
+        o[k] = (unsigned char)(fastPowDev((double)x, 1.0 / 2.2) * 255.0);
+    }
+    out[i] = make_uchar4(o[0], o[1], o[2], o[3]);
+}
+
+// ---- test hook / bench: closest hit on a plain ray batch (eleven_trace_*) -----------------------------------------------
+template <int MODE, bool COUNT>
+__global__ void __launch_bounds__(128) k_traceBatch(const float* __restrict__ rays, uint32_t n, ElevenHit* __restrict__ hits,
+                                                  const __grid_constant__ DevScene S, uint32_t* workCounter, unsigned long long* stats) {
+    const uint32_t lane = threadIdx.x & 31u;
+    TraceCounters tc; tc.nodes = 0; tc.tris = 0;
+    for (;;) {
+        const uint32_t base = warpFetch(workCounter, lane);
+        if (base >= n) break;
+        const uint32_t i = base + lane;
+        if (i >= n) continue;
+        const float* r = rays + 6 * (size_t)i;
+        const Ray ray = makeRay(f3(r[0], r[1], r[2]), f3(r[3], r[4], r[5]));
+        HitRec h;
+        traverse<MODE, COUNT>(S, ray, INFINITY, h, &tc);
+        ElevenHit o; o.tri = h.tri; o.t = h.t; o.u = h.u; o.v = h.v; o.key = h.key;
+        hits[i] = o;
+    }
+    if (COUNT && stats) { atomicAdd(&stats[ST_NODES], (unsigned long long)tc.nodes); atomicAdd(&stats[ST_TRIS], (unsigned long long)tc.tris); }
+}
+
+} // namespace eleven

@@ -1,0 +1,277 @@
+/*
+ * shading.cuh — camera, texture fetch, environment, sampling routines and the Disney principled BRDF (device).
+ *
+ * Same estimator as the reference (so that images converge to the same result), new data layout:
+ *   textures   8-bit RGBA texels (4 B, one 32-bit load) decoded through the 256-entry fastPow tables that reproduce
+ *              stb_image's patched LDR decode bit for bit (S/stb_image.h:127-136,1863), instead of float RGB (12 B);
+ *              float textures are padded to float4 (one 128-bit load)
+ *   HDRI       float4 texels whose .w caches (r+g)+b, the quantity both the CDF and pdf() need (S/HDRI.hpp:115,148)
+ * Function-by-function provenance is cited inline.  Plain float arithmetic (FMA contraction allowed): results are
+ * compared with the reference under the image tolerance, not bit-exactly (only libm-free geometry is, see ex::).
+ */
+#pragma once
+#include "common.cuh"
+#include "traverse.cuh"
+
+namespace eleven {
+
+__device__ __forceinline__ float minf_(float a, float b) { return a < b ? a : b; }          // S/Math.hpp:60 (NaN-unsafe on purpose)
+__device__ __forceinline__ float maxf_(float a, float b) { return a > b ? a : b; }          // S/Math.hpp:64
+__device__ __forceinline__ float clampf_(float a, float b, float c) { return a < b ? b : a > c ? c : a; }   // S/Math.hpp:29
+__device__ __forceinline__ float lerpf_(float a, float b, float c) { return a + c * (b - a); }              // S/Math.hpp:43 FAST_LERP
+__device__ __forceinline__ F3 lerp3(F3 a, F3 b, float c) { return f3(lerpf_(a.x, b.x, c), lerpf_(a.y, b.y, c), lerpf_(a.z, b.z, c)); }
+
+// ---- texture fetch: S/Texture.hpp:95-142 -----------------------------------------------------------
+__device__ __forceinline__ F3 texelAt(const DevTex& t, const float* __restrict__ lut, int x, int y) {
+    x = (int)(t.xTile * (x + t.xOffset * t.width)) % t.width;
+    y = (int)(t.yTile * (y + t.yOffset * t.height)) % t.height;
+    long long idx = (long long)y * t.width + x;                       // the reference indexes 3*(y*W+x): negative x walks into row y-1
+    const long long n = (long long)t.width * t.height;
+    idx = idx < 0 ? 0 : (idx >= n ? n - 1 : idx);                     // defined behaviour for the reference's out-of-bounds reads
+    if (t.format == ELEVEN_TEX_F32_RGB) {
+        const float4 v = __ldg((const float4*)t.data + idx);
+        return f3(v.x, v.y, v.z);
+    }
+    const uchar4 c = __ldg((const uchar4*)t.data + idx);
+    const float* l = lut + (t.format == ELEVEN_TEX_U8_SRGB ? 0 : 256);
+    return f3(__ldg(l + c.x), __ldg(l + c.y), __ldg(l + c.z));
+}
+__device__ __forceinline__ F3 texFromUV(const DevTex& t, const float* lut, float u, float v) {            // :110-112
+    return texelAt(t, lut, (int)(u * t.width), (int)(v * t.height));
+}
+__device__ __forceinline__ F3 texBilinear(const DevTex& t, const float* lut, float u, float v) {          // :114-135
+    const float x = u * t.width, y = v * t.height;
+    const float t1x = floorf(x), t1y = floorf(y), t2x = t1x + 1, t2y = t1y + 1;
+    const float a = (x - t1x) / (t2x - t1x), b = (y - t1y) / (t2y - t1y);
+    const F3 v1 = texelAt(t, lut, (int)t1x, (int)t1y), v2 = texelAt(t, lut, (int)t2x, (int)t1y);
+    const F3 v3 = texelAt(t, lut, (int)t1x, (int)t2y), v4 = texelAt(t, lut, (int)t2x, (int)t2y);
+    return lerp3(lerp3(v1, v2, a), lerp3(v3, v4, a), b);
+}
+__device__ __forceinline__ F3 texFiltered(const DevTex& t, const float* lut, float u, float v) {          // :137-142
+    return t.filter == 0 ? texFromUV(t, lut, u, v) : texBilinear(t, lut, u, v);
+}
+
+// ---- environment: S/Texture.hpp:144-207, S/HDRI.hpp:130-162 ------------------------------------------
+__device__ __forceinline__ void limitUV(float& u, float& v) {                                              // S/Math.hpp:38-41
+    u += (float)(-(int)(u > 1) + -(int)(u < 0));
+    v += (float)(-(int)(v > 1) + -(int)(v < 0));
+}
+__device__ __forceinline__ void sphericalMapping(F3 p, float& u, float& v) {                               // S/Texture.hpp:144-156 with origin 0, radius 1
+    const float theta = acosf(-p.y);
+    const float phi = atan2f(-p.z, p.x) + EL_PI;
+    u = phi / (2 * EL_PI);
+    v = theta / EL_PI;
+    limitUV(u, v);
+}
+__device__ __forceinline__ F3 reverseSphericalMapping(float u, float v) {                                  // S/Texture.hpp:195-207
+    const float phi = u * 2 * EL_PI, theta = v * EL_PI;
+    const float px = cosf(phi - EL_PI), py = -cosf(theta), pz = -sinf(phi - EL_PI);
+    const float a = sqrtf(1 - py * py);
+    return f3(a * px, py, a * pz);
+}
+__device__ __forceinline__ void inverseTransformUV(const DevTex& t, float u, float v, float& nu, float& nv) {   // S/Texture.hpp:177-193
+    int x = (int)(u * t.width), y = (int)(v * t.height);
+    x = (int)(t.xTile * (x - t.xOffset * t.width)) % t.width;
+    y = (int)(t.yTile * (y - t.yOffset * t.height)) % t.height;
+    nu = (float)x / (float)t.width; nv = (float)y / (float)t.height;
+    limitUV(nu, nv);
+}
+__device__ __forceinline__ float4 envTexelRaw(const DevTex& t, int x, int y) {
+    x = (int)(t.xTile * (x + t.xOffset * t.width)) % t.width;
+    y = (int)(t.yTile * (y + t.yOffset * t.height)) % t.height;
+    long long idx = (long long)y * t.width + x;
+    const long long n = (long long)t.width * t.height;
+    idx = idx < 0 ? 0 : (idx >= n ? n - 1 : idx);
+    return __ldg((const float4*)t.data + idx);
+}
+// radiance seen by an escaped ray: S/kernel.cu:415-417 (nearest texel; bilinear if the texture says so)
+__device__ __forceinline__ F3 envLookup(const DevScene& S, F3 dir) {
+    float u, v;
+    sphericalMapping(f3(-dir.x, -dir.y, -dir.z), u, v);
+    if (S.hdri.filter == 0) { const float4 c = envTexelRaw(S.hdri, (int)(u * S.hdri.width), (int)(v * S.hdri.height)); return f3(c.x, c.y, c.z); }
+    return texBilinear(S.hdri, nullptr, u, v);
+}
+// S/HDRI.hpp:130-142: the reference's own (approximate) lower bound
+__device__ __forceinline__ int cdfSearch(const float* __restrict__ arr, float value, int length) {
+    int from = 0, to = length - 1;
+    while (to - from > 0) {
+        const int m = from + (to - from) / 2;
+        const float a = __ldg(arr + m);
+        if (value == a) return m;
+        if (value < a) to = m - 1;
+        if (value > a) from = m + 1;
+    }
+    return to;
+}
+// S/HDRI.hpp:145-152
+__device__ __forceinline__ float hdriPdf(const DevScene& S, int x, int y) {
+    const float4 dv = envTexelRaw(S.hdri, x, y);
+    const float theta = (((float)y / (float)S.hdri.height)) * EL_PI;
+    return (float)((double)(((dv.w) / S.radianceSum) * S.hdri.width * S.hdri.height) / (2.0 * (double)EL_PI * (double)sinf(theta)));
+}
+
+// ---- sampling: S/Sampling.hpp:21-54 ------------------------------------------------------------------
+__device__ __forceinline__ void uniformCircleSampling(float u1, float u2, float u3, float& x, float& y) {
+    const float t = 2 * EL_PI * u1, u = u2 + u3, r = u > 1 ? 2 - u : u;
+    float s, c; sincosf(t, &s, &c);
+    x = r * c; y = r * s;
+}
+__device__ __forceinline__ F3 cosineSampleHemisphere(float u1, float u2) {
+    const float r = sqrtf(u1), phi = (float)(2.0 * (double)EL_PI * (double)u2);
+    float s, c; sincosf(phi, &s, &c);
+    F3 d; d.x = r * c; d.y = r * s;
+    d.z = sqrtf(maxf_(0.0f, (float)(1.0 - (double)(d.x * d.x) - (double)(d.y * d.y))));
+    return d;
+}
+__device__ __forceinline__ F3 importanceSampleGGX(float rgh, float r1, float r2) {
+    const float a = maxf_(0.001f, rgh);
+    const float phi = r1 * EL_PI * 2;
+    const float cosTheta = (float)sqrt((1.0 - (double)r2) / (1.0 + ((double)(a * a) - 1.0) * (double)r2));
+    const float sinTheta = clampf_((float)sqrt(1.0 - (double)(cosTheta * cosTheta)), 0.0f, 1.0f);
+    float sp, cp; sincosf(phi, &sp, &cp);
+    return f3(sinTheta * cp, sinTheta * sp, cosTheta);
+}
+
+// ---- Disney principled BRDF: S/Disney.hpp:41-253 -----------------------------------------------------
+struct HitData {                                                                                           // S/kernel.h:46-69
+    float metallic, roughness, clearcoatGloss, clearcoat, anisotropic, eta, transmission, specular, specularTint, sheenTint, subsurface, sheen;
+    F3 emission, albedo, normal;
+};
+__device__ __forceinline__ void createBasis(F3 n, F3& T, F3& B) { T = normalized(cross(f3(0, 1, 0), n)); B = normalized(cross(n, T)); }   // :41-45
+__device__ __forceinline__ float schlick(float u) { const float m = clampf_(1.0f - u, 0.0f, 1.0f); const float m2 = m * m; return m2 * m2 * m; }
+__device__ __forceinline__ float GTR1(float NDotH, float a) {                                              // :67-73
+    if (a >= 1.0f) return 1.0f / EL_PI;
+    const float a2 = a * a;
+    const float t = 1.0f + (a2 - 1.0f) * NDotH * NDotH;
+    return (a2 - 1.0f) / (EL_PI * logf(a2) * t);
+}
+__device__ __forceinline__ float GTR2aniso(float NDotH, float HDotX, float HDotY, float ax, float ay) {    // :81-86
+    const float a = HDotX / ax, b = HDotY / ay, c = a * a + b * b + NDotH * NDotH;
+    return 1.0f / (EL_PI * ax * ay * c * c);
+}
+__device__ __forceinline__ float smithG(float NDotV, float alphaG) { const float a = alphaG * alphaG, b = NDotV * NDotV; return 1.0f / (NDotV + sqrtf(a + b - a * b)); }
+__device__ __forceinline__ float smithGaniso(float NDotV, float VDotX, float VDotY, float ax, float ay) {
+    const float a = VDotX * ax, b = VDotY * ay, c = NDotV;
+    return 1.0f / (NDotV + sqrtf(a * a + b * b + c * c));
+}
+// everything about the BRDF that depends on the hit point only (not on L): hoisted out of the up-to-3 Eval calls per hit
+struct BrdfFrame {
+    F3 N, V, T, B;
+    float NDotV, ax, ay, diffuseRatio;
+    F3 Cspec0, Csheen;
+    bool frontV;
+};
+__device__ __forceinline__ BrdfFrame makeBrdfFrame(const HitData& hd, F3 rayDir) {
+    BrdfFrame f;
+    f.N = hd.normal; f.V = f3(-rayDir.x, -rayDir.y, -rayDir.z);
+    createBasis(hd.normal, f.T, f.B);
+    f.NDotV = fabsf(dot(f.N, f.V)); f.frontV = dot(f.N, f.V) > 0.0f;
+    const float aspect = sqrtf(1.0f - hd.anisotropic * 0.9f);
+    f.ax = maxf_(0.001f, hd.roughness / aspect); f.ay = maxf_(0.001f, hd.roughness * aspect);
+    f.diffuseRatio = 0.5f * (1.0f - hd.metallic);
+    const F3 Cd = hd.albedo;
+    const float Cdlum = 0.3f * Cd.x + 0.6f * Cd.y + 0.1f * Cd.z;
+    const F3 Ctint = Cdlum > 0.0f ? Cd / Cdlum : f3(1.0f);
+    f.Cspec0 = lerp3((hd.specular * 0.08f) * lerp3(f3(1.0f), Ctint, hd.specularTint), Cd, hd.metallic);
+    f.Csheen = lerp3(f3(1.0f), Ctint, hd.sheenTint);
+    return f;
+}
+__device__ __forceinline__ F3 disneyEval(const HitData& hd, const BrdfFrame& f, F3 L) {                    // :179-253
+    if (!(hd.transmission < 1.0f && dot(f.N, L) > 0.0f && f.frontV)) return f3(0.f);
+    const F3 H = normalized(L + f.V);
+    const float NDotL = fabsf(dot(f.N, L)), NDotV = f.NDotV, NDotH = fabsf(dot(f.N, H)), LDotH = fabsf(dot(L, H));
+    const float FL = schlick(NDotL), FV = schlick(NDotV);
+    const float Fd90 = 0.5f + 2.0f * LDotH * LDotH * hd.roughness;
+    const float Fd = lerpf_(1.0f, Fd90, FL) * lerpf_(1.0f, Fd90, FV);
+    const float Fss90 = LDotH * LDotH * hd.roughness;
+    const float Fss = lerpf_(1.0f, Fss90, FL) * lerpf_(1.0f, Fss90, FV);
+    const float ss = 1.25f * (Fss * (1.0f / (NDotL + NDotV) - 0.5f) + 0.5f);
+    const float Ds = GTR2aniso(NDotH, dot(H, f.T), dot(H, f.B), f.ax, f.ay);
+    const float FH = schlick(LDotH);
+    const F3 Fs = lerp3(f.Cspec0, f3(1.0f), FH);
+    float Gs = smithGaniso(NDotL, dot(L, f.T), dot(L, f.B), f.ax, f.ay);
+    Gs *= smithGaniso(NDotV, dot(f.V, f.T), dot(f.V, f.B), f.ax, f.ay);
+    const F3 Fsheen = (FH * hd.sheen) * f.Csheen;
+    const float Dr = GTR1(NDotH, lerpf_(0.1f, 0.001f, hd.clearcoatGloss));
+    const float Fr = lerpf_(0.04f, 1.0f, FH);
+    const float Gr = smithG(NDotL, 0.25f) * smithG(NDotV, 0.25f);
+    const F3 diffuse = (((1.0f / EL_PI) * lerpf_(Fd, ss, hd.subsurface)) * hd.albedo + Fsheen) * (1.0f - hd.metallic);
+    const F3 spec = (Gs * Fs) * Ds;
+    const float coat = 0.25f * hd.clearcoat * Gr * Fr * Dr;
+    return f3(diffuse.x + spec.x + coat, diffuse.y + spec.y + coat, diffuse.z + spec.z + coat);
+}
+__device__ __forceinline__ float disneyPdf(const HitData& hd, const BrdfFrame& f, F3 L) {                  // :108-147
+    if (dot(f.N, L) <= 0.0f) return 1.0f;
+    const F3 H = normalized(L + f.V);
+    const float NDotH = fabsf(dot(f.N, H));
+    const float clearcoatAlpha = lerpf_(0.1f, 0.001f, hd.clearcoatGloss);
+    const float specularRatio = 1.0f - f.diffuseRatio;
+    const float pdfGTR2 = GTR2aniso(NDotH, dot(H, f.T), dot(H, f.B), f.ax, f.ay) * NDotH;
+    const float pdfGTR1 = GTR1(NDotH, clearcoatAlpha) * NDotH;
+    const float ratio = 1.0f / (1.0f + hd.clearcoat);
+    const float pdfSpec = lerpf_(pdfGTR1, pdfGTR2, ratio) / (4.0f * fabsf(dot(L, H)));
+    const float pdfDiff = fabsf(dot(L, f.N)) * (1.0f / EL_PI);
+    return f.diffuseRatio * pdfDiff + specularRatio * pdfSpec;
+}
+__device__ __forceinline__ F3 disneySample(const HitData& hd, const BrdfFrame& f, float r1, float r2, float r3) {   // :150-177
+    if (r3 < f.diffuseRatio) {
+        const F3 H = cosineSampleHemisphere(r1, r2);
+        return f.T * H.x + f.B * H.y + f.N * H.z;
+    }
+    F3 H = importanceSampleGGX(hd.roughness, r1, r2);
+    H = f.T * H.x + f.B * H.y + f.N * H.z;
+    const F3 I = f3(-f.V.x, -f.V.y, -f.V.z);
+    return I - (2 * dot(I, H)) * H;                                                                        // reflect, S/Vector.hpp:214
+}
+
+// ---- S/kernel.cu:54-119 generateHitData ---------------------------------------------------------------
+__device__ __forceinline__ void generateHitData(const DevScene& S, const DevMaterial& m, HitData& hd, F3 normal, F3 tangent, F3 bitangent, float tu, float tv) {
+    hd.albedo = m.albedoTex < 0 ? f3(m.albedo[0], m.albedo[1], m.albedo[2]) : texFiltered(S.textures[m.albedoTex], S.lut, tu, tv);
+    hd.emission = m.emissionTex < 0 ? f3(m.emission[0], m.emission[1], m.emission[2]) : texFiltered(S.textures[m.emissionTex], S.lut, tu, tv);
+    hd.roughness = m.roughnessTex < 0 ? m.roughness : texFiltered(S.textures[m.roughnessTex], S.lut, tu, tv).x;
+    hd.metallic = m.metallicTex < 0 ? m.metallic : texFiltered(S.textures[m.metallicTex], S.lut, tu, tv).x;
+    if (m.normalTex < 0) hd.normal = normal;
+    else {
+        const F3 nc = texFromUV(S.textures[m.normalTex], S.lut, tu, tv);
+        const F3 ln = f3(nc.x * 2 - 1, nc.y * 2 - 1, nc.z * 2 - 1);
+        hd.normal = normalized(ln.x * tangent - ln.y * bitangent + ln.z * normal);
+    }
+    hd.roughness = powf(hd.roughness, 2.2f);            // "linear to sRGB", applied to constants too (S/kernel.cu:103-104)
+    hd.metallic = powf(hd.metallic, 2.2f);
+    hd.clearcoatGloss = m.clearcoatGloss; hd.clearcoat = m.clearcoat; hd.anisotropic = m.anisotropic; hd.eta = m.eta;
+    hd.transmission = m.transmission; hd.specular = m.specular; hd.specularTint = m.specularTint; hd.sheenTint = m.sheenTint;
+    hd.subsurface = m.subsurface; hd.sheen = m.sheen;
+}
+
+// ---- S/kernel.cu:260-337 calculateCameraRay --------------------------------------------------------------
+// The three Euler rotations are per-frame constants: sin/cos are hoisted to the host (CamRot), the reference
+// recomputes six sin/cos per ray (S/kernel.cu:304-306).
+struct CamRot { float sx, cx, sy, cy, sz, cz; };
+__device__ __forceinline__ Ray cameraRay(const DevCamera& c, const CamRot& R, int x, int y, float r1, float r2, float r3, float r4, float r5) {
+    const F3 pos = f3(c.pos[0], c.pos[1], c.pos[2]);
+    const float dx = pos.x + ((float)x) / ((float)c.xRes) * c.sensorWidth;
+    const float dy = pos.y + ((float)y) / ((float)c.yRes) * c.sensorHeight;
+    const float odx = (float)((double)(-c.sensorWidth) / 2.0 + (double)dx);
+    const float ody = (float)((double)(-c.sensorHeight) / 2.0 + (double)dy);
+    const float rx = (float)((1.0 / (double)(float)c.xRes) * ((double)r1 - 0.5) * (double)c.sensorWidth);
+    const float ry = (float)((1.0 / (double)(float)c.yRes) * ((double)r2 - 0.5) * (double)c.sensorHeight);
+    const float SPx = odx + rx, SPy = ody + ry, SPz = pos.z + c.focalLength;
+    const F3 dir = f3(SPx, SPy, SPz) - pos;
+    const F3 dX = f3(dir.x, dir.y * R.cx - dir.z * R.sx, dir.y * R.sx + dir.z * R.cx);
+    const F3 dY = f3(dX.x * R.cy + dX.z * R.sy, dX.y, dX.z * R.cy - dX.x * R.sy);
+    const F3 dZ = f3(dY.x * R.cz - dY.y * R.sz, dY.x * R.sz + dY.y * R.cz, dY.z);
+    Ray ray = makeRay(pos, dZ);
+    if (c.bokeh) {
+        const float diameter = c.focalLength / c.aperture;
+        const float l = c.focusDistance + c.focalLength;
+        const F3 focusPoint = ray.o + ray.d * l;
+        float ix, iy;
+        uniformCircleSampling(r3, r4, r5, ix, iy);
+        ix *= diameter * 0.5f; iy *= diameter * 0.5f;
+        const F3 orig = pos + f3(ix, iy, 0.f);
+        ray = makeRay(orig, focusPoint - orig);
+    }
+    return ray;
+}
+
+} // namespace eleven
