@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""bench.py — samples/s (and Mrays/s) of the path-tracing hot path on the ClockCC0 stand-in, 1..8 B200s.
+
+Contract (see the task statement): `python bench.py --gpus N --steps K --warmup W` prints ONE JSON line on rank 0.
+
+Workload (BASELINE.json configs[2], the configuration the metric is quoted on): the ClockCC0 STAND-IN scene
+(125 281 triangles, 12 x 4096^2 8-bit maps, 4096x2048 HDRI, depth of field; the real asset is not in the reference
+checkout) at 1920x1080.  One step = `--spp-per-step` samples of every pixel on every GPU (weak scaling:
+GPU g renders the global samples g, g+N, g+2N, ...), followed for N > 1 by one NCCL reduce of the per-GPU film sums +
+sample counts to rank 0 over NVLink.  value = pixel-samples rendered by all ranks / time.
+
+  value     fast path (counter RNG, alias-table env sampling, dead-path termination), scene resident in HBM
+  e2e       same metric through the C ABI with host buffers: per step a camera upload (H2D), the render, and the
+            BEAUTY film read back to host memory (D2H), all inside the timed region
+  roofline  the closest-hit kernel: algorithmic bytes/ray (80 B x nodes + 48 B x triangles + 48 B ray in / hit out,
+            counted by a counters build of the same kernel on the same rays) / its CUDA-event time, vs measured HBM copy
+  cpu_baseline   the CPU oracle (port of the reference algorithm) on the host cores, bounded sample
+
+`--impl reference` times the UNMODIFIED reference renderer.  The reference has no CPU render path, so —
+as BASELINE.json's north_star prescribes — this arm runs the reference CUDA build (oracle/_ref/eleven_ref_headless_fast,
+the flavour its author shipped: -use_fast_math) on ONE B200, labelled as such.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "golden")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+CACHE = os.environ.get("ELEVEN_BENCH_CACHE", "/tmp/eleven_bench_cache")
+
+
+# ------------------------------------------------------------------------------------------------------
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled during the timed region."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.p = None
+        self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for ln in self.p.stdout:
+            self.rows.append([c.strip() for c in ln.split(",")])
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def get_scene(args, need_dir):
+    """ClockCC0 stand-in, generated once per box and cached (flat container for us/oracle, scene dir for the reference)."""
+    from tfg_pathtracer_b200 import scenes as S
+    tag = "clock_t%d_%dx%d" % (args.tex, args.width, args.height)
+    flat = os.path.join(CACHE, tag + ".flat")
+    sdir = os.path.join(CACHE, tag + "_dir")
+    os.makedirs(CACHE, exist_ok=True)
+    lock = os.path.join(CACHE, tag + ".lock")
+    # one generator per box; other ranks wait
+    while True:
+        try:
+            fd = os.open(lock, os.O_CREAT | os.O_EXCL | os.O_WRONLY)
+            os.close(fd)
+            break
+        except FileExistsError:
+            if os.path.exists(flat + ".done") and (not need_dir or os.path.exists(sdir + ".done")):
+                return flat, sdir
+            time.sleep(0.5)
+    try:
+        sc = None
+        if not os.path.exists(flat + ".done"):
+            sc = S.clock_standin(tex_res=args.tex, xres=args.width, yres=args.height)
+            S.save_flat(sc, flat)
+            open(flat + ".done", "w").close()
+        if need_dir and not os.path.exists(sdir + ".done"):
+            sc = sc or S.load_flat(flat)
+            sc.object_names, sc.material_names = ["clock", "table", "plant"], ["clock_mat", "table_mat", "plant_mat"]
+            S.write_reference_scene_dir(sc, sdir)
+            open(sdir + ".done", "w").close()
+    finally:
+        os.remove(lock)
+    return flat, sdir
+
+
+# ------------------------------------------------------------------------------------------------------
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    binp = os.path.join(ROOT, "oracle", "_ref", "eleven_ref_headless_fast")
+    base = {"impl": "reference", "metric": "samples_per_second", "unit": "pixel-samples/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic"}
+    if not os.path.exists(binp):
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/eleven_ref_headless_fast not built (needs /root/reference at build time)"}))
+        return
+    flat, sdir = get_scene(args, need_dir=True)
+    spp_w, spp_t = args.warmup * args.ref_spp_per_step, args.steps * args.ref_spp_per_step
+    sm = ClockSampler(0)
+    sm.start()
+    t0 = time.time()
+    p = subprocess.run([binp, sdir, str(spp_t), os.path.join(CACHE, "ref_out"), "--warmup", str(spp_w)], capture_output=True, text=True, cwd=sdir)
+    wall = time.time() - t0
+    clocks = sm.stop()
+    if p.returncode != 0:
+        print(json.dumps({"impl": "reference", "unavailable": "reference run failed rc=%d: %s" % (p.returncode, (p.stderr or p.stdout)[-300:].replace("\n", " "))}))
+        return
+    info = json.loads(open(os.path.join(CACHE, "ref_out.json")).read())
+    v = info["samples_per_s"]
+    base.update({"value": v, "ms_per_step": info["render_ms"] / args.steps,
+                 "config": {"workload": "ClockCC0 stand-in %dx%d, %d spp/step, reference renderer (CUDA build, -use_fast_math) on 1 B200" % (args.width, args.height, args.ref_spp_per_step),
+                            "spp_per_step": args.ref_spp_per_step, "tris": info["tris"], "l2": "working set (2.4 GB float textures) larger than L2"},
+                 "cpu_baseline": {"value": v, "unit": "pixel-samples/s", "cores": 0, "kind": "reference",
+                                  "sample": "%d spp of the full frame on ONE B200 (the reference has no CPU render path, SURVEY F3; north_star: report its CUDA build, labelled)" % spp_t,
+                                  "device": "1x B200, reference CUDA build"},
+                 "e2e": {"value": v, "unit": "pixel-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                 "reference": {"load_ms": info["load_ms"], "setup_ms": info["setup_ms"], "render_ms": info["render_ms"], "kpaths_per_s": info["kpaths_per_s"],
+                               "hit_bounces": info["hit_bounces"], "wall_s": wall},
+                 "clocks": clocks, "gpu_launches": spp_t + spp_w})
+    print(json.dumps(base))
+
+
+# ------------------------------------------------------------------------------------------------------
+class DevArray:
+    """Zero-copy view of a device buffer owned by the C-ABI context, for torch.distributed (plumbing only)."""
+
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+def cpu_baseline(args, flat):
+    import oracle_lib as O
+    from tfg_pathtracer_b200 import scenes as S
+    sc = S.load_flat(flat)
+    threads = os.cpu_count() or 1
+    t0 = time.time()
+    orc = O.Oracle(sc)
+    setup = time.time() - t0
+    rows = max(8, min(sc.height, int(args.cpu_rows)))
+    y0 = (sc.height - rows) // 2
+    t0 = time.time()
+    orc.render(1, threads=threads, rows=(y0, y0 + rows))
+    dt = time.time() - t0
+    n = rows * sc.width
+    rc = orc.ray_counts()
+    orc.close()
+    return {"value": n / dt, "unit": "pixel-samples/s", "cores": threads, "kind": "port",
+            "sample": "1 spp of %d central rows (%d pixel-samples) of the same frame, oracle/eleven_oracle.cpp, %.1f s (+%.1f s reference-style BVH build)" % (rows, n, dt, setup),
+            "mrays_per_s": float(rc.sum()) / dt / 1e6}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--spp-per-step", type=int, default=16)
+    ap.add_argument("--ref-spp-per-step", type=int, default=4)
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--tex", type=int, default=4096)
+    ap.add_argument("--cpu-rows", type=int, default=96)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="fast", choices=["fast", "parity"])
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from tfg_pathtracer_b200 import renderer as R, scenes as S
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the product path)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    flat, _ = get_scene(args, need_dir=False)
+    sc = S.load_flat(flat)
+    W, H = sc.width, sc.height
+    mode = dict(R.FAST if args.mode == "fast" else R.PARITY)
+    t0 = time.time()
+    r = R.Renderer(device=local, sample_offset=rank, sample_stride=world, **mode).render_setup(sc)
+    setup_s = time.time() - t0
+    film = torch.as_tensor(DevArray(*r.film_sums_ptr(R.PASS_BEAUTY), "<f4"), device="cuda:%d" % local)
+    counts = torch.as_tensor(DevArray(*r.film_counts_ptr(), "<i4"), device="cuda:%d" % local)
+    S_ = args.spp_per_step
+
+    def step():
+        r.render_cuda(S_)
+        if world > 1:
+            dist.reduce(film, 0)
+            dist.reduce(counts, 0)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- per-ray algorithmic bytes from a counters build of the same kernels (untimed) ----
+    rc_cfg = dict(mode)
+    rc_cfg["flags"] = rc_cfg["flags"] | R.FLAG_COUNTERS
+    if rank == 0:
+        rc = R.Renderer(device=local, **rc_cfg).render_setup(sc)
+        rc.render_cuda(1)
+        st = rc.stats()
+        rays_all = st["rays_extension"] + st["rays_shadow_env"] + st["rays_shadow_light"]
+        nodes_per_ray = st["nodes_visited"] / max(1, rays_all)
+        tris_per_ray = st["tris_tested"] / max(1, rays_all)
+        rc.close()
+    else:
+        nodes_per_ray = tris_per_ray = 0.0
+
+    for _ in range(args.warmup):
+        r.reset()
+        step()
+    barrier()
+    # ---- timed: value -------------------------------------------------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    r.reset()
+    launches0 = r.stats()["kernel_launches"]
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    barrier()
+    dt = time.perf_counter() - t0
+    st = r.stats()
+    # ---- timed: stage breakdown for the roofline (separate pass so that the events do not perturb `value`) ------
+    tk_cfg = dict(mode)
+    tk_cfg["flags"] = tk_cfg["flags"] | R.FLAG_TIME_KERNELS
+    stage = None
+    if rank == 0:
+        rt = R.Renderer(device=local, **tk_cfg).render_setup(sc)
+        rt.render_cuda(2)
+        rt.reset()
+        rt.render_cuda(S_)
+        stage = rt.stats()
+        rt.close()
+    # ---- timed: e2e ---------------------------------------------------------------------------------------
+    host_film = np.empty((H, W, 4), np.float32)
+    r.reset()
+    barrier()
+    t1 = time.perf_counter()
+    for k in range(args.steps):
+        r.set_camera(sc.camera)                                     # H2D: 56 bytes
+        step()
+        if rank == 0:
+            r._ck(r.L.eleven_get_film(r.h, R.PASS_BEAUTY, host_film.ctypes.data, W * H))   # resolve + D2H of the result
+    barrier()
+    dt_e2e = time.perf_counter() - t1
+    clocks = sampler.stop() if rank == 0 else None
+
+    if world > 1:
+        t = torch.tensor([dt, dt_e2e], device="cuda:%d" % local, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt, dt_e2e = float(t[0]), float(t[1])
+        rays = torch.tensor([st["rays_extension"], st["rays_shadow_env"], st["rays_shadow_light"]], device="cuda:%d" % local, dtype=torch.float64)
+        dist.all_reduce(rays)
+        rays_total = float(rays.sum())
+    else:
+        rays_total = float(st["rays_extension"] + st["rays_shadow_env"] + st["rays_shadow_light"])
+
+    if rank == 0:
+        total = float(W) * H * S_ * args.steps * world
+        value = total / dt
+        peak, peak_src = load_peaks()
+        bytes_per_ray = 80.0 * nodes_per_ray + 48.0 * tris_per_ray + 48.0
+        ext_rays = stage["rays_extension"]
+        ext_s = stage["extend_ms"] * 1e-3
+        achieved = bytes_per_ray * ext_rays / ext_s / 1e9 if ext_s > 0 else 0.0
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("k_extend_dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        out = {
+            "metric": "samples_per_second", "value": value, "unit": "pixel-samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "ClockCC0 stand-in (125281 tris, 12x%d^2 8-bit maps, 4096x2048 HDRI, defocus) %dx%d, %d spp/step/GPU, mode=%s" % (args.tex, W, H, S_, args.mode),
+                       "spp_per_step": S_, "parallelism": "sample-split x%d, scene replicated, 1 NCCL reduce of film sums per step" % world,
+                       "l2": "inputs larger than L2 (textures 805 MB + HDRI 134 MB + 0.7 GB wave state vs 126 MB L2); no flush needed"},
+            "mrays_per_s": rays_total / dt / 1e6,
+            "frame_spp_per_s": S_ * args.steps * world / dt,
+            "e2e": {"value": total / dt_e2e, "unit": "pixel-samples/s", "h2d_bytes_per_step": 56, "d2h_bytes_per_step": W * H * 16},
+            "gpu_launches": int(st["kernel_launches"] - launches0),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "kernel": "k_extend (closest hit over BVH8)", "peak_source": peak_src,
+                         "bytes_per_ray": bytes_per_ray, "nodes_per_ray": nodes_per_ray, "tris_per_ray": tris_per_ray,
+                         "launch_ms": stage["extend_ms"] / max(1, stage["extend_launches"]), "launches": int(stage["extend_launches"]),
+                         "share_of_step": stage["extend_ms"] / stage["render_ms"] if stage["render_ms"] else None,
+                         "stage_ms": {k: stage[k] for k in ("extend_ms", "shade_ms", "connect_ms", "other_ms", "render_ms")},
+                         "note": "BVH8 + triangles of this scene (~8 MB) are L2-resident: the HBM roof is a loose upper bound for this kernel; issue-slot and latency numbers are in profiles/"},
+            "setup": {"scene_upload_s": setup_s, "bvh_build_ms": st["bvh_build_ms"], "bvh_nodes": st["bvh_nodes"], "key_slack": st["key_slack"]},
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            out["cpu_baseline"] = cpu_baseline(args, flat)
+        print(json.dumps(out))
+    r.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -63,6 +63,7 @@ typedef struct ElevenConfig {
 
 #define ELEVEN_FLAG_TERMINATE_DEAD_PATHS 1u  /* stop paths whose throughput is exactly 0 (only legal with RNG_FAST) */
 #define ELEVEN_FLAG_COUNTERS             2u  /* count nodes/triangles visited per ray (slower; for the roofline)    */
+#define ELEVEN_FLAG_TIME_KERNELS         4u  /* CUDA-event timing around every pipeline stage (ElevenStats *_ms)   */
 
 /* ---- scene description (what renderSetup copies out of Scene, S/kernel.cu:566-661) ---- */
 
@@ -146,7 +147,12 @@ typedef struct ElevenStats {
     uint64_t tris_tested;        /* triangles intersected (only with ELEVEN_FLAG_COUNTERS)   */
     uint64_t kernel_launches;    /* CUDA kernels launched by eleven_render so far            */
     double   render_ms;          /* device time inside eleven_render (CUDA events)           */
-    double   trace_ms;           /* device time of the traversal kernels only                */
+    double   trace_ms;           /* device time of eleven_trace_* batches                    */
+    double   extend_ms;          /* with ELEVEN_FLAG_TIME_KERNELS: closest-hit kernels       */
+    double   shade_ms;           /*   "   : shade kernels                                    */
+    double   connect_ms;         /*   "   : shadow-ray + MIS kernels                         */
+    double   other_ms;           /*   "   : raygen, queue bookkeeping, accumulate            */
+    uint64_t extend_launches;    /* closest-hit kernel launches inside eleven_render         */
     double   bvh_build_ms;       /* host wall time of the BVH8 build                         */
     uint32_t bvh_nodes;          /* BVH8 node count                                          */
     uint32_t bvh_tri_slots;      /* triangle slots in leaf order                             */
@@ -179,6 +185,10 @@ int  eleven_get_film(ElevenCtx* ctx, int pass, float* rgba, size_t n_pixels);
 int  eleven_get_pathcount(ElevenCtx* ctx, int32_t* out, size_t n_pixels);   /* dev_pathcount */
 int  eleven_get_samples(ElevenCtx* ctx);                                    /* getSamples, S/kernel.cu:712 */
 int  eleven_get_stats(ElevenCtx* ctx, ElevenStats* out);
+
+/* Replace the camera (same resolution) without touching the scene: 56 bytes host->device.  The reference has no such
+ * call (its camera is baked by renderSetup); it is what an interactive host needs between frames. */
+int  eleven_set_camera(ElevenCtx* ctx, const ElevenCamera* camera);
 
 /* Zero film + counters and re-seed, keeping the uploaded scene (the reference has no such call:
  * it is what re-running renderSetup's setupKernel would do). */

@@ -666,7 +666,14 @@ static V3 hdriLight(Scene& S, const Ray& ray, V3 point, const HitData& hd, float
     Ray shadow = makeRay(point + newDir * 0.001f, newDir);
     S.raysEnv++;
     Hit sh = throwRay(S, shadow);
-    if (sh.valid) { pdf = 0; return v3(0.f); }
+    if (sh.valid) {
+        // UB in the reference: hdriPdf is left uninitialised here (S/kernel.cu:248,344).  Defined as 0 (mode 0).
+        // Modes 1/2 exist only to probe what the compiled reference actually does (tools/, not used by tests).
+        static int ubMode = getenv("ORC_HDRIPDF_UB") ? atoi(getenv("ORC_HDRIPDF_UB")) : 0;
+        if (ubMode == 1) pdf = hdriPdf(S, (int)(iu * t.width), (int)(iv * t.height));
+        else if (ubMode == 0) pdf = 0;                                   // modes 2,3: keep the stale value
+        return v3(0.f);
+    }
     V3 val = t.fromUV(iu, iv);
     V3 brdf = disneyEval(ray, hd, newDir);
     pdf = hdriPdf(S, (int)(iu * t.width), (int)(iv * t.height));
@@ -691,18 +698,23 @@ static V3 pointLight(Scene& S, const Ray& ray, const HitData& hd, V3 point, floa
     V3 brdf = disneyEval(ray, hd, newDir);
     return value * brdf * fabsf(dot(newDir, hd.normal)) / pdf;
 }
+static thread_local bool g_debugPixel = false;
+static thread_local float g_stalePdf = 0;   // probe modes 2/3 only (see hdriLight)
 // S/kernel.cu:339-358
 static void shade(Scene& S, const Ray& ray, const HitData& hd, const Hit& hit, V3 newDir, float r1, V3& hitLight, V3& reduction) {
     V3 brdf = disneyEval(ray, hd, newDir);
     float brdfPdf = disneyPdf(ray, hd, newDir);
-    float hPdf = 0, pPdf = 0;
+    float hPdf = g_stalePdf, pPdf = 0;
     V3 hdriCalc = hdriLight(S, ray, hit.position, hd, r1, hPdf);
+    g_stalePdf = hPdf;
     V3 pointCalc = pointLight(S, ray, hd, hit.position, pPdf, r1);
     V3 brdfCalc = hd.emission * (brdf * fabsf(dot(newDir, hd.normal))) / brdfPdf;
     float w1 = hPdf / (hPdf + pPdf + brdfPdf);
     float w2 = pPdf / (hPdf + pPdf + brdfPdf);
     float w3 = brdfPdf / (hPdf + pPdf + brdfPdf);
     hitLight = reduction * (w1 * hdriCalc + w2 * pointCalc + w3 * brdfCalc);
+    if (g_debugPixel) fprintf(stderr, "  [orc] N=(%g %g %g) L=(%g %g %g) brdf=(%g %g %g) brdfPdf=%g hPdf=%g pPdf=%g hdriCalc=(%g %g %g) pointCalc.x=%g w=(%g %g %g) red=(%g %g %g)\n",
+        hd.normal.x, hd.normal.y, hd.normal.z, newDir.x, newDir.y, newDir.z, brdf.x, brdf.y, brdf.z, brdfPdf, hPdf, pPdf, hdriCalc.x, hdriCalc.y, hdriCalc.z, pointCalc.x, w1, w2, w3, reduction.x, reduction.y, reduction.z);
     reduction = reduction * ((brdf * fabsf(dot(newDir, hd.normal))) / brdfPdf);
 }
 
@@ -713,8 +725,10 @@ static void renderPixelSample(Scene& S, int x, int y, int maxBounces) {
     int idx = (int)(c.xRes * (c.yRes - y - 1) + x);
     Xorwow rs = S.rng[idx];
     uint32_t sa = S.samples[idx];
+    { static int ubMode = getenv("ORC_HDRIPDF_UB") ? atoi(getenv("ORC_HDRIPDF_UB")) : 0; if (ubMode == 3) g_stalePdf = 0; }
     float c1 = xorwowUniform(rs), c2 = xorwowUniform(rs), c3 = xorwowUniform(rs), c4 = xorwowUniform(rs), c5 = xorwowUniform(rs);
     Ray ray = cameraRay(c, x, y, c1, c2, c3, c4, c5);
+    { static const char* dp = getenv("ORC_DEBUG_PIXEL"); int dx = -1, dy = -1; if (dp) sscanf(dp, "%d,%d", &dx, &dy); g_debugPixel = dp && (int)(c.yRes - y - 1) == dy && x == dx; }
     V3 light = v3(0.f), normal = v3(0.f), tangent = v3(0.f), bitangent = v3(0.f), reduction = v3(1.f);
     int i = 0;
     for (i = 0; i < maxBounces; i++) {
@@ -725,6 +739,7 @@ static void renderPixelSample(Scene& S, int x, int y, int maxBounces) {
             light = light + S.hdri.filtered(u, v) * reduction;
             break;
         }
+        if (g_debugPixel) fprintf(stderr, "[orc] bounce %d tri %d t=%g pos=(%g %g %g) dir=(%g %g %g)\n", i, hit.tri, hit.t, hit.position.x, hit.position.y, hit.position.z, ray.d.x, ray.d.y, ray.d.z);
         const ElevenMaterial& m = S.mats[S.objMat[hit.objectID]];
         HitData hd; generateHitData(S, m, hd, hit);
         float b1 = xorwowUniform(rs), b2 = xorwowUniform(rs), b3 = xorwowUniform(rs);

@@ -8,7 +8,7 @@
  * applied by sed to a temporary copy at build time, see the Makefile — nothing is copied into
  * the repo).  Output: oracle/_ref/eleven_ref_headless_{precise,fast} (git-ignored binaries).
  *
- * usage: eleven_ref_headless <scene_dir> <spp> <out_prefix> [--dump-scene file] [--external-textures]
+ * usage: eleven_ref_headless <scene_dir> <spp> <out_prefix> [--dump-scene file] [--external-textures] [--warmup spp]
  *   <out_prefix>.beauty.f32 / .normal.f32 / .tangent.f32 / .bitangent.f32  (W*H*4 floats each)
  *   <out_prefix>.pathcount.i32, <out_prefix>.json (timings, counters)
  */
@@ -88,9 +88,10 @@ static void dumpScene(Scene& s, const char* path, bool externalTextures) {
 int main(int argc, char** argv) {
     if (argc < 4) { fprintf(stderr, "usage: %s <scene_dir> <spp> <out_prefix> [--dump-scene file] [--external-textures]\n", argv[0]); return 1; }
     std::string dir = argv[1]; int spp = atoi(argv[2]); std::string out = argv[3];
-    const char* dump = 0; bool ext = false;
+    const char* dump = 0; bool ext = false; int warm = 0;
     for (int i = 4; i < argc; i++) {
         if (!strcmp(argv[i], "--dump-scene") && i + 1 < argc) dump = argv[++i];
+        else if (!strcmp(argv[i], "--warmup") && i + 1 < argc) warm = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--external-textures")) ext = true;
     }
     int ndev = 0;
@@ -107,6 +108,8 @@ int main(int argc, char** argv) {
     cudaError_t e = renderSetup(&scene);
     double t3 = nowMs();
     if (e != cudaSuccess) { fprintf(stderr, "renderSetup: %s\n", cudaGetErrorString(e)); return 5; }
+    const double setupMs = t3 - t2;
+    if (warm > 0) { renderCuda(&scene, warm); cudaDeviceSynchronize(); t3 = nowMs(); }     // untimed warm-up samples
     renderCuda(&scene, spp);
     e = cudaDeviceSynchronize();
     double t4 = nowMs();
@@ -129,7 +132,7 @@ int main(int argc, char** argv) {
     snprintf(js, sizeof js,
         "{\"impl\": \"reference-cuda\", \"width\": %d, \"height\": %d, \"spp\": %d, \"tris\": %d, \"load_ms\": %.3f, "
         "\"setup_ms\": %.3f, \"render_ms\": %.3f, \"samples_per_s\": %.1f, \"hit_bounces\": %lld, \"kpaths_per_s\": %.3f, \"samples_pixel0\": %d}\n",
-        W, H, spp, (int)scene.tris.size(), t1 - t0, t3 - t2, renderMs, (double)W * H * spp / (renderMs * 1e-3), paths, paths / renderMs, samples);
+        W, H, spp, (int)scene.tris.size(), t1 - t0, setupMs, renderMs, (double)W * H * spp / (renderMs * 1e-3), paths, paths / renderMs, samples);
     fputs(js, stdout);
     writeRaw(out + ".json", js, strlen(js));
     return 0;

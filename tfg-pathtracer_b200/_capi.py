@@ -20,7 +20,7 @@ PASS_BEAUTY, PASS_DENOISE, PASS_NORMAL, PASS_TANGENT, PASS_BITANGENT = range(5)
 RNG_REFERENCE, RNG_FAST = 0, 1
 ENV_CDF, ENV_ALIAS = 0, 1
 HIT_KEY, HIT_MIN_T = 0, 1
-FLAG_TERMINATE_DEAD_PATHS, FLAG_COUNTERS = 1, 2
+FLAG_TERMINATE_DEAD_PATHS, FLAG_COUNTERS, FLAG_TIME_KERNELS = 1, 2, 4
 
 
 class ElevenConfig(C.Structure):
@@ -62,7 +62,8 @@ class ElevenStats(C.Structure):
     _fields_ = [("pixel_samples", C.c_uint64), ("rays_extension", C.c_uint64), ("rays_shadow_env", C.c_uint64),
                 ("rays_shadow_light", C.c_uint64), ("hit_bounces", C.c_uint64), ("nodes_visited", C.c_uint64),
                 ("tris_tested", C.c_uint64), ("kernel_launches", C.c_uint64), ("render_ms", C.c_double),
-                ("trace_ms", C.c_double), ("bvh_build_ms", C.c_double), ("bvh_nodes", C.c_uint32),
+                ("trace_ms", C.c_double), ("extend_ms", C.c_double), ("shade_ms", C.c_double), ("connect_ms", C.c_double),
+                ("other_ms", C.c_double), ("extend_launches", C.c_uint64), ("bvh_build_ms", C.c_double), ("bvh_nodes", C.c_uint32),
                 ("bvh_tri_slots", C.c_uint32), ("key_slack", C.c_float), ("samples_done", C.c_uint32)]
 
     def as_dict(self):
@@ -128,6 +129,7 @@ def load_library(path: str = LIB_PATH):
     L.eleven_get_samples.argtypes = [vp]
     L.eleven_get_stats.argtypes = [vp, C.POINTER(ElevenStats)]
     L.eleven_film_reset.argtypes = [vp]
+    L.eleven_set_camera.argtypes = [vp, C.POINTER(ElevenCamera)]
     L.eleven_trace_closest.argtypes = [vp, vp, sz, vp]
     L.eleven_trace_device.argtypes = [vp, vp, sz, vp, C.c_int, C.POINTER(C.c_float)]
     L.eleven_film_sums_device.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(sz)]
@@ -146,7 +148,7 @@ def load_library(path: str = LIB_PATH):
 EXPORTED_SYMBOLS = [
     "eleven_abi_version", "eleven_last_error", "eleven_init", "eleven_destroy", "eleven_scene_upload",
     "eleven_render", "eleven_get_film", "eleven_get_pathcount", "eleven_get_samples", "eleven_get_stats",
-    "eleven_film_reset", "eleven_trace_closest", "eleven_trace_device", "eleven_film_sums_device",
+    "eleven_film_reset", "eleven_set_camera", "eleven_trace_closest", "eleven_trace_device", "eleven_film_sums_device",
     "eleven_film_counts_device", "eleven_device_alloc", "eleven_device_free", "eleven_device_upload",
     "eleven_device_download", "eleven_resolve_rgba8",
 ]

@@ -48,6 +48,8 @@ struct ElevenCtx {
     uint32_t* d_seqMat = nullptr;
     float4* d_resolve = nullptr;
     uint32_t* d_workCounter = nullptr;
+    ElevenCamera* d_camera = nullptr;
+    std::vector<cudaEvent_t> evPool;
     ElevenStats stats;
 };
 
@@ -100,6 +102,7 @@ extern "C" void eleven_destroy(ElevenCtx* c) {
     freeAll(c->sceneAllocs); freeAll(c->waveAllocs);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    for (cudaEvent_t e : c->evPool) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -196,8 +199,11 @@ static int resetFilm(ElevenCtx* c) {
     CK(cudaStreamSynchronize(c->stream));
     c->samplesRendered = 0;
     c->stats.render_ms = 0; c->stats.trace_ms = 0; c->stats.kernel_launches = 0; c->stats.pixel_samples = 0;
+    c->stats.extend_ms = c->stats.shade_ms = c->stats.connect_ms = c->stats.other_ms = 0; c->stats.extend_launches = 0;
     return ELEVEN_OK;
 }
+
+static void setCameraParams(ElevenCtx* c, const ElevenCamera& cam);
 
 extern "C" int eleven_scene_upload(ElevenCtx* c, const ElevenSceneDesc* d) {
     if (!c || !d) return fail(ELEVEN_ERR_ARG, "eleven_scene_upload: null argument");
@@ -207,7 +213,7 @@ extern "C" int eleven_scene_upload(ElevenCtx* c, const ElevenSceneDesc* d) {
     if (d->objectCount == 0 || !d->objectMaterial) return fail(ELEVEN_ERR_ARG, "objectMaterial is required");
     CK(cudaSetDevice(c->cfg.device));
     freeAll(c->sceneAllocs);
-    c->d_seqMat = nullptr;
+    c->d_seqMat = nullptr; c->d_camera = nullptr;
     c->haveScene = false;
     DevScene& S = c->scene; memset(&S, 0, sizeof S);
     int rc;
@@ -306,13 +312,31 @@ extern "C" int eleven_scene_upload(ElevenCtx* c, const ElevenSceneDesc* d) {
     RenderParams& P = c->P; memset(&P, 0, sizeof P);
     P.rngMode = c->cfg.rng_mode; P.envMode = c->cfg.env_mode; P.hitMode = c->cfg.hit_mode; P.maxBounces = c->cfg.max_bounces; P.flags = c->cfg.flags;
     P.seedLo = (uint32_t)c->cfg.seed; P.seedHi = (uint32_t)(c->cfg.seed >> 32);
-    {   // rotation *= PI/180.0 in float, then sin/cos (S/kernel.cu:299-306)
-        const float k = (float)((double)EL_PI / 180.0);
-        const float rx = d->camera.rotation[0] * k, ry = d->camera.rotation[1] * k, rz = d->camera.rotation[2] * k;
-        P.rot.sx = sinf(rx); P.rot.cx = cosf(rx); P.rot.sy = sinf(ry); P.rot.cy = cosf(ry); P.rot.sz = sinf(rz); P.rot.cz = cosf(rz);
-    }
+    setCameraParams(c, d->camera);
+    { const ElevenCamera* dc = nullptr; if ((rc = devUpload(c->sceneAllocs, &dc, &d->camera, 1))) return rc; c->d_camera = (ElevenCamera*)dc; }
     c->haveScene = true;
     return resetFilm(c);
+}
+
+static void setCameraParams(ElevenCtx* c, const ElevenCamera& cam) {
+    memcpy(&c->scene.cam, &cam, sizeof(DevCamera));
+    // rotation *= PI/180.0 in float, then sin/cos (S/kernel.cu:299-306)
+    const float k = (float)((double)EL_PI / 180.0);
+    const float rx = cam.rotation[0] * k, ry = cam.rotation[1] * k, rz = cam.rotation[2] * k;
+    RenderParams& P = c->P;
+    P.rot.sx = sinf(rx); P.rot.cx = cosf(rx); P.rot.sy = sinf(ry); P.rot.cy = cosf(ry); P.rot.sz = sinf(rz); P.rot.cz = cosf(rz);
+}
+
+extern "C" int eleven_set_camera(ElevenCtx* c, const ElevenCamera* cam) {
+    if (!c || !cam) return fail(ELEVEN_ERR_ARG, "eleven_set_camera: null argument");
+    if (!c->haveScene) return fail(ELEVEN_ERR_STATE, "eleven_set_camera: no scene uploaded");
+    if (cam->xRes != c->width || cam->yRes != c->height) return fail(ELEVEN_ERR_ARG, "eleven_set_camera: resolution change needs eleven_scene_upload");
+    CK(cudaSetDevice(c->cfg.device));
+    setCameraParams(c, *cam);
+    // the camera travels to the device as a kernel argument (__grid_constant__); mirror it in device memory too so that
+    // the copy is observable (and so that later device-side consumers can read it)
+    CK(cudaMemcpyAsync(c->d_camera, cam, sizeof(ElevenCamera), cudaMemcpyHostToDevice, c->stream));
+    return ELEVEN_OK;
 }
 
 extern "C" int eleven_film_reset(ElevenCtx* c) {
@@ -341,19 +365,38 @@ extern "C" int eleven_render(ElevenCtx* c, int spp) {
     const int gridPix = (int)((n + 255) / 256);
     const int gridPersist = c->numSMs * 8;             // 148 SMs x 8 CTAs of 128 threads: a multiple of the SM count
     const bool count = (c->cfg.flags & ELEVEN_FLAG_COUNTERS) != 0;
+    const bool timeK = (c->cfg.flags & ELEVEN_FLAG_TIME_KERNELS) != 0;
+    // stage timing: one event after every stage launch; stage i spans events [i, i+1)
+    std::vector<int> evKind;                      // 0 extend, 1 shade, 2 connect, 3 other
+    size_t evUsed = 0;
+    auto mark = [&](int kind) {
+        if (!timeK) return;
+        if (evUsed == c->evPool.size()) { cudaEvent_t e; cudaEventCreate(&e); c->evPool.push_back(e); }
+        cudaEventRecord(c->evPool[evUsed++], c->stream); evKind.push_back(kind);
+    };
     CK(cudaEventRecord(c->ev0, c->stream));
+    mark(3);
     for (int s = 0; s < spp; s++) {
         c->P.sampleIndex = c->cfg.sample_offset + c->samplesRendered * c->cfg.sample_stride;
         k_raygen<<<gridPix, 256, 0, c->stream>>>(c->W, c->scene, c->P);
+        mark(3);
         for (uint32_t b = 0; b < c->cfg.max_bounces; b++) {
             if (count) launchExtend<true>(c, gridPersist); else launchExtend<false>(c, gridPersist);
+            mark(0);
             k_shade<<<gridPersist, 128, 0, c->stream>>>(c->W, c->scene, c->P);
+            mark(1);
             k_advance<<<1, 32, 0, c->stream>>>(c->W, c->scene.lightCount, 0);
+            mark(3);
             if (count) launchConnect<true>(c, gridPersist); else launchConnect<false>(c, gridPersist);
+            mark(2);
             k_advance<<<1, 32, 0, c->stream>>>(c->W, c->scene.lightCount, 1);
+            mark(3);
+            c->stats.extend_launches += 1;
+            std::swap(c->W.qCur, c->W.qNext);      // kernel arguments are captured at launch: the next bounce reads the list just written
             c->stats.kernel_launches += 5;
         }
         k_accumulate<<<gridPix, 256, 0, c->stream>>>(c->W);
+        mark(3);
         c->stats.kernel_launches += 2;
         c->samplesRendered++;
     }
@@ -362,6 +405,11 @@ extern "C" int eleven_render(ElevenCtx* c, int spp) {
     CK(cudaStreamSynchronize(c->stream));
     float ms = 0; CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
     c->stats.render_ms += ms;
+    for (size_t i = 1; i < evUsed; i++) {
+        float t = 0; CK(cudaEventElapsedTime(&t, c->evPool[i - 1], c->evPool[i]));
+        double* dst[4] = {&c->stats.extend_ms, &c->stats.shade_ms, &c->stats.connect_ms, &c->stats.other_ms};
+        *dst[evKind[i]] += t;
+    }
     c->stats.pixel_samples += (uint64_t)n * (uint64_t)spp;
     return ELEVEN_OK;
 }

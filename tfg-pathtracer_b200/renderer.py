@@ -18,7 +18,7 @@ import numpy as np
 
 from . import _capi
 from . import scenes as S
-from ._capi import (ENV_ALIAS, ENV_CDF, FLAG_COUNTERS, FLAG_TERMINATE_DEAD_PATHS, HIT_KEY, HIT_MIN_T,  # noqa: F401
+from ._capi import (ENV_ALIAS, ENV_CDF, FLAG_COUNTERS, FLAG_TERMINATE_DEAD_PATHS, FLAG_TIME_KERNELS, HIT_KEY, HIT_MIN_T,  # noqa: F401
                     PASS_BEAUTY, PASS_BITANGENT, PASS_NORMAL, PASS_TANGENT, RNG_FAST, RNG_REFERENCE)
 
 
@@ -87,6 +87,11 @@ class Renderer:
     # --- extras ---------------------------------------------------------------------------------------
     def film(self, p=PASS_BEAUTY):
         return self.get_buffers((p,))[0][p]
+
+    def set_camera(self, camera):
+        cam = _capi.ElevenCamera()
+        C.memmove(C.byref(cam), np.asarray(camera).tobytes(), C.sizeof(cam))
+        self._ck(self.L.eleven_set_camera(self.h, C.byref(cam)))
 
     def reset(self):
         self._ck(self.L.eleven_film_reset(self.h))

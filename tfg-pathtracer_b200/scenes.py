@@ -439,7 +439,7 @@ def material_maps(res, seed, tint):
 # ------------------------------------------------------------------------------------------------
 # scene generators
 # ------------------------------------------------------------------------------------------------
-def cornell_box(res=1024, env=(0.01, 0.01, 0.01), light=True, env_size=(1024, 1024)):
+def cornell_box(res=1024, env=(0.01, 0.01, 0.01), light=True, env_size=(1024, 1024), tilt=None):
     """Config 2: 5 walls + short box + tall box, Kd-only materials
     (roughness 1, metallic 0 => diffuse Disney), point light (10,10,10) under the ceiling."""
     parts = []
@@ -459,11 +459,29 @@ def cornell_box(res=1024, env=(0.01, 0.01, 0.01), light=True, env_size=(1024, 10
     rot_box((0.15, 0.0, -0.65), (0.75, 0.6, -0.05), 0.3, 3)      # short box
     rot_box((-0.75, 0.0, 0.0), (-0.15, 1.2, 0.6), -0.35, 4)      # tall box
     tris = np.concatenate(parts)
+    light_pos = np.array([0.0, 1.8, 0.0])
+    if tilt is not None:
+        # Rigidly rotate the whole box about its centre so that nothing is axis-aligned.  The reference's slab test
+        # turns 0*inf into NaN for rays lying exactly in an axis-aligned box face (S/BVH.hpp:75-99) and
+        # then MISSES geometry; an axis-aligned Cornell box under an equirect environment provokes this constantly
+        # (pole/equator texels give exactly vertical/horizontal shadow rays along walls/floor).  The parity scenes use
+        # the tilted box; the axis-aligned one remains the benchmark scene.
+        ax, ay, az = np.deg2rad(tilt)
+        Rx = np.array([[1, 0, 0], [0, np.cos(ax), -np.sin(ax)], [0, np.sin(ax), np.cos(ax)]])
+        Ry = np.array([[np.cos(ay), 0, np.sin(ay)], [0, 1, 0], [-np.sin(ay), 0, np.cos(ay)]])
+        Rz = np.array([[np.cos(az), -np.sin(az), 0], [np.sin(az), np.cos(az), 0], [0, 0, 1]])
+        Rm = Rz @ Ry @ Rx
+        c0 = np.array([0.0, 1.0, 0.0])
+        rot = lambda a: ((a.astype(np.float64) - c0) @ Rm.T + c0).astype(np.float32)
+        tris["vertices"] = rot(tris["vertices"].reshape(-1, 3)).reshape(-1, 3, 3)
+        tris["normals"] = (tris["normals"].reshape(-1, 3).astype(np.float64) @ Rm.T).astype(np.float32).reshape(-1, 3, 3)
+        tris["tangents"] = (tris["tangents"].reshape(-1, 3).astype(np.float64) @ Rm.T).astype(np.float32).reshape(-1, 3, 3)
+        light_pos = (light_pos - c0) @ Rm.T + c0
     mats = np.stack([default_material(albedo=(0.73, 0.73, 0.73)), default_material(albedo=(0.65, 0.05, 0.05)),
                      default_material(albedo=(0.12, 0.45, 0.15))])
     lights = np.zeros(1 if light else 0, LIGHT_DT)
     if light:
-        lights[0]["position"] = (0.0, 1.8, 0.0)
+        lights[0]["position"] = light_pos
         lights[0]["radiance"] = (10.0, 10.0, 10.0)
     cam = make_camera(res, res, position=(0.0, 1.0, -3.6), focal_length=0.035)
     return SceneData(cam, tris, np.array([0, 1, 2, 0, 0], np.int32), mats, [], constant_env(env, env_size), lights,
