@@ -164,13 +164,6 @@ def run_reference(args, rank):
 
 
 # ------------------------------------------------------------------------------------------------------
-class DevArray:
-    """Zero-copy view of a device buffer owned by the C-ABI context, for torch.distributed (plumbing only)."""
-
-    def __init__(self, ptr, n, typestr):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
-
-
 def cpu_baseline(args, flat):
     import oracle_lib as O
     from tfg_pathtracer_b200 import scenes as S
@@ -217,7 +210,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from tfg_pathtracer_b200 import renderer as R, scenes as S
+    from tfg_pathtracer_b200 import dist as D, renderer as R, scenes as S
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the product path)")
@@ -230,17 +223,15 @@ def main():
     W, H = sc.width, sc.height
     mode = dict(R.FAST if args.mode == "fast" else R.PARITY)
     t0 = time.time()
-    r = R.Renderer(device=local, sample_offset=rank, sample_stride=world, **mode).render_setup(sc)
+    off, stride, _ = D.sample_plan(args.spp_per_step * world, rank, world)
+    r = R.Renderer(device=local, sample_offset=off, sample_stride=stride, **mode).render_setup(sc)
     setup_s = time.time() - t0
-    film = torch.as_tensor(DevArray(*r.film_sums_ptr(R.PASS_BEAUTY), "<f4"), device="cuda:%d" % local)
-    counts = torch.as_tensor(DevArray(*r.film_counts_ptr(), "<i4"), device="cuda:%d" % local)
+    film, counts = D.film_tensors(r, "cuda:%d" % local)
     S_ = args.spp_per_step
 
     def step():
         r.render_cuda(S_)
-        if world > 1:
-            dist.reduce(film, 0)
-            dist.reduce(counts, 0)
+        D.reduce_film(film, counts, 0)
 
     def barrier():
         torch.cuda.synchronize()

@@ -184,6 +184,9 @@ int  eleven_render(ElevenCtx* ctx, int spp);
 int  eleven_get_film(ElevenCtx* ctx, int pass, float* rgba, size_t n_pixels);
 int  eleven_get_pathcount(ElevenCtx* ctx, int32_t* out, size_t n_pixels);   /* dev_pathcount */
 int  eleven_get_samples(ElevenCtx* ctx);                                    /* getSamples, S/kernel.cu:712 */
+/* dev_samples (S/kernel.cu:44): per-pixel count of accepted samples; NaN samples are dropped without counting
+ * (S/kernel.cu:449,477), so pixels can lag the number of samples rendered. */
+int  eleven_get_sample_counts(ElevenCtx* ctx, uint32_t* out, size_t n_pixels);
 int  eleven_get_stats(ElevenCtx* ctx, ElevenStats* out);
 
 /* Replace the camera (same resolution) without touching the scene: 56 bytes host->device.  The reference has no such

@@ -52,7 +52,8 @@ def sha(a):
 def golden_scenes():
     """The parity scenes: small enough for the CPU suite, covering big flat triangles (cornell), smooth small
     triangles + textures + defocus (clock stand-in), a regular height field (grid) and tiling/offset env."""
-    c = S.cornell_box(96, env_size=(66, 33), tilt=(3.0, 7.0, 2.0))     # tilted: see scenes.cornell_box
+    # tilted + boxes lifted 2 mm off the floor: no NaN slab misses, no coplanar equal-key ties (see scenes.cornell_box)
+    c = S.cornell_box(96, env_size=(66, 33), tilt=(3.0, 7.0, 2.0), box_gap=0.002)
     k = S.clock_standin(tex_res=32, xres=160, yres=90, env_size=(128, 64))
     k.hdri.xOffset = 0.25
     g = S.displaced_grid(64, xres=96, yres=54, env_size=(64, 32))

@@ -1,0 +1,61 @@
+"""Image-level pin against the UNMODIFIED reference renderer run on a B200.
+
+tests/golden/ref_cuda_<scene>.npz were produced on the GPU box by tools/ref_compare.py --save, which runs
+oracle/_ref/eleven_ref_headless_precise (the reference's own loader + BVH builder + kernel.cu, nvcc --fmad=false) on a
+scene directory written by scenes.write_reference_scene_dir, and stores (a) the raw float BEAUTY film it rendered and (b)
+the scene exactly as the reference's loader produced it (flat dump: MikkTSpace tangents, stb texel decode).
+Only scenes without point lights/emission are pinned this way: with them the reference reads an uninitialised
+hdriPdf (S/kernel.cu:344,248 — undefined behaviour).
+The AOV passes are not compared at these resolutions: the reference's getBuffers reads pass i at offset W*H*16*i of a
+[5][1920*1080*4] array (S/kernel.cu:697), which is only correct at 1920x1080.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from tfg_pathtracer_b200 import scenes as S
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+ABS_TOL, REL_TOL = 1e-3, 1e-3
+
+
+def load_case(name, tmp_path):
+    g = np.load(os.path.join(G, "ref_cuda_%s.npz" % name))
+    p = str(tmp_path / (name + ".flat"))
+    with open(p, "wb") as f:
+        f.write(g["scene_flat"].tobytes())
+    return g, S.load_flat(p)
+
+
+def within(a, b):
+    return float((np.abs(a - b) <= ABS_TOL + REL_TOL * np.abs(b)).all(-1).mean())
+
+
+@pytest.mark.parametrize("name", ["cornell_nolight", "clock"])
+def test_oracle_image_matches_reference_cuda_build(name, tmp_path):
+    g, sc = load_case(name, tmp_path)
+    orc = O.Oracle(sc)
+    orc.render(int(g["spp"]), threads=os.cpu_count() or 4)
+    img = orc.film(0)
+    assert within(img[..., :3], g["beauty"][..., :3]) >= 0.995
+    pc = orc.counts()[1].astype(np.int32)
+    assert (pc == g["pathcount"]).mean() >= 0.995
+    assert abs(img[..., :3].mean() - g["beauty"][..., :3].mean()) <= 2e-3 * g["beauty"][..., :3].mean()
+    orc.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["cornell_nolight", "clock"])
+def test_cuda_path_matches_reference_cuda_build(name, tmp_path):
+    from tfg_pathtracer_b200 import renderer as R
+    g, sc = load_case(name, tmp_path)
+    r = R.Renderer(**R.PARITY).render_setup(sc)
+    r.render_cuda(int(g["spp"]))
+    bufs, pc = r.get_buffers((R.PASS_BEAUTY,))
+    # the axis-aligned Cornell box provokes the reference's NaN slab misses: looser pixel fraction there
+    frac = 0.97 if name == "cornell_nolight" else 0.995
+    assert within(bufs[R.PASS_BEAUTY][..., :3], g["beauty"][..., :3]) >= frac
+    assert (pc == g["pathcount"]).mean() >= frac
+    r.close()

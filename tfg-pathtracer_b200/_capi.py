@@ -127,6 +127,7 @@ def load_library(path: str = LIB_PATH):
     L.eleven_get_film.argtypes = [vp, C.c_int, vp, sz]
     L.eleven_get_pathcount.argtypes = [vp, vp, sz]
     L.eleven_get_samples.argtypes = [vp]
+    L.eleven_get_sample_counts.argtypes = [vp, vp, sz]
     L.eleven_get_stats.argtypes = [vp, C.POINTER(ElevenStats)]
     L.eleven_film_reset.argtypes = [vp]
     L.eleven_set_camera.argtypes = [vp, C.POINTER(ElevenCamera)]
@@ -147,7 +148,7 @@ def load_library(path: str = LIB_PATH):
 
 EXPORTED_SYMBOLS = [
     "eleven_abi_version", "eleven_last_error", "eleven_init", "eleven_destroy", "eleven_scene_upload",
-    "eleven_render", "eleven_get_film", "eleven_get_pathcount", "eleven_get_samples", "eleven_get_stats",
+    "eleven_render", "eleven_get_film", "eleven_get_pathcount", "eleven_get_samples", "eleven_get_sample_counts", "eleven_get_stats",
     "eleven_film_reset", "eleven_set_camera", "eleven_trace_closest", "eleven_trace_device", "eleven_film_sums_device",
     "eleven_film_counts_device", "eleven_device_alloc", "eleven_device_free", "eleven_device_upload",
     "eleven_device_download", "eleven_resolve_rgba8",

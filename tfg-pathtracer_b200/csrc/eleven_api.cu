@@ -462,6 +462,16 @@ extern "C" int eleven_get_pathcount(ElevenCtx* c, int32_t* out, size_t nPixels) 
     return ELEVEN_OK;
 }
 
+extern "C" int eleven_get_sample_counts(ElevenCtx* c, uint32_t* out, size_t nPixels) {
+    if (!c || !out) return fail(ELEVEN_ERR_ARG, "eleven_get_sample_counts: null argument");
+    if (!c->haveScene) return fail(ELEVEN_ERR_STATE, "eleven_get_sample_counts: no scene uploaded");
+    if (nPixels != c->nPixels) return fail(ELEVEN_ERR_ARG, "eleven_get_sample_counts: n_pixels must be W*H");
+    CK(cudaSetDevice(c->cfg.device));
+    CK(cudaMemcpyAsync(out, c->W.filmCount, (size_t)c->nPixels * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return ELEVEN_OK;
+}
+
 extern "C" int eleven_get_samples(ElevenCtx* c) {
     if (!c || !c->haveScene) return fail(ELEVEN_ERR_STATE, "eleven_get_samples: no scene uploaded");
     uint32_t v = 0;

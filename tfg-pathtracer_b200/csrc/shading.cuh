@@ -113,12 +113,12 @@ __device__ __forceinline__ float hdriPdf(const DevScene& S, int x, int y) {
 // ---- sampling: S/Sampling.hpp:21-54 ------------------------------------------------------------------
 __device__ __forceinline__ void uniformCircleSampling(float u1, float u2, float u3, float& x, float& y) {
     const float t = 2 * EL_PI * u1, u = u2 + u3, r = u > 1 ? 2 - u : u;
-    float s, c; sincosf(t, &s, &c);
+    const float s = sinf(t), c = cosf(t);        /* separate calls like the reference (S/Sampling.hpp:27-28) */
     x = r * c; y = r * s;
 }
 __device__ __forceinline__ F3 cosineSampleHemisphere(float u1, float u2) {
     const float r = sqrtf(u1), phi = (float)(2.0 * (double)EL_PI * (double)u2);
-    float s, c; sincosf(phi, &s, &c);
+    const float s = sinf(phi), c = cosf(phi);
     F3 d; d.x = r * c; d.y = r * s;
     d.z = sqrtf(maxf_(0.0f, (float)(1.0 - (double)(d.x * d.x) - (double)(d.y * d.y))));
     return d;
@@ -128,7 +128,7 @@ __device__ __forceinline__ F3 importanceSampleGGX(float rgh, float r1, float r2)
     const float phi = r1 * EL_PI * 2;
     const float cosTheta = (float)sqrt((1.0 - (double)r2) / (1.0 + ((double)(a * a) - 1.0) * (double)r2));
     const float sinTheta = clampf_((float)sqrt(1.0 - (double)(cosTheta * cosTheta)), 0.0f, 1.0f);
-    float sp, cp; sincosf(phi, &sp, &cp);
+    const float sp = sinf(phi), cp = cosf(phi);
     return f3(sinTheta * cp, sinTheta * sp, cosTheta);
 }
 

@@ -84,6 +84,11 @@ class Renderer:
             self._ck(v)
         return v
 
+    def get_sample_counts(self):
+        c = np.empty(self.W * self.H, np.uint32)
+        self._ck(self.L.eleven_get_sample_counts(self.h, c.ctypes.data, self.W * self.H))
+        return c
+
     # --- extras ---------------------------------------------------------------------------------------
     def film(self, p=PASS_BEAUTY):
         return self.get_buffers((p,))[0][p]

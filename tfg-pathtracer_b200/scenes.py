@@ -439,7 +439,7 @@ def material_maps(res, seed, tint):
 # ------------------------------------------------------------------------------------------------
 # scene generators
 # ------------------------------------------------------------------------------------------------
-def cornell_box(res=1024, env=(0.01, 0.01, 0.01), light=True, env_size=(1024, 1024), tilt=None):
+def cornell_box(res=1024, env=(0.01, 0.01, 0.01), light=True, env_size=(1024, 1024), tilt=None, box_gap=0.0):
     """Config 2: 5 walls + short box + tall box, Kd-only materials
     (roughness 1, metallic 0 => diffuse Disney), point light (10,10,10) under the ceiling."""
     parts = []
@@ -456,8 +456,8 @@ def cornell_box(res=1024, env=(0.01, 0.01, 0.01), light=True, env_size=(1024, 10
         ca, sa = np.cos(ang), np.sin(ang)
         R = np.array([[ca, 0, sa], [0, 1, 0], [-sa, 0, ca]])
         add((P - c) @ R.T + c, UV, N @ R.T, obj)
-    rot_box((0.15, 0.0, -0.65), (0.75, 0.6, -0.05), 0.3, 3)      # short box
-    rot_box((-0.75, 0.0, 0.0), (-0.15, 1.2, 0.6), -0.35, 4)      # tall box
+    rot_box((0.15, box_gap, -0.65), (0.75, 0.6, -0.05), 0.3, 3)      # short box
+    rot_box((-0.75, box_gap, 0.0), (-0.15, 1.2, 0.6), -0.35, 4)      # tall box
     tris = np.concatenate(parts)
     light_pos = np.array([0.0, 1.8, 0.0])
     if tilt is not None:
