@@ -262,9 +262,10 @@ def value_noise(shape, seed, octaves=4, base=8):
         iy, ix = fy.astype(int), fx.astype(int)
         ty, tx = fy - iy, fx - ix
         ty, tx = ty * ty * (3 - 2 * ty), tx * tx * (3 - 2 * tx)
-        a = lat[iy][:, ix] * (1 - tx)[None, :] + lat[iy][:, ix + 1] * tx[None, :]
-        b = lat[iy + 1][:, ix] * (1 - tx)[None, :] + lat[iy + 1][:, ix + 1] * tx[None, :]
-        out += amp * (a * (1 - ty)[:, None] + b * ty[:, None])
+        # separable smooth interpolation as two small matrix products: out = Wy @ lat @ Wx^T
+        Wy = np.zeros((H, n + 1)); Wy[np.arange(H), iy] = 1 - ty; Wy[np.arange(H), iy + 1] += ty
+        Wx = np.zeros((W, n + 1)); Wx[np.arange(W), ix] = 1 - tx; Wx[np.arange(W), ix + 1] += tx
+        out += amp * ((Wy @ lat) @ Wx.T)
         tot += amp
         amp *= 0.5
     return out / tot

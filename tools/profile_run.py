@@ -1,0 +1,26 @@
+#!/usr/bin/env python
+"""Small fixed workload for ncu: the bench scene (cached by bench.py), N spp in the fast mode.  Run under
+`ncu --metrics gpu__time_duration.sum ...` (launch list) or `ncu --set full -k regex:k_extend ...` (one kernel)."""
+import argparse
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+from tfg_pathtracer_b200 import renderer as R, scenes as S  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--spp", type=int, default=2)
+ap.add_argument("--tex", type=int, default=4096)
+ap.add_argument("--width", type=int, default=1920)
+ap.add_argument("--height", type=int, default=1080)
+ap.add_argument("--mode", default="fast")
+a = ap.parse_args()
+flat, _ = bench.get_scene(a, need_dir=False)
+sc = S.load_flat(flat)
+r = R.Renderer(**(R.FAST if a.mode == "fast" else R.PARITY)).render_setup(sc)
+r.render_cuda(a.spp)
+st = r.stats()
+print({k: st[k] for k in ("render_ms", "rays_extension", "rays_shadow_env", "kernel_launches")})
+r.close()
