@@ -19,6 +19,7 @@
 #include "../../include/eleven_b200.h"
 #include "bvh8.h"
 #include "kernels.cuh"
+#include "kernels_trace.cuh"
 
 using namespace eleven;
 
@@ -350,10 +351,14 @@ static void launchExtend(ElevenCtx* c, int grid) {
     if (c->cfg.hit_mode == ELEVEN_HIT_KEY) k_extend<TRACE_CLOSEST_KEY, COUNT><<<grid, 128, 0, c->stream>>>(c->W, c->scene);
     else k_extend<TRACE_CLOSEST_T, COUNT><<<grid, 128, 0, c->stream>>>(c->W, c->scene);
 }
+// shadow stages of one bounce; the last one also performs the MIS combination (kernels_trace.cuh).  Returns launches.
 template <bool COUNT>
-static void launchConnect(ElevenCtx* c, int grid) {
-    if (c->cfg.hit_mode == ELEVEN_HIT_KEY) k_connect<ELEVEN_HIT_KEY, COUNT><<<grid, 128, 0, c->stream>>>(c->W, c->scene, c->P);
-    else k_connect<ELEVEN_HIT_MIN_T, COUNT><<<grid, 128, 0, c->stream>>>(c->W, c->scene, c->P);
+static int launchConnect(ElevenCtx* c, int grid) {
+    if (c->scene.lightCount == 0) { k_shadowEnv<false, COUNT><<<grid, 128, 0, c->stream>>>(c->W, c->scene); return 1; }
+    k_shadowEnv<true, COUNT><<<grid, 128, 0, c->stream>>>(c->W, c->scene);
+    if (c->cfg.hit_mode == ELEVEN_HIT_KEY) k_shadowLight<ELEVEN_HIT_KEY, COUNT><<<grid, 128, 0, c->stream>>>(c->W, c->scene);
+    else k_shadowLight<ELEVEN_HIT_MIN_T, COUNT><<<grid, 128, 0, c->stream>>>(c->W, c->scene);
+    return 2;
 }
 
 extern "C" int eleven_render(ElevenCtx* c, int spp) {
@@ -387,13 +392,13 @@ extern "C" int eleven_render(ElevenCtx* c, int spp) {
             mark(1);
             k_advance<<<1, 32, 0, c->stream>>>(c->W, c->scene.lightCount, 0);
             mark(3);
-            if (count) launchConnect<true>(c, gridPersist); else launchConnect<false>(c, gridPersist);
+            c->stats.kernel_launches += count ? launchConnect<true>(c, gridPersist) : launchConnect<false>(c, gridPersist);
             mark(2);
             k_advance<<<1, 32, 0, c->stream>>>(c->W, c->scene.lightCount, 1);
             mark(3);
             c->stats.extend_launches += 1;
             std::swap(c->W.qCur, c->W.qNext);      // kernel arguments are captured at launch: the next bounce reads the list just written
-            c->stats.kernel_launches += 5;
+            c->stats.kernel_launches += 4;
         }
         k_accumulate<<<gridPix, 256, 0, c->stream>>>(c->W);
         mark(3);

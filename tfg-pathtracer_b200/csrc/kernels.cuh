@@ -23,7 +23,7 @@
 
 namespace eleven {
 
-enum { CNT_CUR = 0, CNT_NEXT = 1, CNT_NEE = 2, CNT_WORK_TRACE = 3, CNT_WORK_SHADE = 4, CNT_WORK_CONNECT = 5, CNT_WORK_SORT = 6, CNT_COUNT = 16 };
+enum { CNT_CUR = 0, CNT_NEXT = 1, CNT_NEE = 2, CNT_WORK_TRACE = 3, CNT_WORK_SHADE = 4, CNT_WORK_CONNECT = 5, CNT_WORK_LIGHT = 6, CNT_COUNT = 16 };
 enum { ST_RAYS_EXT = 0, ST_RAYS_ENV = 1, ST_RAYS_LIGHT = 2, ST_NODES = 3, ST_TRIS = 4, ST_COUNT = 8 };
 
 struct WaveState {
@@ -133,31 +133,10 @@ __global__ void __launch_bounds__(256) k_raygen(WaveState W, const __grid_consta
     W.qCur[i] = i;
     if (i == 0) {
         W.cnt[CNT_CUR] = W.nPixels; W.cnt[CNT_NEXT] = 0u; W.cnt[CNT_NEE] = 0u;
-        W.cnt[CNT_WORK_TRACE] = 0u; W.cnt[CNT_WORK_SHADE] = 0u; W.cnt[CNT_WORK_CONNECT] = 0u;
+        W.cnt[CNT_WORK_TRACE] = 0u; W.cnt[CNT_WORK_SHADE] = 0u; W.cnt[CNT_WORK_CONNECT] = 0u; W.cnt[CNT_WORK_LIGHT] = 0u;
     }
 }
 
-// ---- extend: closest hit for every queued path ---------------------------------------------------------------
-template <int MODE, bool COUNT>
-__global__ void __launch_bounds__(128) k_extend(WaveState W, const __grid_constant__ DevScene S) {
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t n = W.cnt[CNT_CUR];
-    TraceCounters tc; tc.nodes = 0; tc.tris = 0;
-    for (;;) {
-        const uint32_t base = warpFetch(&W.cnt[CNT_WORK_TRACE], lane);
-        if (base >= n) break;
-        const uint32_t qi = base + lane;
-        if (qi < n) {
-            const uint32_t pid = W.qCur[qi];
-            const float4 o = W.rayO[pid], d = W.rayD[pid];
-            Ray ray; ray.o = f3(o.x, o.y, o.z); ray.d = f3(d.x, d.y, d.z);
-            HitRec h;
-            traverse<MODE, COUNT>(S, ray, INFINITY, h, &tc);
-            W.hit[pid] = make_float4(__int_as_float(h.tri), h.t, h.u, h.v);
-        }
-    }
-    if (COUNT) { atomicAdd(&W.stats[ST_NODES], (unsigned long long)tc.nodes); atomicAdd(&W.stats[ST_TRIS], (unsigned long long)tc.tris); }
-}
 
 // ---- shade -----------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void appendWarpAggregated(uint32_t* q, uint32_t* counter, bool pred, uint32_t value) {
@@ -308,66 +287,6 @@ __global__ void __launch_bounds__(128) k_shade(WaveState W, const __grid_constan
     }
 }
 
-// ---- connect: shadow rays + MIS ------------------------------------------------------------------------------------
-template <int HITMODE, bool COUNT>
-__global__ void __launch_bounds__(128) k_connect(WaveState W, const __grid_constant__ DevScene S, const __grid_constant__ RenderParams P) {
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t n = W.cnt[CNT_NEE];
-    TraceCounters tc; tc.nodes = 0; tc.tris = 0;
-    for (;;) {
-        const uint32_t base = warpFetch(&W.cnt[CNT_WORK_CONNECT], lane);
-        if (base >= n) break;
-        const uint32_t qi = base + lane;
-        if (qi >= n) continue;
-        const uint32_t pid = W.qNee[qi];
-        const float4 pos4 = W.neePos[pid];
-        const F3 Pp = f3(pos4.x, pos4.y, pos4.z);
-        const float4 ed = W.neeEnvDir[pid], ec = W.neeEnvC[pid];
-        const float pB = ec.w;
-        float pE = ed.w;
-        F3 CE = f3(ec.x, ec.y, ec.z);
-        HitRec h;
-        {   // environment shadow ray: any valid hit occludes (S/kernel.cu:246-248)
-            const F3 w = f3(ed.x, ed.y, ed.z);
-            const Ray sr = makeRay(ex::madd(Pp, w, 0.001f), w);
-            if (traverse<TRACE_ANY, COUNT>(S, sr, INFINITY, h, &tc)) { pE = 0.f; CE = f3(0.f); }   // hdriPdf defined as 0 when occluded
-        }
-        float pP = 0.f; F3 CP = f3(0.f);
-        if (S.lightCount > 0) {
-            const float4 ld = W.neeLightDir[pid], lc = W.neeLightC[pid];
-            pP = lc.w; CP = f3(lc.x, lc.y, lc.z);
-            const F3 w = f3(ld.x, ld.y, ld.z);
-            const float dist = ld.w;
-            const Ray sr = makeRay(ex::madd(Pp, w, 0.001f), w);
-            bool occluded;
-            if (HITMODE == ELEVEN_HIT_KEY) {
-                // the reference takes the closest hit and compares |hit.position - point| with the light distance (S/kernel.cu:193-197)
-                occluded = false;
-                if (traverse<TRACE_CLOSEST_KEY, COUNT>(S, sr, INFINITY, h, &tc)) {
-                    const TriGeom g = loadTriGeom(S.shadeTris, h.tri);
-                    F3 sn;
-                    const F3 hp = hitPosition(sr, g, h.t, h.u, h.v, sn);
-                    occluded = length(hp - Pp) < dist;
-                }
-            } else {
-                occluded = traverse<TRACE_ANY, COUNT>(S, sr, dist - 0.001f, h, &tc);
-            }
-            if (occluded) CP = f3(0.f);
-        }
-        const float4 bc = W.neeBrdfC[pid];
-        const float sum = pE + pP + pB;
-        const float w1 = pE / sum, w2 = pP / sum, w3 = pB / sum;
-        const float4 thr4 = W.thr[pid];
-        const F3 thr = f3(thr4.x, thr4.y, thr4.z);
-        const F3 mix = f3(w1 * CE.x + w2 * CP.x + w3 * bc.x, w1 * CE.y + w2 * CP.y + w3 * bc.y, w1 * CE.z + w2 * CP.z + w3 * bc.z);
-        float4 r = W.rad[pid];
-        r.x += thr.x * mix.x; r.y += thr.y * mix.y; r.z += thr.z * mix.z;
-        W.rad[pid] = r;
-        const float4 tm = W.neeThrMul[pid];
-        W.thr[pid] = make_float4(thr.x * tm.x, thr.y * tm.y, thr.z * tm.z, 0.f);
-    }
-    if (COUNT) { atomicAdd(&W.stats[ST_NODES], (unsigned long long)tc.nodes); atomicAdd(&W.stats[ST_TRIS], (unsigned long long)tc.tris); }
-}
 
 // ---- queue bookkeeping between bounces (single thread) ---------------------------------------------------------------
 __global__ void k_advance(WaveState W, uint32_t lights, int phase) {
@@ -376,7 +295,7 @@ __global__ void k_advance(WaveState W, uint32_t lights, int phase) {
         W.stats[ST_RAYS_EXT] += W.cnt[CNT_CUR];
         W.stats[ST_RAYS_ENV] += W.cnt[CNT_NEE];
         if (lights) W.stats[ST_RAYS_LIGHT] += W.cnt[CNT_NEE];
-        W.cnt[CNT_WORK_CONNECT] = 0u;
+        W.cnt[CNT_WORK_CONNECT] = 0u; W.cnt[CNT_WORK_LIGHT] = 0u;
     } else {                     // after connect: next bounce
         W.cnt[CNT_CUR] = W.cnt[CNT_NEXT]; W.cnt[CNT_NEXT] = 0u; W.cnt[CNT_NEE] = 0u;
         W.cnt[CNT_WORK_TRACE] = 0u; W.cnt[CNT_WORK_SHADE] = 0u;
@@ -428,25 +347,5 @@ __global__ void k_resolve8(const float4* __restrict__ sums, const uint32_t* __re
     out[i] = make_uchar4(o[0], o[1], o[2], o[3]);
 }
 
-// ---- test hook / bench: closest hit on a plain ray batch (eleven_trace_*) -----------------------------------------------
-template <int MODE, bool COUNT>
-__global__ void __launch_bounds__(128) k_traceBatch(const float* __restrict__ rays, uint32_t n, ElevenHit* __restrict__ hits,
-                                                  const __grid_constant__ DevScene S, uint32_t* workCounter, unsigned long long* stats) {
-    const uint32_t lane = threadIdx.x & 31u;
-    TraceCounters tc; tc.nodes = 0; tc.tris = 0;
-    for (;;) {
-        const uint32_t base = warpFetch(workCounter, lane);
-        if (base >= n) break;
-        const uint32_t i = base + lane;
-        if (i >= n) continue;
-        const float* r = rays + 6 * (size_t)i;
-        const Ray ray = makeRay(f3(r[0], r[1], r[2]), f3(r[3], r[4], r[5]));
-        HitRec h;
-        traverse<MODE, COUNT>(S, ray, INFINITY, h, &tc);
-        ElevenHit o; o.tri = h.tri; o.t = h.t; o.u = h.u; o.v = h.v; o.key = h.key;
-        hits[i] = o;
-    }
-    if (COUNT && stats) { atomicAdd(&stats[ST_NODES], (unsigned long long)tc.nodes); atomicAdd(&stats[ST_TRIS], (unsigned long long)tc.tris); }
-}
 
 } // namespace eleven

@@ -1,0 +1,158 @@
+/*
+ * kernels_trace.cuh — the traversal kernels: thin Source/Sink adapters around trace_engine.cuh.
+ *
+ *   k_extend        closest hit for every queued path (throwRay, S/kernel.cu:152; BVH::transverse, S/BVH.hpp:120)
+ *   k_shadowEnv     environment NEE shadow rays: any valid hit occludes (S/kernel.cu:246-248)
+ *   k_shadowLight   point-light NEE shadow rays (S/kernel.cu:192-197)
+ *   the last shadow stage of a bounce also performs the balance-heuristic MIS combination and the throughput update
+ *   (shade, S/kernel.cu:351-357) in its Sink, so no separate combine pass reads the NEE records again
+ *   k_traceBatch    the closest-hit contract on plain ray batches (eleven_trace_*)
+ */
+#pragma once
+#include "kernels.cuh"
+#include "trace_engine.cuh"
+
+namespace eleven {
+
+// ---- extension rays -----------------------------------------------------------------------------------------------------
+struct ExtendSource {
+    const WaveState& W;
+    __device__ __forceinline__ void load(uint32_t qi, LaneRay& lr) const {
+        const uint32_t pid = W.qCur[qi];
+        const float4 o = W.rayO[pid], d = W.rayD[pid];
+        lr.ray.o = f3(o.x, o.y, o.z); lr.ray.d = f3(d.x, d.y, d.z);
+        lr.tmaxAny = INFINITY; lr.tag = pid;
+    }
+};
+struct ExtendSink {
+    const WaveState& W;
+    __device__ __forceinline__ void done(const LaneRay& lr, const HitRec& h) const {
+        W.hit[lr.tag] = make_float4(__int_as_float(h.tri), h.t, h.u, h.v);
+    }
+};
+template <int MODE, bool COUNT>
+__global__ void __launch_bounds__(128) k_extend(const __grid_constant__ WaveState W, const __grid_constant__ DevScene S) {
+    TraceCounters tc; tc.nodes = 0; tc.tris = 0;
+    ExtendSource src{W}; ExtendSink sink{W};
+    traceQueue<MODE, COUNT>(S, W.cnt[CNT_CUR], &W.cnt[CNT_WORK_TRACE], src, sink, tc);
+    if (COUNT) { atomicAdd(&W.stats[ST_NODES], (unsigned long long)tc.nodes); atomicAdd(&W.stats[ST_TRIS], (unsigned long long)tc.tris); }
+}
+
+// ---- MIS combination (shade, S/kernel.cu:351-357) --------------------------------------------------------------------------
+// hdriPdf is DEFINED as 0 when the environment shadow ray is occluded (the reference leaves it uninitialised).
+__device__ __forceinline__ void misCombine(const WaveState& W, uint32_t pid, bool lights, bool envOccluded, bool lightOccluded) {
+    const float4 ed = W.neeEnvDir[pid], ec = W.neeEnvC[pid], bc = W.neeBrdfC[pid];
+    const float pB = ec.w;
+    const float pE = envOccluded ? 0.f : ed.w;
+    const F3 CE = envOccluded ? f3(0.f) : f3(ec.x, ec.y, ec.z);
+    float pP = 0.f; F3 CP = f3(0.f);
+    if (lights) {
+        const float4 lc = W.neeLightC[pid];
+        pP = lc.w;
+        if (!lightOccluded) CP = f3(lc.x, lc.y, lc.z);
+    }
+    const float sum = pE + pP + pB;
+    const float w1 = pE / sum, w2 = pP / sum, w3 = pB / sum;
+    const float4 thr4 = W.thr[pid];
+    const F3 thr = f3(thr4.x, thr4.y, thr4.z);
+    const F3 mix = f3(w1 * CE.x + w2 * CP.x + w3 * bc.x, w1 * CE.y + w2 * CP.y + w3 * bc.y, w1 * CE.z + w2 * CP.z + w3 * bc.z);
+    float4 r = W.rad[pid];
+    r.x += thr.x * mix.x; r.y += thr.y * mix.y; r.z += thr.z * mix.z;
+    W.rad[pid] = r;
+    const float4 tm = W.neeThrMul[pid];
+    W.thr[pid] = make_float4(thr.x * tm.x, thr.y * tm.y, thr.z * tm.z, 0.f);
+}
+
+// ---- environment shadow rays --------------------------------------------------------------------------------------------------
+struct ShadowEnvSource {
+    const WaveState& W;
+    __device__ __forceinline__ void load(uint32_t qi, LaneRay& lr) const {
+        const uint32_t pid = W.qNee[qi];
+        const float4 p = W.neePos[pid], e = W.neeEnvDir[pid];
+        const F3 w = f3(e.x, e.y, e.z);
+        lr.ray = makeRay(ex::madd(f3(p.x, p.y, p.z), w, 0.001f), w);      // Ray(point + newDir*0.001, newDir), S/kernel.cu:246
+        lr.tmaxAny = INFINITY; lr.tag = pid;
+    }
+};
+template <bool LIGHTS>
+struct ShadowEnvSink {
+    const WaveState& W;
+    __device__ __forceinline__ void done(const LaneRay& lr, const HitRec& h) const {
+        const bool occluded = h.tri >= 0;
+        if (LIGHTS) { if (occluded) { float4 e = W.neeEnvDir[lr.tag]; e.w = -1.f; W.neeEnvDir[lr.tag] = e; } }   // p_e < 0 marks "occluded" for the light stage
+        else misCombine(W, lr.tag, false, occluded, false);
+    }
+};
+template <bool LIGHTS, bool COUNT>
+__global__ void __launch_bounds__(128) k_shadowEnv(const __grid_constant__ WaveState W, const __grid_constant__ DevScene S) {
+    TraceCounters tc; tc.nodes = 0; tc.tris = 0;
+    ShadowEnvSource src{W}; ShadowEnvSink<LIGHTS> sink{W};
+    traceQueue<TRACE_ANY, COUNT>(S, W.cnt[CNT_NEE], &W.cnt[CNT_WORK_CONNECT], src, sink, tc);
+    if (COUNT) { atomicAdd(&W.stats[ST_NODES], (unsigned long long)tc.nodes); atomicAdd(&W.stats[ST_TRIS], (unsigned long long)tc.tris); }
+}
+
+// ---- point-light shadow rays -------------------------------------------------------------------------------------------------
+template <int HITMODE>
+struct ShadowLightSource {
+    const WaveState& W;
+    __device__ __forceinline__ void load(uint32_t qi, LaneRay& lr) const {
+        const uint32_t pid = W.qNee[qi];
+        const float4 p = W.neePos[pid], l = W.neeLightDir[pid];
+        const F3 w = f3(l.x, l.y, l.z);
+        lr.ray = makeRay(ex::madd(f3(p.x, p.y, p.z), w, 0.001f), w);      // S/kernel.cu:192
+        lr.tmaxAny = HITMODE == ELEVEN_HIT_KEY ? INFINITY : l.w - 0.001f;
+        lr.tag = pid;
+    }
+};
+template <int HITMODE>
+struct ShadowLightSink {
+    const WaveState& W; const DevScene& S;
+    __device__ __forceinline__ void done(const LaneRay& lr, const HitRec& h) const {
+        const uint32_t pid = lr.tag;
+        bool occluded = h.tri >= 0;
+        if (HITMODE == ELEVEN_HIT_KEY && occluded) {
+            // the reference takes the CLOSEST hit and compares |hit.position - point| with the light distance (S/kernel.cu:193-197)
+            const float4 p = W.neePos[pid];
+            const TriGeom g = loadTriGeom(S.shadeTris, h.tri);
+            F3 sn;
+            const F3 hp = hitPosition(lr.ray, g, h.t, h.u, h.v, sn);
+            occluded = length(hp - f3(p.x, p.y, p.z)) < W.neeLightDir[pid].w;
+        }
+        const bool envOccluded = W.neeEnvDir[pid].w < 0.f;
+        misCombine(W, pid, true, envOccluded, occluded);
+    }
+};
+template <int HITMODE, bool COUNT>
+__global__ void __launch_bounds__(128) k_shadowLight(const __grid_constant__ WaveState W, const __grid_constant__ DevScene S) {
+    TraceCounters tc; tc.nodes = 0; tc.tris = 0;
+    ShadowLightSource<HITMODE> src{W}; ShadowLightSink<HITMODE> sink{W, S};
+    traceQueue<(HITMODE == ELEVEN_HIT_KEY ? TRACE_CLOSEST_KEY : TRACE_ANY), COUNT>(S, W.cnt[CNT_NEE], &W.cnt[CNT_WORK_LIGHT], src, sink, tc);
+    if (COUNT) { atomicAdd(&W.stats[ST_NODES], (unsigned long long)tc.nodes); atomicAdd(&W.stats[ST_TRIS], (unsigned long long)tc.tris); }
+}
+
+// ---- plain ray batches (test hook / bench) -----------------------------------------------------------------------------------------
+struct BatchSource {
+    const float* rays;
+    __device__ __forceinline__ void load(uint32_t qi, LaneRay& lr) const {
+        const float* r = rays + 6 * (size_t)qi;
+        lr.ray = makeRay(f3(r[0], r[1], r[2]), f3(r[3], r[4], r[5]));    // Ray's constructor normalises (S/Ray.hpp:14-18)
+        lr.tmaxAny = INFINITY; lr.tag = qi;
+    }
+};
+struct BatchSink {
+    ElevenHit* hits;
+    __device__ __forceinline__ void done(const LaneRay& lr, const HitRec& h) const {
+        ElevenHit o; o.tri = h.tri; o.t = h.t; o.u = h.u; o.v = h.v; o.key = h.key;
+        hits[lr.tag] = o;
+    }
+};
+template <int MODE, bool COUNT>
+__global__ void __launch_bounds__(128) k_traceBatch(const float* __restrict__ rays, uint32_t n, ElevenHit* __restrict__ hits,
+                                                  const __grid_constant__ DevScene S, uint32_t* workCounter, unsigned long long* stats) {
+    TraceCounters tc; tc.nodes = 0; tc.tris = 0;
+    BatchSource src{rays}; BatchSink sink{hits};
+    traceQueue<MODE, COUNT>(S, n, workCounter, src, sink, tc);
+    if (COUNT && stats) { atomicAdd(&stats[ST_NODES], (unsigned long long)tc.nodes); atomicAdd(&stats[ST_TRIS], (unsigned long long)tc.tris); }
+}
+
+} // namespace eleven

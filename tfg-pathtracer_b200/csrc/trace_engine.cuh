@@ -1,0 +1,192 @@
+/*
+ * trace_engine.cuh — the persistent, warp-synchronous ray queue engine used by every traversal kernel.
+ *
+ * Why (ncu on the first version, profiles/r1_extend_v1.txt): the closest-hit kernel is ISSUE-bound, not memory-bound
+ * (issue slots 70-73 % busy, DRAM 1 %, L2 2-5 %), and on incoherent bounce rays only 4.7 of 32 lanes were active per
+ * issued instruction: lanes idled (a) inside per-lane `while (triangles)` loops whose trip count is the warp maximum,
+ * and (b) after their ray finished, until the slowest ray of the 32-ray batch finished.  This engine removes both:
+ *
+ *   - ONE unit of work per lane per iteration: every active lane either intersects one node (8 child boxes) or one
+ *     triangle; the two phases are warp-uniformly skipped when no lane needs them (__any_sync), so a lane is never
+ *     parked in somebody else's inner loop;
+ *   - dynamic ray fetch: a lane whose ray finished writes its result immediately and goes idle; as soon as REFILL lanes
+ *     are idle the warp grabs that many rays from the global queue with one atomicAdd (warp-level work fetch) and the
+ *     idle lanes start new rays while the others continue theirs;
+ *   - child-box bytes are converted to float with PRMT + FADD (full-rate pipes) instead of I2F (quarter-rate
+ *     conversion pipe): 48 conversions per node made I2F the busiest pipe of the old kernel.
+ *
+ * Source supplies rays by queue index, Sink consumes finished rays; both are small functors so that the same engine
+ * serves the extension rays, the shadow rays and the plain ray batches of the test hook.
+ */
+#pragma once
+#include "traverse.cuh"
+
+namespace eleven {
+
+#ifndef EL_REFILL
+#define EL_REFILL 8            /* idle lanes that trigger a queue fetch */
+#endif
+
+struct LaneRay {
+    Ray ray;
+    float tmaxAny;             /* TRACE_ANY: accept hits with t < tmaxAny */
+    uint32_t tag;              /* opaque to the engine (path id / ray index) */
+};
+
+// float(byte j of q) without the conversion pipe: 0x4B000000 | b is 2^23 + b exactly
+__device__ __forceinline__ float byteToFloat(uint32_t q4, uint32_t selector) {
+    return __uint_as_float(__byte_perm(q4, 0x4B000000u, selector)) - 8388608.0f;
+}
+
+template <int MODE, bool COUNT, class Source, class Sink>
+__device__ __forceinline__ void traceQueue(const DevScene& S, uint32_t n, uint32_t* workCounter, Source& src, Sink& sink, TraceCounters& tc) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t FULL = 0xffffffffu;
+    const uint32_t ltMask = (1u << lane) - 1u;
+
+    bool active = false, exhausted = (S.nodeCount == 0 && false);
+    LaneRay lr; lr.tag = 0; lr.tmaxAny = INFINITY; lr.ray.o = f3(0.f); lr.ray.d = f3(0.f, 0.f, 1.f);
+    float idx = 0.f, idy = 0.f, idz = 0.f, dx = 1.f, dy = 1.f, dz = 1.f;
+    uint32_t octinv4 = 0;
+    float slack = 0.f, tcull = INFINITY, bestKey = INFINITY;
+    HitRec best; best.tri = -1; best.t = best.u = best.v = best.key = 0.f;
+    uint2 ngroup = make_uint2(0u, 0u), tgroup = make_uint2(0u, 0u);
+    uint2 stack[EL_STACK];
+    int sp = 0;
+
+    for (;;) {
+        // ---- dynamic fetch ---------------------------------------------------------------------------------------
+        const uint32_t idle = __ballot_sync(FULL, !active);
+        if (idle != 0u && !exhausted && (__popc(idle) >= EL_REFILL || idle == FULL)) {
+            const uint32_t cnt = __popc(idle);
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(workCounter, cnt);
+            base = __shfl_sync(FULL, base, 0);
+            if (base + cnt >= n) exhausted = true;
+            if (!active) {
+                const uint32_t qi = base + __popc(idle & ltMask);
+                if (qi < n) {
+                    src.load(qi, lr);
+                    const F3 d = lr.ray.d;
+                    dx = fabsf(d.x) > 1e-20f ? d.x : copysignf(1e-20f, d.x);
+                    dy = fabsf(d.y) > 1e-20f ? d.y : copysignf(1e-20f, d.y);
+                    dz = fabsf(d.z) > 1e-20f ? d.z : copysignf(1e-20f, d.z);
+                    idx = 1.0f / dx; idy = 1.0f / dy; idz = 1.0f / dz;
+                    octinv4 = ((dx >= 0.f ? 4u : 0u) | (dy >= 0.f ? 2u : 0u) | (dz >= 0.f ? 1u : 0u)) * 0x01010101u;
+                    const F3 o = lr.ray.o;
+                    slack = (MODE == TRACE_CLOSEST_KEY) ? S.keySlack + 4e-6f * (fabsf(o.x) + fabsf(o.y) + fabsf(o.z)) : 0.f;
+                    tcull = (MODE == TRACE_ANY) ? lr.tmaxAny : INFINITY;
+                    bestKey = INFINITY;
+                    best.tri = -1; best.t = best.u = best.v = best.key = 0.f;
+                    ngroup = make_uint2(0u, S.nodeCount ? 0x80000000u : 0u);
+                    tgroup = make_uint2(0u, 0u);
+                    sp = 0;
+                    active = true;
+                }
+            }
+        }
+        if (__ballot_sync(FULL, active) == 0u) {
+            if (exhausted) break;
+            continue;
+        }
+
+        // ---- every active lane must own a node group with pending children or pending triangles; else pop / finish ---
+        if (active && tgroup.y == 0u && ngroup.y <= 0x00ffffffu) {
+            if (sp > 0) ngroup = stack[--sp];
+            else { sink.done(lr, best); active = false; }
+        }
+
+        // ---- node phase: one node (8 quantised child boxes) ------------------------------------------------------------
+        const bool doNode = active && tgroup.y == 0u;
+        if (__any_sync(FULL, doNode)) {
+            if (doNode) {
+                const uint32_t octinv = octinv4 & 7u;
+                const uint32_t imask = ngroup.y;
+                const uint32_t bit = 31u - __clz(ngroup.y);
+                ngroup.y &= ~(1u << bit);
+                if (ngroup.y > 0x00ffffffu) stack[sp++] = ngroup;
+                const uint32_t slot = (bit - 24u) ^ octinv;
+                const uint32_t rank = __popc(imask & ~(0xffffffffu << slot));
+                const float4* np = S.nodes + (size_t)(ngroup.x + rank) * 5;
+                const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+                if (COUNT) tc.nodes++;
+                const F3 o = lr.ray.o;
+                const uint32_t eim = __float_as_uint(n0.w);
+                const float ax = __uint_as_float((eim & 0xffu) << 23) * idx;
+                const float ay = __uint_as_float(((eim >> 8) & 0xffu) << 23) * idy;
+                const float az = __uint_as_float(((eim >> 16) & 0xffu) << 23) * idz;
+                const float ox = (n0.x - o.x) * idx, oy = (n0.y - o.y) * idy, oz = (n0.z - o.z) * idz;
+                uint32_t hitmask = 0;
+#pragma unroll
+                for (int half = 0; half < 2; half++) {
+                    const uint32_t meta4 = __float_as_uint(half ? n1.w : n1.z);
+                    const uint32_t isInner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+                    const uint32_t innerMask4 = (isInner4 >> 4) * 0xffu;
+                    const uint32_t bitIndex4 = (meta4 ^ (octinv4 & innerMask4)) & 0x1f1f1f1fu;
+                    const uint32_t childBits4 = (meta4 >> 5) & 0x07070707u;
+                    const uint32_t qlox = __float_as_uint(half ? n2.y : n2.x), qloy = __float_as_uint(half ? n2.w : n2.z);
+                    const uint32_t qloz = __float_as_uint(half ? n3.y : n3.x), qhix = __float_as_uint(half ? n3.w : n3.z);
+                    const uint32_t qhiy = __float_as_uint(half ? n4.y : n4.x), qhiz = __float_as_uint(half ? n4.w : n4.z);
+                    const uint32_t xmin = dx < 0.f ? qhix : qlox, xmax = dx < 0.f ? qlox : qhix;
+                    const uint32_t ymin = dy < 0.f ? qhiy : qloy, ymax = dy < 0.f ? qloy : qhiy;
+                    const uint32_t zmin = dz < 0.f ? qhiz : qloz, zmax = dz < 0.f ? qloz : qhiz;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const uint32_t sel = 0x7540u + (uint32_t)j;
+                        const float tminx = fmaf(byteToFloat(xmin, sel), ax, ox), tmaxx = fmaf(byteToFloat(xmax, sel), ax, ox);
+                        const float tminy = fmaf(byteToFloat(ymin, sel), ay, oy), tmaxy = fmaf(byteToFloat(ymax, sel), ay, oy);
+                        const float tminz = fmaf(byteToFloat(zmin, sel), az, oz), tmaxz = fmaf(byteToFloat(zmax, sel), az, oz);
+                        const float cmin = fmaxf(fmaxf(tminx, tminy), fmaxf(tminz, 0.f));
+                        const float cmax = fminf(fminf(tmaxx, tmaxy), fminf(tmaxz, tcull));
+                        if (cmin * 0.9999995f <= cmax * 1.0000005f) {
+                            const uint32_t cb = (childBits4 >> (8 * j)) & 0xffu, bi = (bitIndex4 >> (8 * j)) & 0xffu;
+                            hitmask |= cb << bi;
+                        }
+                    }
+                }
+                ngroup.x = __float_as_uint(n1.x);
+                ngroup.y = (hitmask & 0xff000000u) | (eim >> 24);
+                tgroup.x = __float_as_uint(n1.y);
+                tgroup.y = hitmask & 0x00ffffffu;
+            }
+        }
+
+        // ---- triangle phase: one triangle ---------------------------------------------------------------------------------
+        const bool doTri = active && tgroup.y != 0u;
+        if (__any_sync(FULL, doTri)) {
+            if (doTri) {
+                const uint32_t ti = 31u - __clz(tgroup.y);
+                tgroup.y &= ~(1u << ti);
+                const float4* tp = S.slots + (size_t)(tgroup.x + ti) * 3;
+                const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+                if (COUNT) tc.tris++;
+                float t, u, v;
+                if (mollerTrumbore(lr.ray, f3(a.x, a.y, a.z), f3(a.w, b.x, b.y), f3(b.z, b.w, c.x), t, u, v)) {
+                    const int tri = __float_as_int(c.y);
+                    if (MODE == TRACE_ANY) {
+                        if (t < lr.tmaxAny) {
+                            best.tri = tri; best.t = t; best.u = u; best.v = v; best.key = t;
+                            sink.done(lr, best); active = false;
+                        }
+                    } else if (MODE == TRACE_CLOSEST_T) {
+                        if (best.tri < 0 || t < best.t || (t == best.t && tri < best.tri)) {
+                            best.tri = tri; best.t = t; best.u = u; best.v = v; best.key = t; tcull = t;
+                        }
+                    } else {
+                        if (t <= tcull) {
+                            const TriGeom g = loadTriGeom(S.shadeTris, tri);
+                            F3 sn;
+                            const float key = hitKey(lr.ray, hitPosition(lr.ray, g, t, u, v, sn));
+                            if (best.tri < 0 || key < bestKey || (key == bestKey && tri < best.tri)) {
+                                best.tri = tri; best.t = t; best.u = u; best.v = v; best.key = key; bestKey = key;
+                                tcull = fmaf(key, 1.000004f, slack);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+} // namespace eleven
