@@ -1,0 +1,136 @@
+/*
+ * eleven_main.cpp — the `eleven <scene_path> <#samples> <output.bmp>` command line of the reference (README.md:12-16,
+ * S/main.cpp:111-195) over the C ABI of include/eleven_b200.h.  Headless: no GL preview, no OIDN thread (out of scope,
+ * SURVEY §2).  Output is a 24-bit BMP written with the reference's save curve fastPow(clamp01(x), 1/2.2)*255
+ * (S/main.cpp:156-158; the reference actually writes PNG bytes whatever the extension).
+ *
+ *   eleven <scene_dir | scene.flat> <#samples> <output.bmp> [--mode fast|parity] [--gpus N] [--slice K] [--raw file.f32]
+ *   eleven --dump-flat <scene_dir> <out.flat>          (loader only, needs no GPU)
+ */
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/eleven_b200.h"
+#include "scene_loader.h"
+
+using namespace eleven_host;
+
+static double nowS() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+static double fastPowHost(double a, double b) {           // S/stb_image.h:127-136 (Ankerl's approximate pow)
+    union { double d; int32_t x[2]; } u; u.d = a;
+    u.x[1] = (int32_t)(b * (u.x[1] - 1072632447) + 1072632447); u.x[0] = 0; return u.d;
+}
+
+struct DeviceJob {
+    int device = 0, spp = 0; ElevenConfig cfg; ElevenSceneDesc* desc = nullptr;
+    std::vector<float> film; std::vector<uint32_t> counts; ElevenStats stats; std::string err; int rc = 0;
+    ElevenCtx* ctx = nullptr;
+};
+
+static void runDevice(DeviceJob* j, int slice, bool report) {
+    if ((j->rc = eleven_init(&j->cfg, &j->ctx))) { j->err = eleven_last_error(); return; }
+    if ((j->rc = eleven_scene_upload(j->ctx, j->desc))) { j->err = eleven_last_error(); return; }
+    const double t0 = nowS();
+    for (int done = 0; done < j->spp;) {
+        const int k = std::min(slice, j->spp - done);
+        if ((j->rc = eleven_render(j->ctx, k))) { j->err = eleven_last_error(); return; }
+        done += k;
+        if (report) {                                         // the reference's status line (S/main.cpp:172-179)
+            ElevenStats st; eleven_get_stats(j->ctx, &st);
+            const double ms = (nowS() - t0) * 1e3;
+            printf("\rkPaths/s: %.1f, %d/%d samples, %.2f seconds running, %llu total paths", st.hit_bounces / ms, done, j->spp, ms / 1e3,
+                   (unsigned long long)st.hit_bounces);
+            fflush(stdout);
+        }
+    }
+    const size_t n = (size_t)j->desc->camera.xRes * j->desc->camera.yRes;
+    j->film.resize(n * 4); j->counts.resize(n);
+    if ((j->rc = eleven_get_film(j->ctx, ELEVEN_PASS_BEAUTY, j->film.data(), n))) { j->err = eleven_last_error(); return; }
+    if ((j->rc = eleven_get_sample_counts(j->ctx, j->counts.data(), n))) { j->err = eleven_last_error(); return; }
+    eleven_get_stats(j->ctx, &j->stats);
+}
+
+int main(int argc, char** argv) {
+    std::string err;
+    if (argc >= 4 && !strcmp(argv[1], "--dump-flat")) {
+        LoadedScene s;
+        if (!loadScene(argv[2], s, err) || !saveFlat(s, argv[3], err)) { fprintf(stderr, "eleven: %s\n", err.c_str()); return 1; }
+        printf("%zu triangles, %zu objects, %zu materials, %zu textures, %zu lights -> %s\n", s.tris.size(), s.objectMaterial.size(),
+               s.materials.size(), s.textures.size(), s.lights.size(), argv[3]);
+        return 0;
+    }
+    if (argc < 4) { fprintf(stderr, "usage: eleven <scene_path> <#samples> <output.bmp> [--mode fast|parity] [--gpus N] [--slice K] [--raw file.f32]\n"); return 2; }
+    const std::string scenePath = argv[1], outPath = argv[3];
+    const int spp = atoi(argv[2]);
+    bool fast = true; int gpus = 1, slice = 16; const char* rawPath = nullptr;
+    for (int i = 4; i < argc; i++) {
+        if (!strcmp(argv[i], "--mode") && i + 1 < argc) fast = strcmp(argv[++i], "parity") != 0;
+        else if (!strcmp(argv[i], "--gpus") && i + 1 < argc) gpus = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "--slice") && i + 1 < argc) slice = std::max(1, atoi(argv[++i]));
+        else if (!strcmp(argv[i], "--raw") && i + 1 < argc) rawPath = argv[++i];
+        else { fprintf(stderr, "eleven: unknown option %s\n", argv[i]); return 2; }
+    }
+    if (spp <= 0 || gpus < 1) { fprintf(stderr, "eleven: bad sample or GPU count\n"); return 2; }
+    if (!fast && gpus > 1) { fprintf(stderr, "eleven: the reference RNG stream cannot be split across GPUs; use --mode fast\n"); return 2; }
+
+    printf("Loading scene \n");
+    double t0 = nowS();
+    LoadedScene scene;
+    if (!loadScene(scenePath, scene, err)) { fprintf(stderr, "eleven: %s\n", err.c_str()); return 1; }
+    ElevenSceneDesc desc = scene.desc();
+    printf("%s: %zu triangles, %zu textures, %ux%u, loaded in %.0f ms\n", scenePath.c_str(), scene.tris.size(), scene.textures.size(),
+           desc.camera.xRes, desc.camera.yRes, (nowS() - t0) * 1e3);
+
+    std::vector<DeviceJob> jobs(gpus);
+    for (int g = 0; g < gpus; g++) {
+        DeviceJob& j = jobs[g]; memset(&j.cfg, 0, sizeof j.cfg);
+        j.device = g; j.desc = &desc;
+        j.cfg.device = g; j.cfg.max_bounces = 5;
+        j.cfg.rng_mode = fast ? ELEVEN_RNG_FAST : ELEVEN_RNG_REFERENCE; j.cfg.env_mode = fast ? ELEVEN_ENV_ALIAS : ELEVEN_ENV_CDF;
+        j.cfg.hit_mode = ELEVEN_HIT_KEY; j.cfg.flags = fast ? ELEVEN_FLAG_TERMINATE_DEAD_PATHS : 0u;
+        j.cfg.sample_offset = (uint32_t)g; j.cfg.sample_stride = (uint32_t)gpus;
+        j.spp = spp / gpus + (g < spp % gpus ? 1 : 0);          // global sample s goes to device s % gpus
+    }
+    t0 = nowS();
+    std::vector<std::thread> th;
+    for (int g = 1; g < gpus; g++) th.emplace_back(runDevice, &jobs[g], slice, false);
+    runDevice(&jobs[0], slice, true);
+    for (auto& t : th) t.join();
+    printf("\n");
+    for (auto& j : jobs) if (j.rc) { fprintf(stderr, "eleven: device %d: %s\n", j.device, j.err.c_str()); return 1; }
+    const double wall = nowS() - t0;
+
+    const size_t n = (size_t)desc.camera.xRes * desc.camera.yRes;
+    std::vector<unsigned char> rgba(n * 4);
+    std::vector<float> mean;
+    if (gpus == 1) {
+        if (eleven_resolve_rgba8(jobs[0].ctx, ELEVEN_PASS_BEAUTY, rgba.data(), n)) { fprintf(stderr, "eleven: %s\n", eleven_last_error()); return 1; }
+        mean = jobs[0].film;
+    } else {                                                     // host-side combine of the per-device means (CLI only; bench uses NCCL)
+        mean.assign(n * 4, 0.f);
+        for (size_t i = 0; i < n; i++) {
+            double s[3] = {0, 0, 0}; uint64_t c = 0;
+            for (auto& j : jobs) { for (int k = 0; k < 3; k++) s[k] += (double)j.film[4 * i + k] * j.counts[i]; c += j.counts[i]; }
+            for (int k = 0; k < 3; k++) mean[4 * i + k] = c ? (float)(s[k] / c) : 0.f;
+            mean[4 * i + 3] = 1.f;
+            for (int k = 0; k < 4; k++) { float x = mean[4 * i + k]; x = x < 0 ? 0 : x > 1 ? 1 : x; rgba[4 * i + k] = (unsigned char)(fastPowHost(x, 1.0 / 2.2) * 255); }
+        }
+    }
+    printf("Saving file %s...\n", outPath.c_str());
+    if (!writeBmp24(outPath, (int)desc.camera.xRes, (int)desc.camera.yRes, rgba.data(), err)) { fprintf(stderr, "eleven: %s\n", err.c_str()); return 1; }
+    if (rawPath) { FILE* f = fopen(rawPath, "wb"); if (f) { fwrite(mean.data(), 4, mean.size(), f); fclose(f); } }
+    printf("Saved!\n");
+    double renderMs = 0; uint64_t rays = 0, samples = 0;
+    for (auto& j : jobs) { renderMs = std::max(renderMs, j.stats.render_ms); rays += j.stats.rays_extension + j.stats.rays_shadow_env + j.stats.rays_shadow_light; samples += j.stats.pixel_samples; }
+    printf("%d spp on %d GPU(s): render %.1f ms (wall incl. upload %.1f ms), %.1f M pixel-samples/s, %.1f Mrays/s, BVH8 %u nodes built in %.1f ms\n",
+           spp, gpus, renderMs, wall * 1e3, samples / renderMs / 1e3, rays / renderMs / 1e3, jobs[0].stats.bvh_nodes, jobs[0].stats.bvh_build_ms);
+    for (auto& j : jobs) eleven_destroy(j.ctx);
+    return 0;
+}
