@@ -602,8 +602,8 @@ def clock_standin(seed=11, tex_res=4096, xres=1920, yres=1080, env_size=(4096, 2
                      ["clock", "table", "plant"], ["clock_mat", "table_mat", "plant_mat"])
 
 
-def displaced_grid(n=3162, seed=4, xres=1920, yres=1080, env_size=(4096, 2048)):
-    """Config 4: n x n vertex grid -> 2(n-1)^2 triangles (n=3162 -> 9 991 922), 4-octave value-noise height,
+def displaced_grid(n=2237, seed=4, xres=1920, yres=1080, env_size=(4096, 2048)):
+    """Config 4: n x n vertex grid -> 2(n-1)^2 triangles (n=2237 -> 9 999 392; SURVEY §8d's 3162 would give 19.98 M), 4-octave value-noise height,
     smooth normals, one material, sun+sky HDRI."""
     h = value_noise((n, n), seed, 4, 6).astype(np.float32)
     ext = 10.0

@@ -1,0 +1,163 @@
+#!/usr/bin/env python
+"""Runs one BASELINE.json config at its FULL size on the GPU box and prints one JSON line: timings, throughput, and the
+size-independent parity properties of SURVEY §8c (what can be checked without an O(N) CPU oracle run):
+
+  P1  every reported hit recomputed in float64 from (triangle, ray): |t-t64|, |u-u64|, |v-v64| tiny, u,v,u+v in range
+  P2  rays aimed at the centroid of a random triangle hit something no farther than that triangle
+  P3  any-hit says "occluded" exactly where closest-hit found a triangle
+  P4  KEY and MIN_T modes pick the same triangle except inside the per-scene key slack
+  P5  rendering: film finite, sample counts == spp except NaN-dropped pixels, fast-mode mean == parity-mode mean (statistically)
+  P6  on a 2 048-ray subsample, the CPU oracle's BRUTE-FORCE closest hit (exact reference arithmetic) equals ours bit for bit
+
+configs: 2 = Cornell box 1024^2 256 spp; 3 = ClockCC0 stand-in 1000 spp; 4 = ~10 M-triangle displaced grid 1920x1080 512 spp;
+         5 = 3840x2160 4096 spp textured + 4 point lights (spp can be cut with --spp: throughput is per sample)
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "golden")):
+    sys.path.insert(0, p)
+from tfg_pathtracer_b200 import renderer as R, scenes as S  # noqa: E402
+
+
+def build(cfg, grid_n, tex):
+    if cfg == 2:
+        return S.cornell_box(1024), 256
+    if cfg == 3:
+        return S.clock_standin(tex_res=tex), 1000
+    if cfg == 4:
+        return S.displaced_grid(grid_n), 512
+    if cfg == 5:
+        return S.textured_lights(tex_res=tex), 4096
+    raise SystemExit("config must be 2..5")
+
+
+def mt64(tri, rays):
+    """Moeller-Trumbore in float64 for (triangle vertices (n,3,3), rays (n,6) with normalised dirs)."""
+    v0, e1, e2 = tri[:, 0], tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0]
+    o, d = rays[:, :3], rays[:, 3:]
+    p = np.cross(d, e2)
+    det = (e1 * p).sum(1)
+    tv = o - v0
+    u = (tv * p).sum(1) / det
+    q = np.cross(tv, e1)
+    v = (d * q).sum(1) / det
+    t = (e2 * q).sum(1) / det
+    return t, u, v
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", type=int, required=True)
+    ap.add_argument("--spp", type=int, default=0, help="override the config's spp (throughput is per sample)")
+    ap.add_argument("--grid", type=int, default=2237, help="n x n vertices -> 2(n-1)^2 triangles; 2237 -> 9.999 M")
+    ap.add_argument("--tex", type=int, default=4096)
+    ap.add_argument("--rays", type=int, default=1 << 20)
+    ap.add_argument("--no-oracle", action="store_true")
+    a = ap.parse_args()
+    out = {"config": a.config}
+    t0 = time.time()
+    sc, spp = build(a.config, a.grid, a.tex)
+    spp = a.spp or spp
+    out.update(scene=sc.name, tris=int(len(sc.tris)), width=sc.width, height=sc.height, spp=spp, generate_s=time.time() - t0)
+
+    t0 = time.time()
+    r = R.Renderer(**R.PARITY).render_setup(sc)
+    out["upload_s"] = time.time() - t0
+    st = r.stats()
+    out.update(bvh_build_ms=st["bvh_build_ms"], bvh_nodes=st["bvh_nodes"], key_slack=st["key_slack"])
+
+    # ---- closest-hit properties on camera rays + rays aimed at triangle centroids ----
+    rng = np.random.RandomState(5)
+    n = a.rays
+    cam = S.camera_rays(sc, n // 2, seed=1)
+    ti = rng.randint(0, len(sc.tris), n // 2)
+    cen = sc.tris["vertices"][ti].astype(np.float64).mean(1)
+    V = sc.tris["vertices"].reshape(-1, 3)
+    lo, hi = V.min(0), V.max(0)
+    org = (lo + hi) / 2 + (hi - lo) * (rng.rand(n // 2, 3) - 0.5) * np.array([1.0, 0.2, 1.0]) + np.array([0, (hi - lo)[1] * 1.5 + 0.5, 0])
+    aimed = np.concatenate([org, cen - org], 1)
+    rays = np.concatenate([cam, aimed]).astype(np.float32)
+    t0 = time.time()
+    hits = r.trace_closest(rays)
+    out["trace_closest_host_s"] = time.time() - t0
+    d = rays[:, 3:].astype(np.float64)
+    dn = (d / np.sqrt((d * d).sum(1, keepdims=True)))
+    ok = hits["tri"] >= 0
+    t64, u64, v64 = mt64(sc.tris["vertices"][hits["tri"][ok]].astype(np.float64), np.concatenate([rays[ok, :3].astype(np.float64), dn[ok]], 1))
+    scale = np.maximum(1.0, np.abs(t64))
+    out["P1_max_rel_dt"] = float((np.abs(hits["t"][ok] - t64) / scale).max())
+    out["P1_max_du_dv"] = float(max(np.abs(hits["u"][ok] - u64).max(), np.abs(hits["v"][ok] - v64).max()))
+    out["P1_uv_in_range"] = bool(((hits["u"][ok] >= 0) & (hits["v"][ok] >= 0) & (hits["u"][ok] + hits["v"][ok] <= 1.0 + 1e-6)).all())
+    ha = hits[n // 2:]
+    dist = np.sqrt(((cen - org) ** 2).sum(1))
+    out["P2_aimed_hit_fraction"] = float((ha["tri"] >= 0).mean())
+    out["P2_no_farther_than_target"] = bool((ha["t"][ha["tri"] >= 0] <= dist[ha["tri"] >= 0] * (1 + 1e-4) + 1e-4 + 2 * st["key_slack"]).all())   # closest by KEY may have a larger t, within the slack
+    out["hit_fraction"] = float(ok.mean())
+    # any-hit vs closest (device buffers)
+    d_r = r.device_alloc(rays.nbytes)
+    d_h = r.device_alloc(len(rays) * 20)
+    r.device_upload(d_r, rays)
+    ms_any = r.trace_device(d_r, len(rays), d_h, any_hit=True)
+    ah = np.zeros(len(rays), hits.dtype)
+    r.device_download(ah, d_h)
+    out["P3_anyhit_equals_closest_valid"] = bool(((ah["tri"] >= 0) == ok).all())
+    ms_closest = min(r.trace_device(d_r, len(rays), d_h) for _ in range(3))
+    out["trace_device_mrays_s"] = len(rays) / ms_closest / 1e3
+    out["trace_device_anyhit_mrays_s"] = len(rays) / ms_any / 1e3
+    cfgT = dict(R.PARITY); cfgT["hit_mode"] = R.HIT_MIN_T
+    rt = R.Renderer(**cfgT).render_setup(sc)
+    ht = rt.trace_closest(rays)
+    dif = ht["tri"] != hits["tri"]
+    out["P4_min_t_differs"] = int(dif.sum())
+    out["P4_within_slack"] = bool((np.abs(ht["t"][dif] - hits["t"][dif]) <= 2 * st["key_slack"] + 1e-5).all()) if dif.any() else True
+    rt.close()
+    if not a.no_oracle:
+        import oracle_lib as O
+        sub = rng.choice(len(rays), 2048, replace=False)
+        orc = O.Oracle(sc, build_bvh=False)
+        t0 = time.time()
+        ob = orc.trace(rays[sub], mode=1, threads=os.cpu_count() or 8)
+        out["oracle_bruteforce_s"] = time.time() - t0
+        hs = hits[sub]
+        same = (ob["tri"] == hs["tri"]) & ((ob["tri"] < 0) | ((ob["t"].view(np.uint32) == hs["t"].view(np.uint32)) & (ob["u"].view(np.uint32) == hs["u"].view(np.uint32)) & (ob["key"].view(np.uint32) == hs["key"].view(np.uint32))))
+        tie = ~same & (ob["tri"] >= 0) & (hs["tri"] >= 0) & (ob["key"].view(np.uint32) == hs["key"].view(np.uint32))
+        out["P6_bit_exact"] = int(same.sum()); out["P6_ties"] = int(tie.sum()); out["P6_bad"] = int((~same & ~tie).sum())
+        orc.close()
+    r.device_free(d_r); r.device_free(d_h)
+
+    # ---- render: parity mode few spp, fast mode at the requested spp ----
+    r.render_cuda(2)
+    fp = r.film()[..., :3]
+    cnt = r.get_sample_counts()
+    out["P5_parity_finite"] = bool(np.isfinite(fp).all())
+    out["P5_parity_dropped_fraction"] = float((cnt < 2).mean())
+    stp = r.stats()
+    out["parity_samples_per_s"] = sc.width * sc.height * 2 / (stp["render_ms"] * 1e-3)
+    r.close()
+    f = R.Renderer(**R.FAST).render_setup(sc)
+    f.render_cuda(2); f.reset()
+    t0 = time.time()
+    f.render_cuda(spp)
+    wall = time.time() - t0
+    stf = f.stats()
+    ff = f.film()[..., :3]
+    rays_total = stf["rays_extension"] + stf["rays_shadow_env"] + stf["rays_shadow_light"]
+    out.update(fast_spp=spp, fast_render_ms=stf["render_ms"], fast_wall_s=wall,
+               fast_samples_per_s=sc.width * sc.height * spp / (stf["render_ms"] * 1e-3), fast_frame_spp_per_s=spp / (stf["render_ms"] * 1e-3),
+               fast_mrays_per_s=rays_total / (stf["render_ms"] * 1e3), rays_per_sample=rays_total / (sc.width * sc.height * spp),
+               P5_fast_finite=bool(np.isfinite(ff).all()), P5_mean_fast=float(ff.mean()), P5_mean_parity_2spp=float(fp.mean()))
+    f.close()
+    print(json.dumps(out))
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(out, open(os.path.join(ROOT, "gpurun_out", "config%d.json" % a.config), "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
