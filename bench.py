@@ -199,6 +199,7 @@ def main():
     ap.add_argument("--cpu-rows", type=int, default=96)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mode", default="fast", choices=["fast", "parity"])
+    ap.add_argument("--hit-mode", default="key", choices=["key", "min_t"], help="closest-hit ordering: the reference key (default) or classic min t")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -222,6 +223,8 @@ def main():
     sc = S.load_flat(flat)
     W, H = sc.width, sc.height
     mode = dict(R.FAST if args.mode == "fast" else R.PARITY)
+    if args.hit_mode == "min_t":
+        mode["hit_mode"] = R.HIT_MIN_T
     t0 = time.time()
     off, stride, _ = D.sample_plan(args.spp_per_step * world, rank, world)
     r = R.Renderer(device=local, sample_offset=off, sample_stride=stride, **mode).render_setup(sc)
@@ -249,9 +252,10 @@ def main():
         rays_all = st["rays_extension"] + st["rays_shadow_env"] + st["rays_shadow_light"]
         nodes_per_ray = st["nodes_visited"] / max(1, rays_all)
         tris_per_ray = st["tris_tested"] / max(1, rays_all)
+        keys_per_ray = st["key_evals"] / max(1, rays_all)
         rc.close()
     else:
-        nodes_per_ray = tris_per_ray = 0.0
+        nodes_per_ray = tris_per_ray = keys_per_ray = 0.0
 
     for _ in range(args.warmup):
         r.reset()
@@ -332,7 +336,7 @@ def main():
             "gpu_launches": int(st["kernel_launches"] - launches0),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "kernel": "k_extend (closest hit over BVH8)", "peak_source": peak_src,
-                         "bytes_per_ray": bytes_per_ray, "nodes_per_ray": nodes_per_ray, "tris_per_ray": tris_per_ray,
+                         "bytes_per_ray": bytes_per_ray, "nodes_per_ray": nodes_per_ray, "tris_per_ray": tris_per_ray, "exact_key_evals_per_ray": keys_per_ray,
                          "launch_ms": stage["extend_ms"] / max(1, stage["extend_launches"]), "launches": int(stage["extend_launches"]),
                          "share_of_step": stage["extend_ms"] / stage["render_ms"] if stage["render_ms"] else None,
                          "stage_ms": {k: stage[k] for k in ("extend_ms", "shade_ms", "connect_ms", "other_ms", "render_ms")},

@@ -64,6 +64,8 @@ typedef struct ElevenConfig {
 #define ELEVEN_FLAG_TERMINATE_DEAD_PATHS 1u  /* stop paths whose throughput is exactly 0 (only legal with RNG_FAST) */
 #define ELEVEN_FLAG_COUNTERS             2u  /* count nodes/triangles visited per ray (slower; for the roofline)    */
 #define ELEVEN_FLAG_TIME_KERNELS         4u  /* CUDA-event timing around every pipeline stage (ElevenStats *_ms)   */
+#define ELEVEN_FLAG_SKIP_NULL_NEE        8u  /* no env shadow ray when its contribution is 0 whatever it hits (no point
+                                              * lights, no emission, BRDF 0 towards the sample): same image, fewer rays */
 
 /* ---- scene description (what renderSetup copies out of Scene, S/kernel.cu:566-661) ---- */
 
@@ -158,6 +160,7 @@ typedef struct ElevenStats {
     uint32_t bvh_tri_slots;      /* triangle slots in leaf order                             */
     float    key_slack;          /* per-scene bound on |key - t| used for culling in HIT_KEY */
     uint32_t samples_done;       /* per-pixel sample count of pixel 0 (getSamples)           */
+    uint64_t key_evals;          /* exact reference-key evaluations (only with ELEVEN_FLAG_COUNTERS) */
 } ElevenStats;
 
 typedef struct ElevenCtx ElevenCtx;

@@ -20,7 +20,7 @@ PASS_BEAUTY, PASS_DENOISE, PASS_NORMAL, PASS_TANGENT, PASS_BITANGENT = range(5)
 RNG_REFERENCE, RNG_FAST = 0, 1
 ENV_CDF, ENV_ALIAS = 0, 1
 HIT_KEY, HIT_MIN_T = 0, 1
-FLAG_TERMINATE_DEAD_PATHS, FLAG_COUNTERS, FLAG_TIME_KERNELS = 1, 2, 4
+FLAG_TERMINATE_DEAD_PATHS, FLAG_COUNTERS, FLAG_TIME_KERNELS, FLAG_SKIP_NULL_NEE = 1, 2, 4, 8
 
 
 class ElevenConfig(C.Structure):
@@ -64,7 +64,7 @@ class ElevenStats(C.Structure):
                 ("tris_tested", C.c_uint64), ("kernel_launches", C.c_uint64), ("render_ms", C.c_double),
                 ("trace_ms", C.c_double), ("extend_ms", C.c_double), ("shade_ms", C.c_double), ("connect_ms", C.c_double),
                 ("other_ms", C.c_double), ("extend_launches", C.c_uint64), ("bvh_build_ms", C.c_double), ("bvh_nodes", C.c_uint32),
-                ("bvh_tri_slots", C.c_uint32), ("key_slack", C.c_float), ("samples_done", C.c_uint32)]
+                ("bvh_tri_slots", C.c_uint32), ("key_slack", C.c_float), ("samples_done", C.c_uint32), ("key_evals", C.c_uint64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

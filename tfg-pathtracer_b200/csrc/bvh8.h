@@ -38,13 +38,14 @@ static_assert(sizeof(Node8) == 80, "Node8 must be 80 bytes");
 struct alignas(16) TriSlot {
     float v0x, v0y, v0z, e1x;
     float e1y, e1z, e2x, e2y;
-    float e2z; int32_t tri; int32_t material; uint32_t pad;
+    float e2z; int32_t tri; int32_t material; float shiftBound;   /* bound on |hit.position - geometric position| for THIS triangle */
 };
 static_assert(sizeof(TriSlot) == 48, "TriSlot must be 48 bytes");
 
 struct Bvh8 {
     std::vector<Node8>   nodes;       /* nodes[0] is the root */
     std::vector<TriSlot> slots;       /* triangles in leaf order */
+    std::vector<float>   nodeSlack;   /* per node: max TriSlot::shiftBound in its subtree */
     float  keySlack;                  /* bound on |reference key - t| over the scene (see build) */
     float  boundsLo[3], boundsHi[3];
     double buildMs;

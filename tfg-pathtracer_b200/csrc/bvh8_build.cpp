@@ -29,7 +29,7 @@ struct Box {
     }
 };
 
-struct Node2 { Box box; int left, right, first, count; };   // leaf iff count > 0
+struct Node2 { Box box; int left, right, first, count, span; };   // leaf iff count > 0; span = triangles in the subtree
 
 static const int   BINS = 16;
 static const int   MAX_LEAF = 3;
@@ -48,7 +48,7 @@ struct Builder {
         Node2& N = nodes[ni];
         Box b, cb; b.reset(); cb.reset();
         for (int i = first; i < first + count; i++) { b.grow(tbox[idx[i]]); cb.grow(&cen[3 * idx[i]]); }
-        N.box = b; N.left = N.right = -1; N.first = first; N.count = count;
+        N.box = b; N.left = N.right = -1; N.first = first; N.count = count; N.span = count;
         if (count <= 1) return;
 
         // binned SAH over the three axes
@@ -132,6 +132,7 @@ void buildBvh8(const ElevenTri* tris, uint32_t n, const int32_t* triMaterial, Bv
     B.tbox.resize(n); B.cen.resize(3 * (size_t)n); B.idx.resize(n);
     Box scene; scene.reset();
     double slack = 0;
+    std::vector<float> triShift(n);
     for (uint32_t i = 0; i < n; i++) {
         Box b; b.reset();
         for (int k = 0; k < 3; k++) b.grow(tris[i].vertices[k]);
@@ -141,6 +142,7 @@ void buildBvh8(const ElevenTri* tris, uint32_t n, const int32_t* triMaterial, Bv
         // Bound on the shadow-terminator shift |shadingPosition - geomPosition| (S/Tri.hpp:81-89): shadingPosition is
         // a convex combination of the projections p_i = P - dot(P - v_i, n_i) n_i, and dot(P - v_i, n_i) is linear in
         // P over the triangle, so max |p_i - P| is attained at a vertex: max_{i,j} |dot(v_j - v_i, n_i)| * |n_i|.
+        double mine = 0;
         for (int vi = 0; vi < 3; vi++) {
             const float* nn = tris[i].normals[vi];
             double nl = std::sqrt((double)nn[0] * nn[0] + (double)nn[1] * nn[1] + (double)nn[2] * nn[2]);
@@ -148,9 +150,11 @@ void buildBvh8(const ElevenTri* tris, uint32_t n, const int32_t* triMaterial, Bv
                 if (vj == vi) continue;
                 double d = 0;
                 for (int a = 0; a < 3; a++) d += ((double)tris[i].vertices[vj][a] - tris[i].vertices[vi][a]) * nn[a];
-                slack = std::max(slack, std::fabs(d) * nl);
+                mine = std::max(mine, std::fabs(d) * nl);
             }
         }
+        triShift[i] = (float)(mine * 1.0001);
+        slack = std::max(slack, mine);
     }
     if (n == 0) { scene.lo[0] = scene.lo[1] = scene.lo[2] = 0; scene.hi[0] = scene.hi[1] = scene.hi[2] = 0; }
     float ext = 0, mag = 0;
@@ -173,7 +177,7 @@ void buildBvh8(const ElevenTri* tris, uint32_t n, const int32_t* triMaterial, Bv
     // ---- collapse to 8-wide, breadth-first so that a node's internal children are contiguous ---------
     struct Item { int n2; uint32_t n8; uint32_t depth; };
     std::vector<Item> queue; queue.reserve(n / 4 + 16);
-    out.nodes.reserve(n / 3 + 16); out.slots.reserve(n);
+    out.nodes.reserve(n / 3 + 16); out.slots.reserve(n); out.nodeSlack.clear(); out.nodeSlack.reserve(n / 3 + 16);
     out.nodes.emplace_back(); memset(&out.nodes[0], 0, sizeof(Node8));
     queue.push_back({0, 0u, 1u});
     for (size_t qi = 0; qi < queue.size(); qi++) {
@@ -239,7 +243,7 @@ void buildBvh8(const ElevenTri* tris, uint32_t n, const int32_t* triMaterial, Bv
                     S.v0x = T.vertices[0][0]; S.v0y = T.vertices[0][1]; S.v0z = T.vertices[0][2];
                     S.e1x = T.vertices[1][0] - T.vertices[0][0]; S.e1y = T.vertices[1][1] - T.vertices[0][1]; S.e1z = T.vertices[1][2] - T.vertices[0][2];
                     S.e2x = T.vertices[2][0] - T.vertices[0][0]; S.e2y = T.vertices[2][1] - T.vertices[0][1]; S.e2z = T.vertices[2][2] - T.vertices[0][2];
-                    S.tri = t; S.material = triMaterial ? triMaterial[t] : 0; S.pad = 0;
+                    S.tri = t; S.material = triMaterial ? triMaterial[t] : 0; S.shiftBound = triShift[t];
                     out.slots.push_back(S);
                 }
                 triOff += cnt;
@@ -257,7 +261,14 @@ void buildBvh8(const ElevenTri* tris, uint32_t n, const int32_t* triMaterial, Bv
             queue.push_back({c2, id, it.depth + 1});
         }
         out.nodes[it.n8] = N;
+        {   // largest shift bound of any triangle below this node: lets the traversal cull with a LOCAL slack
+            float ms = 0.f;
+            for (int k = root.first; k < root.first + root.span; k++) ms = std::max(ms, triShift[B.idx[k]]);
+            if (out.nodeSlack.size() <= it.n8) out.nodeSlack.resize(it.n8 + 1, 0.f);
+            out.nodeSlack[it.n8] = ms;
+        }
     }
+    out.nodeSlack.resize(out.nodes.size(), 0.f);
     out.buildMs = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 }
 

@@ -110,6 +110,7 @@ struct AliasEntry { float prob; uint32_t alias; };
 struct DevScene {
     const float4* nodes;          // Node8 as 5 x float4
     const float4* slots;          // TriSlot as 3 x float4
+    const float* nodeSlack;       // per node: max shadow-terminator shift bound in its subtree
     const float4* shadeTris;      // 9 x float4 per triangle, original index order
     const int32_t* objectMaterial;
     const DevMaterial* materials;

@@ -235,6 +235,7 @@ extern "C" int eleven_scene_upload(ElevenCtx* c, const ElevenSceneDesc* d) {
     c->stats.key_slack = bvh.keySlack;
     if ((rc = devUpload(c->sceneAllocs, &S.nodes, (const float4*)bvh.nodes.data(), bvh.nodes.size() * 5))) return rc;
     if ((rc = devUpload(c->sceneAllocs, &S.slots, (const float4*)bvh.slots.data(), bvh.slots.size() * 3))) return rc;
+    if ((rc = devUpload(c->sceneAllocs, &S.nodeSlack, bvh.nodeSlack.data(), bvh.nodeSlack.size()))) return rc;
     S.nodeCount = d->triCount ? (uint32_t)bvh.nodes.size() : 0u; S.triCount = d->triCount; S.keySlack = bvh.keySlack;
     {
         std::vector<float> st((size_t)d->triCount * 36);
@@ -498,7 +499,7 @@ extern "C" int eleven_get_stats(ElevenCtx* c, ElevenStats* out) {
         CK(cudaMemcpyAsync(&s0, c->W.filmCount, 4, cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
         c->stats.rays_extension = st[ST_RAYS_EXT]; c->stats.rays_shadow_env = st[ST_RAYS_ENV]; c->stats.rays_shadow_light = st[ST_RAYS_LIGHT];
-        c->stats.nodes_visited = st[ST_NODES]; c->stats.tris_tested = st[ST_TRIS];
+        c->stats.nodes_visited = st[ST_NODES]; c->stats.tris_tested = st[ST_TRIS]; c->stats.key_evals = st[ST_KEYS];
         uint64_t hb = 0; for (uint32_t v : pc) hb += v;
         c->stats.hit_bounces = hb; c->stats.samples_done = s0;
     }

@@ -24,7 +24,7 @@
 namespace eleven {
 
 enum { CNT_CUR = 0, CNT_NEXT = 1, CNT_NEE = 2, CNT_WORK_TRACE = 3, CNT_WORK_SHADE = 4, CNT_WORK_CONNECT = 5, CNT_WORK_LIGHT = 6, CNT_COUNT = 16 };
-enum { ST_RAYS_EXT = 0, ST_RAYS_ENV = 1, ST_RAYS_LIGHT = 2, ST_NODES = 3, ST_TRIS = 4, ST_COUNT = 8 };
+enum { ST_RAYS_EXT = 0, ST_RAYS_ENV = 1, ST_RAYS_LIGHT = 2, ST_NODES = 3, ST_TRIS = 4, ST_KEYS = 5, ST_COUNT = 8 };
 
 struct WaveState {
     // per path (index = film index)
@@ -274,6 +274,13 @@ __global__ void __launch_bounds__(128) k_shade(WaveState W, const __grid_constan
                 W.rayD[pid] = make_float4(nr.d.x, nr.d.y, nr.d.z, 0.f);
                 W.depth[pid] = depth + 1u;
                 toNee = true;
+                if ((P.flags & ELEVEN_FLAG_SKIP_NULL_NEE) && S.lightCount == 0 && isfinite(pE) &&
+                    CE.x == 0.f && CE.y == 0.f && CE.z == 0.f && CB.x == 0.f && CB.y == 0.f && CB.z == 0.f) {
+                    // the MIS sum is w1*0 + 0 + w3*0 whatever the shadow ray finds (e.g. the environment sample lies below
+                    // the surface): no shadow ray, apply the throughput factor here
+                    W.thr[pid] = make_float4(thr.x * mulB.x, thr.y * mulB.y, thr.z * mulB.z, 0.f);
+                    toNee = false;
+                }
                 toNext = depth + 1u < P.maxBounces;
                 if ((P.flags & ELEVEN_FLAG_TERMINATE_DEAD_PATHS) && toNext) {
                     // throughput after this bounce is thr * mulB: exactly zero means no later bounce can contribute

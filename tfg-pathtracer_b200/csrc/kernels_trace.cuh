@@ -32,10 +32,10 @@ struct ExtendSink {
 };
 template <int MODE, bool COUNT>
 __global__ void __launch_bounds__(128) k_extend(const __grid_constant__ WaveState W, const __grid_constant__ DevScene S) {
-    TraceCounters tc; tc.nodes = 0; tc.tris = 0;
+    TraceCounters tc; tc.nodes = 0; tc.tris = 0; tc.keys = 0;
     ExtendSource src{W}; ExtendSink sink{W};
-    traceQueue<MODE, COUNT>(S, W.cnt[CNT_CUR], &W.cnt[CNT_WORK_TRACE], src, sink, tc);
-    if (COUNT) { atomicAdd(&W.stats[ST_NODES], (unsigned long long)tc.nodes); atomicAdd(&W.stats[ST_TRIS], (unsigned long long)tc.tris); }
+    traceQueue<MODE, COUNT, false>(S, W.cnt[CNT_CUR], &W.cnt[CNT_WORK_TRACE], src, sink, tc);
+    if (COUNT) { atomicAdd(&W.stats[ST_NODES], (unsigned long long)tc.nodes); atomicAdd(&W.stats[ST_TRIS], (unsigned long long)tc.tris); atomicAdd(&W.stats[ST_KEYS], (unsigned long long)tc.keys); }
 }
 
 // ---- MIS combination (shade, S/kernel.cu:351-357) --------------------------------------------------------------------------
@@ -85,10 +85,10 @@ struct ShadowEnvSink {
 };
 template <bool LIGHTS, bool COUNT>
 __global__ void __launch_bounds__(128) k_shadowEnv(const __grid_constant__ WaveState W, const __grid_constant__ DevScene S) {
-    TraceCounters tc; tc.nodes = 0; tc.tris = 0;
+    TraceCounters tc; tc.nodes = 0; tc.tris = 0; tc.keys = 0;
     ShadowEnvSource src{W}; ShadowEnvSink<LIGHTS> sink{W};
-    traceQueue<TRACE_ANY, COUNT>(S, W.cnt[CNT_NEE], &W.cnt[CNT_WORK_CONNECT], src, sink, tc);
-    if (COUNT) { atomicAdd(&W.stats[ST_NODES], (unsigned long long)tc.nodes); atomicAdd(&W.stats[ST_TRIS], (unsigned long long)tc.tris); }
+    traceQueue<TRACE_ANY, COUNT, false>(S, W.cnt[CNT_NEE], &W.cnt[CNT_WORK_CONNECT], src, sink, tc);
+    if (COUNT) { atomicAdd(&W.stats[ST_NODES], (unsigned long long)tc.nodes); atomicAdd(&W.stats[ST_TRIS], (unsigned long long)tc.tris); atomicAdd(&W.stats[ST_KEYS], (unsigned long long)tc.keys); }
 }
 
 // ---- point-light shadow rays -------------------------------------------------------------------------------------------------
@@ -124,10 +124,10 @@ struct ShadowLightSink {
 };
 template <int HITMODE, bool COUNT>
 __global__ void __launch_bounds__(128) k_shadowLight(const __grid_constant__ WaveState W, const __grid_constant__ DevScene S) {
-    TraceCounters tc; tc.nodes = 0; tc.tris = 0;
+    TraceCounters tc; tc.nodes = 0; tc.tris = 0; tc.keys = 0;
     ShadowLightSource<HITMODE> src{W}; ShadowLightSink<HITMODE> sink{W, S};
-    traceQueue<(HITMODE == ELEVEN_HIT_KEY ? TRACE_CLOSEST_KEY : TRACE_ANY), COUNT>(S, W.cnt[CNT_NEE], &W.cnt[CNT_WORK_LIGHT], src, sink, tc);
-    if (COUNT) { atomicAdd(&W.stats[ST_NODES], (unsigned long long)tc.nodes); atomicAdd(&W.stats[ST_TRIS], (unsigned long long)tc.tris); }
+    traceQueue<(HITMODE == ELEVEN_HIT_KEY ? TRACE_CLOSEST_KEY : TRACE_ANY), COUNT, false>(S, W.cnt[CNT_NEE], &W.cnt[CNT_WORK_LIGHT], src, sink, tc);
+    if (COUNT) { atomicAdd(&W.stats[ST_NODES], (unsigned long long)tc.nodes); atomicAdd(&W.stats[ST_TRIS], (unsigned long long)tc.tris); atomicAdd(&W.stats[ST_KEYS], (unsigned long long)tc.keys); }
 }
 
 // ---- plain ray batches (test hook / bench) -----------------------------------------------------------------------------------------
@@ -149,10 +149,10 @@ struct BatchSink {
 template <int MODE, bool COUNT>
 __global__ void __launch_bounds__(128) k_traceBatch(const float* __restrict__ rays, uint32_t n, ElevenHit* __restrict__ hits,
                                                   const __grid_constant__ DevScene S, uint32_t* workCounter, unsigned long long* stats) {
-    TraceCounters tc; tc.nodes = 0; tc.tris = 0;
+    TraceCounters tc; tc.nodes = 0; tc.tris = 0; tc.keys = 0;
     BatchSource src{rays}; BatchSink sink{hits};
-    traceQueue<MODE, COUNT>(S, n, workCounter, src, sink, tc);
-    if (COUNT && stats) { atomicAdd(&stats[ST_NODES], (unsigned long long)tc.nodes); atomicAdd(&stats[ST_TRIS], (unsigned long long)tc.tris); }
+    traceQueue<MODE, COUNT, true>(S, n, workCounter, src, sink, tc);
+    if (COUNT && stats) { atomicAdd(&stats[ST_NODES], (unsigned long long)tc.nodes); atomicAdd(&stats[ST_TRIS], (unsigned long long)tc.tris); atomicAdd(&stats[ST_KEYS], (unsigned long long)tc.keys); }
 }
 
 } // namespace eleven

@@ -33,12 +33,15 @@ struct LaneRay {
     uint32_t tag;              /* opaque to the engine (path id / ray index) */
 };
 
-// float(byte j of q) without the conversion pipe: 0x4B000000 | b is 2^23 + b exactly
-__device__ __forceinline__ float byteToFloat(uint32_t q4, uint32_t selector) {
+// float(byte j of q4) without the conversion pipe: 0x4B000000 | b is 2^23 + b exactly (one PRMT + one FADD).
+// (Folding the subtraction into the FMA constant saves the FADD but loses up to 1/512 of a cell crossing time in
+// ABSOLUTE t, which is not small against the other axes' planes when the ray is nearly parallel to an axis: measured
+// false negatives on rays through box corners, so the exact form stays.)
+__device__ __forceinline__ float byteMagic(uint32_t q4, uint32_t selector) {
     return __uint_as_float(__byte_perm(q4, 0x4B000000u, selector)) - 8388608.0f;
 }
 
-template <int MODE, bool COUNT, class Source, class Sink>
+template <int MODE, bool COUNT, bool NEED_KEY, class Source, class Sink>
 __device__ __forceinline__ void traceQueue(const DevScene& S, uint32_t n, uint32_t* workCounter, Source& src, Sink& sink, TraceCounters& tc) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t FULL = 0xffffffffu;
@@ -48,7 +51,8 @@ __device__ __forceinline__ void traceQueue(const DevScene& S, uint32_t n, uint32
     LaneRay lr; lr.tag = 0; lr.tmaxAny = INFINITY; lr.ray.o = f3(0.f); lr.ray.d = f3(0.f, 0.f, 1.f);
     float idx = 0.f, idy = 0.f, idz = 0.f, dx = 1.f, dy = 1.f, dz = 1.f;
     uint32_t octinv4 = 0;
-    float slack = 0.f, tcull = INFINITY, bestKey = INFINITY;
+    float slack = 0.f, epsRay = 0.f, tcull = INFINITY, bestLo = INFINITY, bestHi = INFINITY;   // [bestLo, bestHi] brackets the best key
+    bool bestExact = false;
     HitRec best; best.tri = -1; best.t = best.u = best.v = best.key = 0.f;
     uint2 ngroup = make_uint2(0u, 0u), tgroup = make_uint2(0u, 0u);
     uint2 stack[EL_STACK];
@@ -74,9 +78,10 @@ __device__ __forceinline__ void traceQueue(const DevScene& S, uint32_t n, uint32
                     idx = 1.0f / dx; idy = 1.0f / dy; idz = 1.0f / dz;
                     octinv4 = ((dx >= 0.f ? 4u : 0u) | (dy >= 0.f ? 2u : 0u) | (dz >= 0.f ? 1u : 0u)) * 0x01010101u;
                     const F3 o = lr.ray.o;
-                    slack = (MODE == TRACE_CLOSEST_KEY) ? S.keySlack + 4e-6f * (fabsf(o.x) + fabsf(o.y) + fabsf(o.z)) : 0.f;
+                    epsRay = 4e-6f * (fabsf(o.x) + fabsf(o.y) + fabsf(o.z));
+                    slack = (MODE == TRACE_CLOSEST_KEY) ? S.keySlack + epsRay : 0.f;
                     tcull = (MODE == TRACE_ANY) ? lr.tmaxAny : INFINITY;
-                    bestKey = INFINITY;
+                    bestLo = bestHi = INFINITY; bestExact = false;
                     best.tri = -1; best.t = best.u = best.v = best.key = 0.f;
                     ngroup = make_uint2(0u, S.nodeCount ? 0x80000000u : 0u);
                     tgroup = make_uint2(0u, 0u);
@@ -93,7 +98,14 @@ __device__ __forceinline__ void traceQueue(const DevScene& S, uint32_t n, uint32
         // ---- every active lane must own a node group with pending children or pending triangles; else pop / finish ---
         if (active && tgroup.y == 0u && ngroup.y <= 0x00ffffffu) {
             if (sp > 0) ngroup = stack[--sp];
-            else { sink.done(lr, best); active = false; }
+            else {
+                if (MODE == TRACE_CLOSEST_KEY && NEED_KEY && best.tri >= 0 && !bestExact) {
+                    const TriGeom g = loadTriGeom(S.shadeTris, best.tri);
+                    F3 sn;
+                    best.key = hitKey(lr.ray, hitPosition(lr.ray, g, best.t, best.u, best.v, sn));
+                }
+                sink.done(lr, best); active = false;
+            }
         }
 
         // ---- node phase: one node (8 quantised child boxes) ------------------------------------------------------------
@@ -107,7 +119,11 @@ __device__ __forceinline__ void traceQueue(const DevScene& S, uint32_t n, uint32
                 if (ngroup.y > 0x00ffffffu) stack[sp++] = ngroup;
                 const uint32_t slot = (bit - 24u) ^ octinv;
                 const uint32_t rank = __popc(imask & ~(0xffffffffu << slot));
-                const float4* np = S.nodes + (size_t)(ngroup.x + rank) * 5;
+                const uint32_t nodeIndex = ngroup.x + rank;
+                const float4* np = S.nodes + (size_t)nodeIndex * 5;
+                // KEY mode: a triangle below this node can only win if t - shift - e <= bestHi, and its shift is bounded
+                // by this node's subtree maximum: cull the children with that LOCAL slack instead of the scene maximum
+                const float tcullNode = (MODE == TRACE_CLOSEST_KEY) ? (bestHi + __ldg(S.nodeSlack + nodeIndex) + epsRay) * 1.00001f : tcull;
                 const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
                 if (COUNT) tc.nodes++;
                 const F3 o = lr.ray.o;
@@ -132,13 +148,13 @@ __device__ __forceinline__ void traceQueue(const DevScene& S, uint32_t n, uint32
                     const uint32_t zmin = dz < 0.f ? qhiz : qloz, zmax = dz < 0.f ? qloz : qhiz;
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
-                        const uint32_t sel = 0x7540u + (uint32_t)j;
-                        const float tminx = fmaf(byteToFloat(xmin, sel), ax, ox), tmaxx = fmaf(byteToFloat(xmax, sel), ax, ox);
-                        const float tminy = fmaf(byteToFloat(ymin, sel), ay, oy), tmaxy = fmaf(byteToFloat(ymax, sel), ay, oy);
-                        const float tminz = fmaf(byteToFloat(zmin, sel), az, oz), tmaxz = fmaf(byteToFloat(zmax, sel), az, oz);
+                        const uint32_t sel = 0x7540u + (uint32_t)j;              // bytes: q_j, 0x00, 0x00, 0x4B
+                        const float tminx = fmaf(byteMagic(xmin, sel), ax, ox), tmaxx = fmaf(byteMagic(xmax, sel), ax, ox);
+                        const float tminy = fmaf(byteMagic(ymin, sel), ay, oy), tmaxy = fmaf(byteMagic(ymax, sel), ay, oy);
+                        const float tminz = fmaf(byteMagic(zmin, sel), az, oz), tmaxz = fmaf(byteMagic(zmax, sel), az, oz);
                         const float cmin = fmaxf(fmaxf(tminx, tminy), fmaxf(tminz, 0.f));
-                        const float cmax = fminf(fminf(tmaxx, tmaxy), fminf(tmaxz, tcull));
-                        if (cmin * 0.9999995f <= cmax * 1.0000005f) {
+                        const float cmax = fminf(fminf(tmaxx, tmaxy), fminf(tmaxz, tcullNode));
+                        if (cmin <= cmax * 1.000001f) {          // relative slack for the rounding of the fused distances
                             const uint32_t cb = (childBits4 >> (8 * j)) & 0xffu, bi = (bitIndex4 >> (8 * j)) & 0xffu;
                             hitmask |= cb << bi;
                         }
@@ -173,14 +189,31 @@ __device__ __forceinline__ void traceQueue(const DevScene& S, uint32_t n, uint32
                             best.tri = tri; best.t = t; best.u = u; best.v = v; best.key = t; tcull = t;
                         }
                     } else {
-                        if (t <= tcull) {
+                        // Closest by the reference KEY = |hit.position - origin| (S/BVH.hpp:170), evaluated LAZILY: the key
+                        // of a candidate lies in [t - s - e, t + s + e] (s = this triangle's shadow-terminator shift bound
+                        // from the builder, e = rounding allowance), so the exact key (5 more 128-bit loads + ~120 flops on
+                        // a divergent path) is only computed when two candidates' brackets overlap.
+                        const float sT = c.w;
+                        const float e = fmaf(t, 4e-6f, epsRay);
+                        const float cLo = t - sT - e, cHi = t + sT + e;
+                        if (best.tri < 0 || cHi < bestLo) {            // certainly closer than the current best
+                            best.tri = tri; best.t = t; best.u = u; best.v = v; bestLo = cLo; bestHi = cHi; bestExact = false;
+                            tcull = (bestHi + slack) * 1.00001f;       // a later triangle with t beyond this cannot have a smaller key
+                        } else if (cLo <= bestHi) {                      // brackets overlap: decide on exact keys
+                            if (COUNT) tc.keys++;
+                            if (!bestExact) {
+                                const TriGeom gb = loadTriGeom(S.shadeTris, best.tri);
+                                F3 snb;
+                                best.key = hitKey(lr.ray, hitPosition(lr.ray, gb, best.t, best.u, best.v, snb));
+                                bestLo = bestHi = best.key; bestExact = true;
+                            }
                             const TriGeom g = loadTriGeom(S.shadeTris, tri);
                             F3 sn;
                             const float key = hitKey(lr.ray, hitPosition(lr.ray, g, t, u, v, sn));
-                            if (best.tri < 0 || key < bestKey || (key == bestKey && tri < best.tri)) {
-                                best.tri = tri; best.t = t; best.u = u; best.v = v; best.key = key; bestKey = key;
-                                tcull = fmaf(key, 1.000004f, slack);
+                            if (key < best.key || (key == best.key && tri < best.tri)) {
+                                best.tri = tri; best.t = t; best.u = u; best.v = v; best.key = key; bestLo = bestHi = key;
                             }
+                            tcull = (bestHi + slack) * 1.00001f;
                         }
                     }
                 }

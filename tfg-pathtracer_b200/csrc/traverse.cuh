@@ -74,132 +74,10 @@ __device__ __forceinline__ float hitKey(const Ray& r, F3 pos) { return ex::lengt
 // ---- BVH8 traversal -------------------------------------------------------------------------------
 enum { TRACE_CLOSEST_KEY = 0, TRACE_CLOSEST_T = 1, TRACE_ANY = 2 };
 
-struct TraceCounters { uint32_t nodes, tris; };
+struct TraceCounters { uint32_t nodes, tris, keys; };
 
 #define EL_STACK 40
 
 __device__ __forceinline__ uint32_t extractByte(uint32_t x, uint32_t i) { return (x >> (i * 8)) & 0xffu; }
-
-/* Traverses the BVH8.  MODE: closest by reference key, closest by t, or any hit with t in [0, tmax).
- * `tmax` bounds t for TRACE_ANY (use INFINITY for "any hit at all").  Returns true when something was hit. */
-template <int MODE, bool COUNT>
-__device__ __forceinline__ bool traverse(const DevScene& S, const Ray& ray, float tmaxAny, HitRec& best, TraceCounters* cnt) {
-    best.tri = -1; best.t = 0.f; best.u = 0.f; best.v = 0.f; best.key = 0.f;
-    if (S.nodeCount == 0) return false;
-
-    const F3 o = ray.o, d = ray.d;
-    // 1/d with |d| clamped away from zero: keeps every slab distance finite (no inf*0 NaNs), still conservative
-    const float dx = fabsf(d.x) > 1e-20f ? d.x : copysignf(1e-20f, d.x);
-    const float dy = fabsf(d.y) > 1e-20f ? d.y : copysignf(1e-20f, d.y);
-    const float dz = fabsf(d.z) > 1e-20f ? d.z : copysignf(1e-20f, d.z);
-    const float idx = 1.0f / dx, idy = 1.0f / dy, idz = 1.0f / dz;
-    const uint32_t octinv = (dx >= 0.f ? 4u : 0u) | (dy >= 0.f ? 2u : 0u) | (dz >= 0.f ? 1u : 0u);
-    const uint32_t octinv4 = octinv * 0x01010101u;
-
-    // cull bound on t: for the key mode a candidate with MT parameter t has key >= t - slack
-    const float epsRay = 4e-6f * (fabsf(o.x) + fabsf(o.y) + fabsf(o.z));
-    const float slack = (MODE == TRACE_CLOSEST_KEY) ? S.keySlack + epsRay : 0.f;
-    float tcull = (MODE == TRACE_ANY) ? tmaxAny : INFINITY;
-    float bestKey = INFINITY;
-
-    uint2 stack[EL_STACK];
-    int sp = 0;
-    uint2 ngroup = make_uint2(0u, 0x80000000u);     // root: "child" bit 31 of a virtual parent with childBase 0
-    uint2 tgroup = make_uint2(0u, 0u);
-
-    for (;;) {
-        if (ngroup.y > 0x00ffffffu) {
-            // pop the nearest pending child of the current node group (root: virtual parent, imask 0 -> index 0)
-            const uint32_t imask = ngroup.y;
-            const uint32_t bit = 31u - __clz(ngroup.y);
-            ngroup.y &= ~(1u << bit);
-            if (ngroup.y > 0x00ffffffu) { stack[sp++] = ngroup; }
-            const uint32_t slot = (bit - 24u) ^ octinv;
-            const uint32_t rank = __popc(imask & ~(0xffffffffu << slot));
-            const uint32_t nodeIndex = ngroup.x + rank;
-            const float4* np = S.nodes + (size_t)nodeIndex * 5;
-            const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
-            if (COUNT) cnt->nodes++;
-
-            const uint32_t eim = __float_as_uint(n0.w);
-            const float ax = __uint_as_float((eim & 0xffu) << 23) * idx;
-            const float ay = __uint_as_float(((eim >> 8) & 0xffu) << 23) * idy;
-            const float az = __uint_as_float(((eim >> 16) & 0xffu) << 23) * idz;
-            const float ox = (n0.x - o.x) * idx, oy = (n0.y - o.y) * idy, oz = (n0.z - o.z) * idz;
-
-            ngroup.x = __float_as_uint(n1.x);
-            tgroup.x = __float_as_uint(n1.y);
-            tgroup.y = 0;
-            uint32_t hitmask = 0;
-#pragma unroll
-            for (int half = 0; half < 2; half++) {
-                const uint32_t meta4 = __float_as_uint(half ? n1.w : n1.z);
-                const uint32_t isInner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
-                const uint32_t innerMask4 = (isInner4 >> 4) * 0xffu;
-                const uint32_t bitIndex4 = (meta4 ^ (octinv4 & innerMask4)) & 0x1f1f1f1fu;
-                const uint32_t childBits4 = (meta4 >> 5) & 0x07070707u;
-                const uint32_t qlox = __float_as_uint(half ? n2.y : n2.x), qloy = __float_as_uint(half ? n2.w : n2.z);
-                const uint32_t qloz = __float_as_uint(half ? n3.y : n3.x), qhix = __float_as_uint(half ? n3.w : n3.z);
-                const uint32_t qhiy = __float_as_uint(half ? n4.y : n4.x), qhiz = __float_as_uint(half ? n4.w : n4.z);
-                const uint32_t xmin = dx < 0.f ? qhix : qlox, xmax = dx < 0.f ? qlox : qhix;
-                const uint32_t ymin = dy < 0.f ? qhiy : qloy, ymax = dy < 0.f ? qloy : qhiy;
-                const uint32_t zmin = dz < 0.f ? qhiz : qloz, zmax = dz < 0.f ? qloz : qhiz;
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const float tminx = fmaf((float)extractByte(xmin, j), ax, ox), tmaxx = fmaf((float)extractByte(xmax, j), ax, ox);
-                    const float tminy = fmaf((float)extractByte(ymin, j), ay, oy), tmaxy = fmaf((float)extractByte(ymax, j), ay, oy);
-                    const float tminz = fmaf((float)extractByte(zmin, j), az, oz), tmaxz = fmaf((float)extractByte(zmax, j), az, oz);
-                    const float cmin = fmaxf(fmaxf(tminx, tminy), fmaxf(tminz, 0.f));
-                    const float cmax = fminf(fminf(tmaxx, tmaxy), fminf(tmaxz, tcull));
-                    // relative padding makes the test robust against rounding in the fused slab distances
-                    if (cmin * 0.9999995f <= cmax * 1.0000005f) {
-                        const uint32_t cb = extractByte(childBits4, j), bi = extractByte(bitIndex4, j);
-                        hitmask |= cb << bi;
-                    }
-                }
-            }
-            ngroup.y = (hitmask & 0xff000000u) | (eim >> 24);
-            tgroup.y = hitmask & 0x00ffffffu;
-        } else {
-            tgroup = ngroup;
-            ngroup = make_uint2(0u, 0u);
-        }
-
-        while (tgroup.y != 0) {
-            const uint32_t ti = 31u - __clz(tgroup.y);
-            tgroup.y &= ~(1u << ti);
-            const float4* tp = S.slots + (size_t)(tgroup.x + ti) * 3;
-            const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
-            if (COUNT) cnt->tris++;
-            float t, u, v;
-            if (mollerTrumbore(ray, f3(a.x, a.y, a.z), f3(a.w, b.x, b.y), f3(b.z, b.w, c.x), t, u, v)) {
-                const int tri = __float_as_int(c.y);
-                if (MODE == TRACE_ANY) {
-                    if (t < tmaxAny) { best.tri = tri; best.t = t; best.u = u; best.v = v; best.key = t; return true; }
-                } else if (MODE == TRACE_CLOSEST_T) {
-                    if (best.tri < 0 || t < best.t || (t == best.t && tri < best.tri)) {
-                        best.tri = tri; best.t = t; best.u = u; best.v = v; best.key = t; tcull = t;
-                    }
-                } else {
-                    if (t <= tcull) {
-                        TriGeom g = loadTriGeom(S.shadeTris, tri);
-                        F3 sn;
-                        const float key = hitKey(ray, hitPosition(ray, g, t, u, v, sn));
-                        if (best.tri < 0 || key < bestKey || (key == bestKey && tri < best.tri)) {
-                            best.tri = tri; best.t = t; best.u = u; best.v = v; best.key = key; bestKey = key;
-                            tcull = fmaf(key, 1.000004f, slack);
-                        }
-                    }
-                }
-            }
-        }
-
-        if (ngroup.y <= 0x00ffffffu) {
-            if (sp == 0) break;
-            ngroup = stack[--sp];
-        }
-    }
-    return best.tri >= 0;
-}
 
 } // namespace eleven

@@ -16,10 +16,14 @@ ap.add_argument("--tex", type=int, default=4096)
 ap.add_argument("--width", type=int, default=1920)
 ap.add_argument("--height", type=int, default=1080)
 ap.add_argument("--mode", default="fast")
+ap.add_argument("--hit-mode", default="key")
 a = ap.parse_args()
 flat, _ = bench.get_scene(a, need_dir=False)
 sc = S.load_flat(flat)
-r = R.Renderer(**(R.FAST if a.mode == "fast" else R.PARITY)).render_setup(sc)
+cfg = dict(R.FAST if a.mode == "fast" else R.PARITY)
+if a.hit_mode == "min_t":
+    cfg["hit_mode"] = R.HIT_MIN_T
+r = R.Renderer(**cfg).render_setup(sc)
 r.render_cuda(a.spp)
 st = r.stats()
 print({k: st[k] for k in ("render_ms", "rays_extension", "rays_shadow_env", "kernel_launches")})
