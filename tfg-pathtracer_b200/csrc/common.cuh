@@ -113,6 +113,7 @@ struct DevScene {
     const float* nodeSlack;       // per node: max shadow-terminator shift bound in its subtree
     const float4* shadeTris;      // 9 x float4 per triangle, original index order
     const int32_t* objectMaterial;
+    const int32_t* triMaterial;   // per triangle (original index): material id, for the material-sorted shading queue
     const DevMaterial* materials;
     const DevTex* textures;
     const float* lut;             // [2][256]: sRGB (gamma 2.2f) then linear (gamma 1.0f) fastPow tables

@@ -179,6 +179,7 @@ static int allocWave(ElevenCtx* c) {
     A(depth, uint32_t) A(rng, Xorwow)
     A(neeEnvDir, float4) A(neeEnvC, float4) A(neeLightDir, float4) A(neeLightC, float4) A(neeBrdfC, float4) A(neePos, float4) A(neeThrMul, float4)
     A(qCur, uint32_t) A(qNext, uint32_t) A(qNee, uint32_t)
+    if ((rc = devAlloc(c->waveAllocs, &W.qBucket, n * EL_BUCKETS))) return rc;
     A(filmBeauty, float4) A(filmNormal, float4) A(filmTangent, float4) A(filmBitangent, float4) A(filmCount, uint32_t) A(pathCount, uint32_t)
 #undef A
     if ((rc = devAlloc(c->waveAllocs, &W.cnt, CNT_COUNT))) return rc;
@@ -249,6 +250,7 @@ extern "C" int eleven_scene_upload(ElevenCtx* c, const ElevenSceneDesc* d) {
         if ((rc = devUpload(c->sceneAllocs, &S.shadeTris, (const float4*)st.data(), (size_t)d->triCount * 9))) return rc;
     }
     if ((rc = devUpload(c->sceneAllocs, &S.objectMaterial, d->objectMaterial, d->objectCount))) return rc;
+    if ((rc = devUpload(c->sceneAllocs, &S.triMaterial, triMat.data(), triMat.size()))) return rc;
     static_assert(sizeof(DevMaterial) == sizeof(ElevenMaterial), "material layout");
     for (uint32_t i = 0; i < d->materialCount; i++) {
         const ElevenMaterial& m = d->materials[i];
@@ -389,6 +391,7 @@ extern "C" int eleven_render(ElevenCtx* c, int spp) {
         for (uint32_t b = 0; b < c->cfg.max_bounces; b++) {
             if (count) launchExtend<true>(c, gridPersist); else launchExtend<false>(c, gridPersist);
             mark(0);
+            k_classify<<<gridPersist, 128, 0, c->stream>>>(c->W, c->scene);
             k_shade<<<gridPersist, 128, 0, c->stream>>>(c->W, c->scene, c->P);
             mark(1);
             k_advance<<<1, 32, 0, c->stream>>>(c->W, c->scene.lightCount, 0);
@@ -399,7 +402,7 @@ extern "C" int eleven_render(ElevenCtx* c, int spp) {
             mark(3);
             c->stats.extend_launches += 1;
             std::swap(c->W.qCur, c->W.qNext);      // kernel arguments are captured at launch: the next bounce reads the list just written
-            c->stats.kernel_launches += 4;
+            c->stats.kernel_launches += 5;
         }
         k_accumulate<<<gridPix, 256, 0, c->stream>>>(c->W);
         mark(3);

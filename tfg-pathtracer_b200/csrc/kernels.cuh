@@ -23,7 +23,9 @@
 
 namespace eleven {
 
-enum { CNT_CUR = 0, CNT_NEXT = 1, CNT_NEE = 2, CNT_WORK_TRACE = 3, CNT_WORK_SHADE = 4, CNT_WORK_CONNECT = 5, CNT_WORK_LIGHT = 6, CNT_COUNT = 16 };
+enum { CNT_CUR = 0, CNT_NEXT = 1, CNT_NEE = 2, CNT_WORK_TRACE = 3, CNT_WORK_SHADE = 4, CNT_WORK_CONNECT = 5, CNT_WORK_LIGHT = 6, CNT_WORK_CLASSIFY = 7,
+       CNT_BUCKET0 = 8, CNT_COUNT = 16 };
+enum { EL_BUCKETS = 8, EL_MISS_BUCKET = 7 };   // shading queue buckets: materials 0..5, 6 = all further materials, 7 = escaped rays
 enum { ST_RAYS_EXT = 0, ST_RAYS_ENV = 1, ST_RAYS_LIGHT = 2, ST_NODES = 3, ST_TRIS = 4, ST_KEYS = 5, ST_COUNT = 8 };
 
 struct WaveState {
@@ -44,6 +46,7 @@ struct WaveState {
     float4* neeThrMul;                   // f*cos/p_b (throughput update factor)
     // queues
     uint32_t* qCur; uint32_t* qNext; uint32_t* qNee;
+    uint32_t* qBucket;                   // EL_BUCKETS x nPixels: the shading queue, sorted by material (k_classify)
     uint32_t* cnt;                       // CNT_*
     unsigned long long* stats;           // ST_*
     // film: per-pixel sums + counts
@@ -134,9 +137,38 @@ __global__ void __launch_bounds__(256) k_raygen(WaveState W, const __grid_consta
     if (i == 0) {
         W.cnt[CNT_CUR] = W.nPixels; W.cnt[CNT_NEXT] = 0u; W.cnt[CNT_NEE] = 0u;
         W.cnt[CNT_WORK_TRACE] = 0u; W.cnt[CNT_WORK_SHADE] = 0u; W.cnt[CNT_WORK_CONNECT] = 0u; W.cnt[CNT_WORK_LIGHT] = 0u;
+        W.cnt[CNT_WORK_CLASSIFY] = 0u;
+        for (int b = 0; b < EL_BUCKETS; b++) W.cnt[CNT_BUCKET0 + b] = 0u;
     }
 }
 
+
+// ---- classify: bucket the traced paths by material (escaped rays last) for a coherent shading queue ------------------
+__global__ void __launch_bounds__(128) k_classify(WaveState W, const __grid_constant__ DevScene S) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t n = W.cnt[CNT_CUR];
+    for (;;) {
+        const uint32_t base = warpFetch(&W.cnt[CNT_WORK_CLASSIFY], lane);
+        if (base >= n) break;
+        const uint32_t qi = base + lane;
+        const bool valid = qi < n;
+        uint32_t pid = 0, bucket = EL_MISS_BUCKET;
+        if (valid) {
+            pid = W.qCur[qi];
+            const int tri = __float_as_int(W.hit[pid].x);
+            if (tri >= 0) bucket = min((uint32_t)__ldg(S.triMaterial + tri), (uint32_t)(EL_MISS_BUCKET - 1));
+        }
+        const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+        if (valid) {
+            const uint32_t peers = __match_any_sync(vmask, bucket);
+            const uint32_t leader = __ffs(peers) - 1u;
+            uint32_t pos = 0;
+            if (lane == leader) pos = atomicAdd(&W.cnt[CNT_BUCKET0 + bucket], (uint32_t)__popc(peers));
+            pos = __shfl_sync(peers, pos, leader);
+            W.qBucket[(size_t)bucket * W.nPixels + pos + __popc(peers & ((1u << lane) - 1u))] = pid;
+        }
+    }
+}
 
 // ---- shade -----------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void appendWarpAggregated(uint32_t* q, uint32_t* counter, bool pred, uint32_t value) {
@@ -152,7 +184,13 @@ __device__ __forceinline__ void appendWarpAggregated(uint32_t* q, uint32_t* coun
 
 __global__ void __launch_bounds__(128) k_shade(WaveState W, const __grid_constant__ DevScene S, const __grid_constant__ RenderParams P) {
     const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t n = W.cnt[CNT_CUR];
+    // the shading queue is the concatenation of the material buckets written by k_classify: consecutive entries share a
+    // material (same textures, same branches), escaped rays come last
+    uint32_t prefix[EL_BUCKETS + 1];
+    prefix[0] = 0;
+#pragma unroll
+    for (int b = 0; b < EL_BUCKETS; b++) prefix[b + 1] = prefix[b] + W.cnt[CNT_BUCKET0 + b];
+    const uint32_t n = prefix[EL_BUCKETS];
     for (;;) {
         const uint32_t base = warpFetch(&W.cnt[CNT_WORK_SHADE], lane);
         if (base >= n) break;
@@ -160,7 +198,10 @@ __global__ void __launch_bounds__(128) k_shade(WaveState W, const __grid_constan
         bool toNee = false, toNext = false;
         uint32_t pid = 0;
         if (qi < n) {
-            pid = W.qCur[qi];
+            uint32_t b = 0;
+#pragma unroll
+            for (int k = 1; k < EL_BUCKETS; k++) b += (qi >= prefix[k]) ? 1u : 0u;
+            pid = W.qBucket[(size_t)b * W.nPixels + (qi - prefix[b])];
             const float4 hv = W.hit[pid];
             const int tri = __float_as_int(hv.x);
             const float4 o4 = W.rayO[pid], d4 = W.rayD[pid];
@@ -305,7 +346,8 @@ __global__ void k_advance(WaveState W, uint32_t lights, int phase) {
         W.cnt[CNT_WORK_CONNECT] = 0u; W.cnt[CNT_WORK_LIGHT] = 0u;
     } else {                     // after connect: next bounce
         W.cnt[CNT_CUR] = W.cnt[CNT_NEXT]; W.cnt[CNT_NEXT] = 0u; W.cnt[CNT_NEE] = 0u;
-        W.cnt[CNT_WORK_TRACE] = 0u; W.cnt[CNT_WORK_SHADE] = 0u;
+        W.cnt[CNT_WORK_TRACE] = 0u; W.cnt[CNT_WORK_SHADE] = 0u; W.cnt[CNT_WORK_CLASSIFY] = 0u;
+        for (int b = 0; b < EL_BUCKETS; b++) W.cnt[CNT_BUCKET0 + b] = 0u;
     }
 }
 
