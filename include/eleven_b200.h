@@ -64,6 +64,8 @@ typedef struct ElevenConfig {
 #define ELEVEN_FLAG_TERMINATE_DEAD_PATHS 1u  /* stop paths whose throughput is exactly 0 (only legal with RNG_FAST) */
 #define ELEVEN_FLAG_COUNTERS             2u  /* count nodes/triangles visited per ray (slower; for the roofline)    */
 #define ELEVEN_FLAG_TIME_KERNELS         4u  /* CUDA-event timing around every pipeline stage (ElevenStats *_ms)   */
+#define ELEVEN_FLAG_FAST_MATH           16u  /* shading with MUFU reciprocal/rsqrt/sin/cos/log2/exp2 and float intermediates, like the
+                                              * reference's shipping -use_fast_math build; geometry (t,u,v,key) stays bit-exact */
 #define ELEVEN_FLAG_SKIP_NULL_NEE        8u  /* no env shadow ray when its contribution is 0 whatever it hits (no point
                                               * lights, no emission, BRDF 0 towards the sample): same image, fewer rays */
 

@@ -20,7 +20,7 @@ PASS_BEAUTY, PASS_DENOISE, PASS_NORMAL, PASS_TANGENT, PASS_BITANGENT = range(5)
 RNG_REFERENCE, RNG_FAST = 0, 1
 ENV_CDF, ENV_ALIAS = 0, 1
 HIT_KEY, HIT_MIN_T = 0, 1
-FLAG_TERMINATE_DEAD_PATHS, FLAG_COUNTERS, FLAG_TIME_KERNELS, FLAG_SKIP_NULL_NEE = 1, 2, 4, 8
+FLAG_TERMINATE_DEAD_PATHS, FLAG_COUNTERS, FLAG_TIME_KERNELS, FLAG_SKIP_NULL_NEE, FLAG_FAST_MATH = 1, 2, 4, 8, 16
 
 
 class ElevenConfig(C.Structure):

@@ -374,6 +374,7 @@ extern "C" int eleven_render(ElevenCtx* c, int spp) {
     const int gridPersist = c->numSMs * 8;             // 148 SMs x 8 CTAs of 128 threads: a multiple of the SM count
     const bool count = (c->cfg.flags & ELEVEN_FLAG_COUNTERS) != 0;
     const bool timeK = (c->cfg.flags & ELEVEN_FLAG_TIME_KERNELS) != 0;
+    const bool fastMath = (c->cfg.flags & ELEVEN_FLAG_FAST_MATH) != 0;
     // stage timing: one event after every stage launch; stage i spans events [i, i+1)
     std::vector<int> evKind;                      // 0 extend, 1 shade, 2 connect, 3 other
     size_t evUsed = 0;
@@ -386,13 +387,15 @@ extern "C" int eleven_render(ElevenCtx* c, int spp) {
     mark(3);
     for (int s = 0; s < spp; s++) {
         c->P.sampleIndex = c->cfg.sample_offset + c->samplesRendered * c->cfg.sample_stride;
-        k_raygen<<<gridPix, 256, 0, c->stream>>>(c->W, c->scene, c->P);
+        if (fastMath) k_raygen<true><<<gridPix, 256, 0, c->stream>>>(c->W, c->scene, c->P);
+        else k_raygen<false><<<gridPix, 256, 0, c->stream>>>(c->W, c->scene, c->P);
         mark(3);
         for (uint32_t b = 0; b < c->cfg.max_bounces; b++) {
             if (count) launchExtend<true>(c, gridPersist); else launchExtend<false>(c, gridPersist);
             mark(0);
             k_classify<<<gridPersist, 128, 0, c->stream>>>(c->W, c->scene);
-            k_shade<<<gridPersist, 128, 0, c->stream>>>(c->W, c->scene, c->P);
+            if (fastMath) k_shade<true><<<gridPersist, 128, 0, c->stream>>>(c->W, c->scene, c->P);
+            else k_shade<false><<<gridPersist, 128, 0, c->stream>>>(c->W, c->scene, c->P);
             mark(1);
             k_advance<<<1, 32, 0, c->stream>>>(c->W, c->scene.lightCount, 0);
             mark(3);

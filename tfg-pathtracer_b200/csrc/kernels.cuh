@@ -110,6 +110,7 @@ __device__ __forceinline__ uint4 fastBits(const RenderParams& P, uint32_t pixel,
 }
 
 // ---- raygen ------------------------------------------------------------------------------------------------
+template <bool FM>
 __global__ void __launch_bounds__(256) k_raygen(WaveState W, const __grid_constant__ DevScene S, const __grid_constant__ RenderParams P) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= W.nPixels) return;
@@ -125,7 +126,7 @@ __global__ void __launch_bounds__(256) k_raygen(WaveState W, const __grid_consta
         r1 = u32ToUniform(a.x); r2 = u32ToUniform(a.y); r3 = u32ToUniform(a.z); r4 = u32ToUniform(a.w);
         r5 = S.cam.bokeh ? u32ToUniform(fastBits(P, i, 1u).x) : 0.5f;
     }
-    const Ray ray = cameraRay(S.cam, P.rot, x, y, r1, r2, r3, r4, r5);
+    const Ray ray = cameraRay<FM>(S.cam, P.rot, x, y, r1, r2, r3, r4, r5);
     W.rayO[i] = make_float4(ray.o.x, ray.o.y, ray.o.z, 0.f);
     W.rayD[i] = make_float4(ray.d.x, ray.d.y, ray.d.z, 0.f);
     W.thr[i] = make_float4(1.f, 1.f, 1.f, 0.f);
@@ -182,6 +183,7 @@ __device__ __forceinline__ void appendWarpAggregated(uint32_t* q, uint32_t* coun
     q[base + __popc(mask & ((1u << lane) - 1u))] = value;
 }
 
+template <bool FM>
 __global__ void __launch_bounds__(128) k_shade(WaveState W, const __grid_constant__ DevScene S, const __grid_constant__ RenderParams P) {
     const uint32_t lane = threadIdx.x & 31u;
     // the shading queue is the concatenation of the material buckets written by k_classify: consecutive entries share a
@@ -233,7 +235,7 @@ __global__ void __launch_bounds__(128) k_shade(WaveState W, const __grid_constan
                 const int objectID = __float_as_int(q8.z);
                 const DevMaterial& m = S.materials[S.objectMaterial[objectID]];
                 HitData hd;
-                generateHitData(S, m, hd, N, T, B, tUV.x, tUV.y);
+                generateHitData<FM>(S, m, hd, N, T, B, tUV.x, tUV.y);
 
                 // --- random numbers: 3 for the bounce, 3 for shade of which only the first is used
                 float b1, b2, b3, s1; uint32_t aliasBitsA = 0, aliasBitsB = 0, lightBits = 0;
@@ -248,10 +250,10 @@ __global__ void __launch_bounds__(128) k_shade(WaveState W, const __grid_constan
                     const uint4 c = fastBits(P, pid, 3u + 2u * depth);
                     aliasBitsA = c.x; aliasBitsB = c.y; lightBits = c.z;
                 }
-                const BrdfFrame bf = makeBrdfFrame(hd, ray.d);
-                const F3 L = disneySample(hd, bf, b1, b2, b3);
-                const F3 fB = disneyEval(hd, bf, L);
-                const float pB = disneyPdf(hd, bf, L);
+                const BrdfFrame bf = makeBrdfFrame<FM>(hd, ray.d);
+                const F3 L = disneySample<FM>(hd, bf, b1, b2, b3);
+                const F3 fB = disneyEval<FM>(hd, bf, L);
+                const float pB = disneyPdf<FM>(hd, bf, L);
 
                 // --- environment NEE set-up (hdriLight, S/kernel.cu:236-256) -----------------------------------
                 const int EW = S.hdri.width, EH = S.hdri.height;
@@ -267,13 +269,13 @@ __global__ void __launch_bounds__(128) k_shade(WaveState W, const __grid_constan
                 const float sx = (float)(texel % EW), sy = (float)(texel / EW);
                 const float nu = sx / (float)EW, nv = sy / (float)EH;
                 float iu, iv; inverseTransformUV(S.hdri, nu, nv, iu, iv);
-                const F3 rsm = normalized(reverseSphericalMapping(iu, iv));
+                const F3 rsm = M<FM>::normalized(reverseSphericalMapping<FM>(iu, iv));
                 const F3 wE = f3(-rsm.x, -rsm.y, -rsm.z);
                 const float4 ev = envTexelRaw(S.hdri, (int)(iu * EW), (int)(iv * EH));
-                const float pE = hdriPdf(S, (int)(iu * EW), (int)(iv * EH));
-                const F3 fE = disneyEval(hd, bf, wE);
+                const float pE = hdriPdf<FM>(S, (int)(iu * EW), (int)(iv * EH));
+                const F3 fE = disneyEval<FM>(hd, bf, wE);
                 const float cE = fabsf(dot(wE, hd.normal));
-                const F3 CE = f3(fE.x * cE * ev.x / pE, fE.y * cE * ev.y / pE, fE.z * cE * ev.z / pE);
+                const F3 CE = f3(M<FM>::div(fE.x * cE * ev.x, pE), M<FM>::div(fE.y * cE * ev.y, pE), M<FM>::div(fE.z * cE * ev.z, pE));
 
                 // --- point-light NEE set-up (pointLight, S/kernel.cu:175-205) -----------------------------------
                 F3 wL = f3(0.f), CP = f3(0.f); float dist = 0.f, pP = 0.f;
@@ -283,16 +285,16 @@ __global__ void __launch_bounds__(128) k_shade(WaveState W, const __grid_constan
                     if (li >= (int)S.lightCount) li = (int)S.lightCount - 1;
                     const float* lp = S.lights + 6 * li;
                     const F3 lpos = f3(lp[0], lp[1], lp[2]), lrad = f3(lp[3], lp[4], lp[5]);
-                    wL = normalized(lpos - Pp);
+                    wL = M<FM>::normalized(lpos - Pp);
                     dist = length(lpos - Pp);
-                    const F3 val = lrad / (dist * dist);
-                    const F3 fL = disneyEval(hd, bf, wL);
+                    const F3 val = M<FM>::div3(lrad, dist * dist);
+                    const F3 fL = disneyEval<FM>(hd, bf, wL);
                     const float cL = fabsf(dot(wL, hd.normal));
-                    CP = f3(val.x * fL.x * cL / pP, val.y * fL.y * cL / pP, val.z * fL.z * cL / pP);
+                    CP = f3(M<FM>::div(val.x * fL.x * cL, pP), M<FM>::div(val.y * fL.y * cL, pP), M<FM>::div(val.z * fL.z * cL, pP));
                 }
                 // --- emission through the BRDF strategy + throughput factor (shade, S/kernel.cu:349,357) ------------
                 const float cB = fabsf(dot(L, hd.normal));
-                const F3 mulB = f3(fB.x * cB / pB, fB.y * cB / pB, fB.z * cB / pB);
+                const F3 mulB = f3(M<FM>::div(fB.x * cB, pB), M<FM>::div(fB.y * cB, pB), M<FM>::div(fB.z * cB, pB));
                 const F3 CB = hd.emission * mulB;
 
                 W.neeEnvDir[pid] = make_float4(wE.x, wE.y, wE.z, pE);
