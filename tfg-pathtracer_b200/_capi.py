@@ -14,7 +14,7 @@ import numpy as np
 from . import scenes as S
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libeleven_b200.so")
+LIB_PATH = os.environ.get("ELEVEN_LIB") or os.path.join(_HERE, "csrc", "libeleven_b200.so")   # ELEVEN_LIB: A/B-testing kernel variants
 
 PASS_BEAUTY, PASS_DENOISE, PASS_NORMAL, PASS_TANGENT, PASS_BITANGENT = range(5)
 RNG_REFERENCE, RNG_FAST = 0, 1

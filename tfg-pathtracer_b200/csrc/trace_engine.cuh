@@ -23,6 +23,9 @@
 
 namespace eleven {
 
+#ifndef EL_TRIS_PER_ITER
+#define EL_TRIS_PER_ITER 2     /* triangle tests per lane per loop iteration */
+#endif
 #ifndef EL_REFILL
 #define EL_REFILL 8            /* idle lanes that trigger a queue fetch */
 #endif
@@ -56,7 +59,7 @@ __device__ __forceinline__ void traceQueue(const DevScene& S, uint32_t n, uint32
     float slack = 0.f, epsRay = 0.f, tcull = INFINITY, bestLo = INFINITY, bestHi = INFINITY;   // [bestLo, bestHi] brackets the best key
     bool bestExact = false;
     HitRec best; best.tri = -1; best.t = best.u = best.v = best.key = 0.f;
-    uint2 ngroup = make_uint2(0u, 0u), tgroup = make_uint2(0u, 0u);
+    uint2 ngroup = make_uint2(0u, 0u), tgroup = make_uint2(0u, 0u), tpost = make_uint2(0u, 0u);   // tpost: one postponed triangle group
     uint2 stack[EL_STACK];
     int sp = 0;
 
@@ -86,7 +89,7 @@ __device__ __forceinline__ void traceQueue(const DevScene& S, uint32_t n, uint32
                     bestLo = bestHi = INFINITY; bestExact = false;
                     best.tri = -1; best.t = best.u = best.v = best.key = 0.f;
                     ngroup = make_uint2(0u, S.nodeCount ? 0x80000000u : 0u);
-                    tgroup = make_uint2(0u, 0u);
+                    tgroup = make_uint2(0u, 0u); tpost = make_uint2(0u, 0u);
                     sp = 0;
                     active = true;
                 }
@@ -97,10 +100,11 @@ __device__ __forceinline__ void traceQueue(const DevScene& S, uint32_t n, uint32
             continue;
         }
 
-        // ---- every active lane must own a node group with pending children or pending triangles; else pop / finish ---
-        if (active && tgroup.y == 0u && ngroup.y <= 0x00ffffffu) {
-            if (sp > 0) ngroup = stack[--sp];
-            else {
+        // ---- bookkeeping: promote the postponed triangle group, pop a node group, or finish -------------------------------
+        if (active) {
+            if (tgroup.y == 0u && tpost.y != 0u) { tgroup = tpost; tpost.y = 0u; }
+            if (ngroup.y <= 0x00ffffffu && sp > 0) ngroup = stack[--sp];
+            if (ngroup.y <= 0x00ffffffu && tgroup.y == 0u) {
                 if (MODE == TRACE_CLOSEST_KEY && NEED_KEY && best.tri >= 0 && !bestExact) {
                     const TriGeom g = loadTriGeom(S.shadeTris, best.tri);
                     F3 sn;
@@ -111,7 +115,9 @@ __device__ __forceinline__ void traceQueue(const DevScene& S, uint32_t n, uint32
         }
 
         // ---- node phase: one node (8 quantised child boxes) ------------------------------------------------------------
-        const bool doNode = active && tgroup.y == 0u;
+        // A lane does node work AND triangle work in the same iteration whenever it has both: the triangles found by this
+        // node are postponed (tpost) while an older group is still being tested, so neither phase idles the lane.
+        const bool doNode = active && ngroup.y > 0x00ffffffu && tpost.y == 0u;
         if (__any_sync(FULL, doNode)) {
             if (doNode) {
                 const uint32_t octinv = octinv4 & 7u;
@@ -166,14 +172,22 @@ __device__ __forceinline__ void traceQueue(const DevScene& S, uint32_t n, uint32
                 }
                 ngroup.x = __float_as_uint(n1.x);
                 ngroup.y = (hitmask & 0xff000000u) | (eim >> 24);
-                tgroup.x = __float_as_uint(n1.y);
-                tgroup.y = hitmask & 0x00ffffffu;
+                const uint32_t newTris = hitmask & 0x00ffffffu;
+                if (newTris) {
+                    if (tgroup.y != 0u) tpost = make_uint2(__float_as_uint(n1.y), newTris);
+                    else tgroup = make_uint2(__float_as_uint(n1.y), newTris);
+                }
             }
         }
 
-        // ---- triangle phase: one triangle ---------------------------------------------------------------------------------
+        // ---- triangle phase: up to EL_TRIS_PER_ITER triangles (leaf nodes yield ~2.5 triangles per node visit, a triangle
+        //      test costs about a third of a node test: this keeps the two phases balanced at the leaf level) ---------------
+#pragma unroll 1
+        for (int round = 0; round < (MODE == TRACE_ANY ? 1 : EL_TRIS_PER_ITER); round++) {   // measured: 2 rounds -10 % on closest hit, +3 % on any hit
+        if (active && tgroup.y == 0u && tpost.y != 0u) { tgroup = tpost; tpost.y = 0u; }
         const bool doTri = active && tgroup.y != 0u;
-        if (__any_sync(FULL, doTri)) {
+        if (!__any_sync(FULL, doTri)) break;
+        {
             if (doTri) {
                 const uint32_t ti = 31u - __clz(tgroup.y);
                 tgroup.y &= ~(1u << ti);
@@ -223,6 +237,7 @@ __device__ __forceinline__ void traceQueue(const DevScene& S, uint32_t n, uint32
                 }
             }
         }
+        }   // triangle rounds
     }
 }
 
