@@ -174,14 +174,15 @@ def cpu_baseline(args, flat):
     setup = time.time() - t0
     rows = max(8, min(sc.height, int(args.cpu_rows)))
     y0 = (sc.height - rows) // 2
+    spp = max(1, int(args.cpu_spp))
     t0 = time.time()
-    orc.render(1, threads=threads, rows=(y0, y0 + rows))
+    orc.render(spp, threads=threads, rows=(y0, y0 + rows))
     dt = time.time() - t0
-    n = rows * sc.width
+    n = rows * sc.width * spp
     rc = orc.ray_counts()
     orc.close()
     return {"value": n / dt, "unit": "pixel-samples/s", "cores": threads, "kind": "port",
-            "sample": "1 spp of %d central rows (%d pixel-samples) of the same frame, oracle/eleven_oracle.cpp, %.1f s (+%.1f s reference-style BVH build)" % (rows, n, dt, setup),
+            "sample": "%d spp of %d central rows (%d pixel-samples) of the same frame, oracle/eleven_oracle.cpp, %.1f s (+%.1f s reference-style BVH build)" % (spp, rows, n, dt, setup),
             "mrays_per_s": float(rc.sum()) / dt / 1e6}
 
 
@@ -196,7 +197,9 @@ def main():
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--tex", type=int, default=4096)
-    ap.add_argument("--cpu-rows", type=int, default=96)
+    ap.add_argument("--cpu-rows", type=int, default=1080)
+    ap.add_argument("--cpu-spp", type=int, default=8)
+    ap.add_argument("--wave-spp", type=int, default=0, help="samples of every pixel in flight per wave (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mode", default="fast", choices=["fast", "parity"])
     ap.add_argument("--hit-mode", default="key", choices=["key", "min_t"], help="closest-hit ordering: the reference key (default) or classic min t")
@@ -227,6 +230,8 @@ def main():
         mode["hit_mode"] = R.HIT_MIN_T
     t0 = time.time()
     off, stride, _ = D.sample_plan(args.spp_per_step * world, rank, world)
+    if args.mode == "fast":
+        mode["wave_spp"] = args.wave_spp
     r = R.Renderer(device=local, sample_offset=off, sample_stride=stride, **mode).render_setup(sc)
     setup_s = time.time() - t0
     film, counts = D.film_tensors(r, "cuda:%d" % local)

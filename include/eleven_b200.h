@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define ELEVEN_ABI_VERSION 1
+#define ELEVEN_ABI_VERSION 2
 
 /* ---- status codes ------------------------------------------------------- */
 enum {
@@ -49,6 +49,9 @@ enum { ELEVEN_ENV_CDF   = 0,       /* the reference's flat float CDF + its binar
 enum { ELEVEN_HIT_KEY   = 0,       /* closest = min |hit.position-origin| with shadow-terminator shift (S/BVH.hpp:170) */
        ELEVEN_HIT_MIN_T = 1 };     /* closest = min t (classic); differs only inside the per-scene shift bound    */
 
+enum { ELEVEN_BVH_HOST   = 0,      /* binned-SAH BVH8 built on the host cores (bvh8_build.cpp)                      */
+       ELEVEN_BVH_DEVICE = 1 };    /* binned-SAH BVH8 built on the GPU (bvh8_build_gpu.cuh)                         */
+
 typedef struct ElevenConfig {
     int32_t  device;        /* CUDA device ordinal                                                     */
     uint32_t rng_mode;      /* ELEVEN_RNG_*                                                            */
@@ -59,6 +62,10 @@ typedef struct ElevenConfig {
     uint32_t sample_stride; /* fast rng: global sample index advances by this per local sample (>=1)   */
     uint32_t flags;         /* ELEVEN_FLAG_*                                                           */
     uint64_t seed;          /* fast rng key; the reference mode always uses seed 0 like the reference  */
+    uint32_t wave_spp;      /* samples of every pixel in flight per wave (power of two, <= 16); 0 = auto: as many as keep
+                             * a wave <= 2^25 paths.  Only ELEVEN_RNG_FAST can have more than 1 (the reference's per-pixel
+                             * XORWOW stream is sequential across samples, S/kernel.cu:380,480).  Same image for any value. */
+    uint32_t bvh_builder;   /* ELEVEN_BVH_*                                                            */
 } ElevenConfig;
 
 #define ELEVEN_FLAG_TERMINATE_DEAD_PATHS 1u  /* stop paths whose throughput is exactly 0 (only legal with RNG_FAST) */

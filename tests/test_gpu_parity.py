@@ -142,6 +142,35 @@ def test_fast_mode_is_unbiased_and_split_invariant(scenes):
     one.close(); r.close(); orc.close()
 
 
+def test_wave_spp_does_not_change_the_film(scenes):
+    """K samples of every pixel in flight per wave (ElevenConfig.wave_spp): the counter-based RNG is keyed by the global
+    sample index and the K samples of a pixel are accumulated in sample order, so the film is bit-identical for any K,
+    including ragged tails (11 = 8 + 2 + 1) and progressive calls."""
+    for name in ("cornell", "clock"):
+        sc = scenes[name]
+        films, counts, stats = [], [], []
+        for k in (1, 4, 8, 0):
+            cfg = dict(R.FAST); cfg.update(wave_spp=k, sample_offset=3, sample_stride=2)
+            r = R.Renderer(**cfg).render_setup(sc)
+            if k == 4:
+                r.render_cuda(5); r.render_cuda(6)
+            else:
+                r.render_cuda(11)
+            b, pc = r.get_buffers()
+            films.append(b); counts.append((pc, r.get_sample_counts())); stats.append(r.stats()); r.close()
+        for b, (pc, sc_), st in zip(films[1:], counts[1:], stats[1:]):
+            for p in b:
+                assert (bits(b[p]) == bits(films[0][p])).all()
+            assert (pc == counts[0][0]).all() and (sc_ == counts[0][1]).all()
+            for key in ("rays_extension", "rays_shadow_env", "rays_shadow_light", "hit_bounces", "pixel_samples"):
+                assert st[key] == stats[0][key], key
+        assert stats[1]["kernel_launches"] < stats[0]["kernel_launches"]
+    with pytest.raises(R.ElevenError):
+        R.Renderer(rng_mode=R.RNG_REFERENCE, env_mode=R.ENV_CDF, flags=0, wave_spp=4)     # the reference stream is sequential per pixel
+    with pytest.raises(R.ElevenError):
+        R.Renderer(**dict(R.FAST, wave_spp=3))
+
+
 def test_env_alias_matches_cdf_distribution(scenes):
     sc = scenes["clock"]
     a = R.Renderer(rng_mode=R.RNG_FAST, env_mode=R.ENV_CDF, flags=0).render_setup(sc); a.render_cuda(96)

@@ -20,13 +20,14 @@ PASS_BEAUTY, PASS_DENOISE, PASS_NORMAL, PASS_TANGENT, PASS_BITANGENT = range(5)
 RNG_REFERENCE, RNG_FAST = 0, 1
 ENV_CDF, ENV_ALIAS = 0, 1
 HIT_KEY, HIT_MIN_T = 0, 1
+BVH_HOST, BVH_DEVICE = 0, 1
 FLAG_TERMINATE_DEAD_PATHS, FLAG_COUNTERS, FLAG_TIME_KERNELS, FLAG_SKIP_NULL_NEE, FLAG_FAST_MATH = 1, 2, 4, 8, 16
 
 
 class ElevenConfig(C.Structure):
     _fields_ = [("device", C.c_int32), ("rng_mode", C.c_uint32), ("env_mode", C.c_uint32), ("hit_mode", C.c_uint32),
                 ("max_bounces", C.c_uint32), ("sample_offset", C.c_uint32), ("sample_stride", C.c_uint32),
-                ("flags", C.c_uint32), ("seed", C.c_uint64)]
+                ("flags", C.c_uint32), ("seed", C.c_uint64), ("wave_spp", C.c_uint32), ("bvh_builder", C.c_uint32)]
 
 
 class ElevenCamera(C.Structure):
@@ -140,7 +141,7 @@ def load_library(path: str = LIB_PATH):
     L.eleven_device_upload.argtypes = [vp, vp, vp, sz]
     L.eleven_device_download.argtypes = [vp, vp, vp, sz]
     L.eleven_resolve_rgba8.argtypes = [vp, C.c_int, vp, sz]
-    if L.eleven_abi_version() != 1:
+    if L.eleven_abi_version() != 2:
         raise RuntimeError("ABI version mismatch")
     _lib = L
     return L

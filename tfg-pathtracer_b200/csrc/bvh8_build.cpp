@@ -32,8 +32,14 @@ struct Box {
 struct Node2 { Box box; int left, right, first, count, span; };   // leaf iff count > 0; span = triangles in the subtree
 
 static const int   BINS = 16;
-static const int   MAX_LEAF = 3;
-static const float COST_TRI = 1.0f, COST_NODE = 1.0f;
+#ifndef EL_MAX_LEAF
+#define EL_MAX_LEAF 3
+#endif
+#ifndef EL_COST_NODE
+#define EL_COST_NODE 1.0f
+#endif
+static const int   MAX_LEAF = EL_MAX_LEAF;
+static const float COST_TRI = 1.0f, COST_NODE = EL_COST_NODE;
 
 struct Builder {
     const ElevenTri* tris; uint32_t n;

@@ -44,6 +44,7 @@ struct ElevenCtx {
     RenderParams P;
     bool haveScene = false;
     uint32_t nPixels = 0, width = 0, height = 0;
+    uint32_t maxLogK = 0;                        // a wave carries up to 2^maxLogK samples of every pixel
     uint32_t samplesRendered = 0;
     int numSMs = 148;
     uint32_t* d_seqMat = nullptr;
@@ -75,7 +76,10 @@ static void freeAll(std::vector<void*>& list) { for (void* p : list) cudaFree(p)
 
 extern "C" int eleven_init(const ElevenConfig* cfg, ElevenCtx** out) {
     if (!cfg || !out) return fail(ELEVEN_ERR_ARG, "eleven_init: null argument");
-    if (cfg->rng_mode > 1 || cfg->env_mode > 1 || cfg->hit_mode > 1) return fail(ELEVEN_ERR_ARG, "eleven_init: bad mode");
+    if (cfg->rng_mode > 1 || cfg->env_mode > 1 || cfg->hit_mode > 1 || cfg->bvh_builder > 1) return fail(ELEVEN_ERR_ARG, "eleven_init: bad mode");
+    if (cfg->wave_spp > 16 || (cfg->wave_spp & (cfg->wave_spp - 1u)) != 0u) return fail(ELEVEN_ERR_ARG, "eleven_init: wave_spp must be 0 (auto) or a power of two <= 16");
+    if (cfg->wave_spp > 1 && cfg->rng_mode == ELEVEN_RNG_REFERENCE)
+        return fail(ELEVEN_ERR_ARG, "eleven_init: the reference RNG stream is sequential per pixel; wave_spp > 1 needs ELEVEN_RNG_FAST");
     if ((cfg->flags & ELEVEN_FLAG_TERMINATE_DEAD_PATHS) && cfg->rng_mode == ELEVEN_RNG_REFERENCE)
         return fail(ELEVEN_ERR_ARG, "eleven_init: dead-path termination changes the XORWOW stream; use it with ELEVEN_RNG_FAST only");
     int ndev = 0;
@@ -172,19 +176,31 @@ static int uploadTexture(ElevenCtx* c, const ElevenTexture& t, DevTex& out, bool
 static int allocWave(ElevenCtx* c) {
     freeAll(c->waveAllocs);
     WaveState& W = c->W; memset(&W, 0, sizeof W);
-    const size_t n = c->nPixels; W.nPixels = c->nPixels;
+    W.nPixels = c->nPixels;
+    // samples per pixel in flight: as many as keep a wave within 2^25 paths (~12 GB of wave state), at most 16
+    c->maxLogK = 0;
+    if (c->cfg.rng_mode == ELEVEN_RNG_FAST) {
+        if (c->cfg.wave_spp) { while ((1u << c->maxLogK) < c->cfg.wave_spp) c->maxLogK++; }
+        else while (c->maxLogK < 4 && ((uint64_t)c->nPixels << (c->maxLogK + 1)) <= (1ull << 25)) c->maxLogK++;
+    }
+    if (((uint64_t)c->nPixels << c->maxLogK) > 0x7fffffffull) return fail(ELEVEN_ERR_ARG, "wave_spp x resolution exceeds 2^31 paths");
+    W.pathCapacity = c->nPixels << c->maxLogK;
+    const size_t n = W.pathCapacity, npx = c->nPixels;
     int rc = 0;
 #define A(field, type) if ((rc = devAlloc(c->waveAllocs, &W.field, n))) return rc;
+#define APX(field, type) if ((rc = devAlloc(c->waveAllocs, &W.field, npx))) return rc;
     A(rayO, float4) A(rayD, float4) A(thr, float4) A(rad, float4) A(hit, float4) A(aovN, float4) A(aovT, float4) A(aovB, float4)
-    A(depth, uint32_t) A(rng, Xorwow)
+    A(depth, uint32_t) APX(rng, Xorwow)
     A(neeEnvDir, float4) A(neeEnvC, float4) A(neeLightDir, float4) A(neeLightC, float4) A(neeBrdfC, float4) A(neePos, float4) A(neeThrMul, float4)
     A(qCur, uint32_t) A(qNext, uint32_t) A(qNee, uint32_t)
     if ((rc = devAlloc(c->waveAllocs, &W.qBucket, n * EL_BUCKETS))) return rc;
-    A(filmBeauty, float4) A(filmNormal, float4) A(filmTangent, float4) A(filmBitangent, float4) A(filmCount, uint32_t) A(pathCount, uint32_t)
+    APX(filmBeauty, float4) APX(filmNormal, float4) APX(filmTangent, float4) APX(filmBitangent, float4) APX(filmCount, uint32_t) APX(pathCount, uint32_t)
 #undef A
+#undef APX
+    const size_t npxResolve = npx;
     if ((rc = devAlloc(c->waveAllocs, &W.cnt, CNT_COUNT))) return rc;
     if ((rc = devAlloc(c->waveAllocs, &W.stats, ST_COUNT))) return rc;
-    if ((rc = devAlloc(c->waveAllocs, &c->d_resolve, n))) return rc;
+    if ((rc = devAlloc(c->waveAllocs, &c->d_resolve, npxResolve))) return rc;
     if ((rc = devAlloc(c->waveAllocs, &c->d_workCounter, 4))) return rc;
     CK(cudaMemsetAsync(W.cnt, 0, CNT_COUNT * sizeof(uint32_t), c->stream));
     CK(cudaMemsetAsync(W.stats, 0, ST_COUNT * sizeof(unsigned long long), c->stream));
@@ -371,6 +387,7 @@ extern "C" int eleven_render(ElevenCtx* c, int spp) {
     CK(cudaSetDevice(c->cfg.device));
     const uint32_t n = c->nPixels;
     const int gridPix = (int)((n + 255) / 256);
+    c->P.sampleStride = c->cfg.sample_stride;
     const int gridPersist = c->numSMs * 8;             // 148 SMs x 8 CTAs of 128 threads: a multiple of the SM count
     const bool count = (c->cfg.flags & ELEVEN_FLAG_COUNTERS) != 0;
     const bool timeK = (c->cfg.flags & ELEVEN_FLAG_TIME_KERNELS) != 0;
@@ -385,10 +402,15 @@ extern "C" int eleven_render(ElevenCtx* c, int spp) {
     };
     CK(cudaEventRecord(c->ev0, c->stream));
     mark(3);
-    for (int s = 0; s < spp; s++) {
+    for (int s = 0; s < spp;) {
+        // this wave: the largest power of two of samples that fits both the wave buffers and what is left to render
+        uint32_t logK = c->maxLogK;
+        while (logK > 0 && (1 << logK) > spp - s) logK--;
+        c->P.logK = logK;
+        const int gridPaths = (int)((((size_t)n << logK) + 255) / 256);
         c->P.sampleIndex = c->cfg.sample_offset + c->samplesRendered * c->cfg.sample_stride;
-        if (fastMath) k_raygen<true><<<gridPix, 256, 0, c->stream>>>(c->W, c->scene, c->P);
-        else k_raygen<false><<<gridPix, 256, 0, c->stream>>>(c->W, c->scene, c->P);
+        if (fastMath) k_raygen<true><<<gridPaths, 256, 0, c->stream>>>(c->W, c->scene, c->P);
+        else k_raygen<false><<<gridPaths, 256, 0, c->stream>>>(c->W, c->scene, c->P);
         mark(3);
         for (uint32_t b = 0; b < c->cfg.max_bounces; b++) {
             if (count) launchExtend<true>(c, gridPersist); else launchExtend<false>(c, gridPersist);
@@ -407,10 +429,11 @@ extern "C" int eleven_render(ElevenCtx* c, int spp) {
             std::swap(c->W.qCur, c->W.qNext);      // kernel arguments are captured at launch: the next bounce reads the list just written
             c->stats.kernel_launches += 5;
         }
-        k_accumulate<<<gridPix, 256, 0, c->stream>>>(c->W);
+        k_accumulate<<<gridPix, 256, 0, c->stream>>>(c->W, logK);
         mark(3);
         c->stats.kernel_launches += 2;
-        c->samplesRendered++;
+        c->samplesRendered += 1u << logK;
+        s += 1 << logK;
     }
     CK(cudaEventRecord(c->ev1, c->stream));
     CK(cudaGetLastError());

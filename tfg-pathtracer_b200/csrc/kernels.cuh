@@ -14,7 +14,11 @@
  *   connect     shadow rays + the balance-heuristic MIS combination (S/kernel.cu:246-248,192-197,351-357)
  *   accumulate  clamp, NaN rejection, film sums (S/kernel.cu:445-480)
  *
- * One path per pixel per wave, path id == film index, so film updates need no atomics.  Queues hold path ids;
+ * K = 2^logK samples of every pixel per wave (K = 1 with the reference's sequential per-pixel RNG), path id =
+ * film index * K + k, so film updates need no atomics and the K samples of a pixel are summed in sample order.  Why K > 1:
+ * the duration of a traversal kernel has a floor set by its slowest rays (~150-200 us on the benchmark scene, the late
+ * bounces of a 2 M-path wave ran at that floor: profiles/r1_launches_final.csv), paid once per kernel whatever the size of
+ * the wave.  Queues hold path ids;
  * their counts live on the device and every kernel is a persistent grid that fetches 32-ray batches per warp with
  * one atomicAdd ("warp-level work fetch"), so a whole wave is enqueued without a single host synchronisation.
  */
@@ -29,7 +33,7 @@ enum { EL_BUCKETS = 8, EL_MISS_BUCKET = 7 };   // shading queue buckets: materia
 enum { ST_RAYS_EXT = 0, ST_RAYS_ENV = 1, ST_RAYS_LIGHT = 2, ST_NODES = 3, ST_TRIS = 4, ST_KEYS = 5, ST_COUNT = 8 };
 
 struct WaveState {
-    // per path (index = film index)
+    // per path (index = film index * K + k)
     float4* rayO; float4* rayD;          // origin / normalised direction
     float4* thr;  float4* rad;           // throughput ("reduction"), accumulated radiance ("light")
     float4* hit;                         // tri (as int bits), t, u, v
@@ -46,18 +50,21 @@ struct WaveState {
     float4* neeThrMul;                   // f*cos/p_b (throughput update factor)
     // queues
     uint32_t* qCur; uint32_t* qNext; uint32_t* qNee;
-    uint32_t* qBucket;                   // EL_BUCKETS x nPixels: the shading queue, sorted by material (k_classify)
+    uint32_t* qBucket;                   // EL_BUCKETS x pathCapacity: the shading queue, sorted by material (k_classify)
     uint32_t* cnt;                       // CNT_*
     unsigned long long* stats;           // ST_*
     // film: per-pixel sums + counts
     float4* filmBeauty; float4* filmNormal; float4* filmTangent; float4* filmBitangent;
     uint32_t* filmCount; uint32_t* pathCount;
     uint32_t nPixels;
+    uint32_t pathCapacity;               // nPixels * largest K: stride of the qBucket rows
 };
 
 struct RenderParams {
     uint32_t rngMode, envMode, hitMode, maxBounces, flags;
-    uint32_t sampleIndex;                // global index of the sample this wave renders (fast rng)
+    uint32_t sampleIndex;                // global index of the first sample this wave renders (fast rng)
+    uint32_t sampleStride;               // global index step between the K samples of a wave
+    uint32_t logK;                       // this wave carries K = 2^logK samples per pixel
     uint32_t seedLo, seedHi;
     CamRot rot;
 };
@@ -105,20 +112,23 @@ __global__ void k_filmReset(WaveState W) {
 }
 
 // fast-mode uniforms: 4 per call, keyed by (pixel, sample, dimension block)
-__device__ __forceinline__ uint4 fastBits(const RenderParams& P, uint32_t pixel, uint32_t block) {
-    return philox4x32(make_uint4(pixel, P.sampleIndex, block, 0x11e7e0u), make_uint2(P.seedLo, P.seedHi));
+__device__ __forceinline__ uint4 fastBits(const RenderParams& P, uint32_t pid, uint32_t block) {
+    const uint32_t pixel = pid >> P.logK, k = pid & ((1u << P.logK) - 1u);
+    return philox4x32(make_uint4(pixel, P.sampleIndex + k * P.sampleStride, block, 0x11e7e0u), make_uint2(P.seedLo, P.seedHi));
 }
 
 // ---- raygen ------------------------------------------------------------------------------------------------
 template <bool FM>
 __global__ void __launch_bounds__(256) k_raygen(WaveState W, const __grid_constant__ DevScene S, const __grid_constant__ RenderParams P) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= W.nPixels) return;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;        // path id
+    const uint32_t nPaths = W.nPixels << P.logK;
+    if (i >= nPaths) return;
+    const uint32_t pix = i >> P.logK;
     const uint32_t Wd = S.cam.xRes, Hd = S.cam.yRes;
-    const int x = (int)(i % Wd), y = (int)(Hd - 1u - i / Wd);        // film index = W*(H-1-y)+x (S/kernel.cu:378)
+    const int x = (int)(pix % Wd), y = (int)(Hd - 1u - pix / Wd);    // film index = W*(H-1-y)+x (S/kernel.cu:378)
     float r1, r2, r3, r4, r5;
     if (P.rngMode == ELEVEN_RNG_REFERENCE) {
-        Xorwow s = W.rng[i];
+        Xorwow s = W.rng[i];                                          // logK == 0 in this mode
         r1 = xorwowUniform(s); r2 = xorwowUniform(s); r3 = xorwowUniform(s); r4 = xorwowUniform(s); r5 = xorwowUniform(s);
         W.rng[i] = s;
     } else {
@@ -136,7 +146,7 @@ __global__ void __launch_bounds__(256) k_raygen(WaveState W, const __grid_consta
     W.depth[i] = 0u;
     W.qCur[i] = i;
     if (i == 0) {
-        W.cnt[CNT_CUR] = W.nPixels; W.cnt[CNT_NEXT] = 0u; W.cnt[CNT_NEE] = 0u;
+        W.cnt[CNT_CUR] = nPaths; W.cnt[CNT_NEXT] = 0u; W.cnt[CNT_NEE] = 0u;
         W.cnt[CNT_WORK_TRACE] = 0u; W.cnt[CNT_WORK_SHADE] = 0u; W.cnt[CNT_WORK_CONNECT] = 0u; W.cnt[CNT_WORK_LIGHT] = 0u;
         W.cnt[CNT_WORK_CLASSIFY] = 0u;
         for (int b = 0; b < EL_BUCKETS; b++) W.cnt[CNT_BUCKET0 + b] = 0u;
@@ -168,7 +178,7 @@ __global__ void __launch_bounds__(128) k_classify(WaveState W, const __grid_cons
             uint32_t pos = 0;
             if (lane == leader) pos = atomicAdd(&W.cnt[CNT_BUCKET0 + bucket], (uint32_t)__popc(peers));
             pos = __shfl_sync(peers, pos, leader);
-            W.qBucket[(size_t)bucket * W.nPixels + pos + __popc(peers & ((1u << lane) - 1u))] = pid;
+            W.qBucket[(size_t)bucket * W.pathCapacity + pos + __popc(peers & ((1u << lane) - 1u))] = pid;
         }
     }
 }
@@ -205,7 +215,7 @@ __global__ void __launch_bounds__(128) k_shade(WaveState W, const __grid_constan
             uint32_t b = 0;
 #pragma unroll
             for (int k = 1; k < EL_BUCKETS; k++) b += (qi >= prefix[k]) ? 1u : 0u;
-            pid = W.qBucket[(size_t)b * W.nPixels + (qi - prefix[b])];
+            pid = W.qBucket[(size_t)b * W.pathCapacity + (qi - prefix[b])];
             const float4 hv = W.hit[pid];
             const int tri = __float_as_int(hv.x);
             const float4 o4 = W.rayO[pid], d4 = W.rayD[pid];
@@ -356,20 +366,29 @@ __global__ void k_advance(WaveState W, uint32_t lights, int phase) {
 }
 
 // ---- accumulate (S/kernel.cu:445-480) with sums instead of running means -------------------------------------------------
-__global__ void __launch_bounds__(256) k_accumulate(WaveState W) {
+// The K samples of a pixel are added in sample order, so the sums are the same floats for every K.
+__global__ void __launch_bounds__(256) k_accumulate(WaveState W, uint32_t logK) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= W.nPixels) return;
-    W.pathCount[i] += W.depth[i];
-    float4 r = W.rad[i];
-    r.x = clampf_(r.x, 0.f, 10.f); r.y = clampf_(r.y, 0.f, 10.f); r.z = clampf_(r.z, 0.f, 10.f);
-    if (!isnan(r.x) && !isnan(r.y) && !isnan(r.z)) {
-        float4 b = W.filmBeauty[i]; b.x += r.x; b.y += r.y; b.z += r.z; W.filmBeauty[i] = b;
-        const float4 n = W.aovN[i], t = W.aovT[i], bt = W.aovB[i];
-        float4 a = W.filmNormal[i]; a.x += n.x; a.y += n.y; a.z += n.z; W.filmNormal[i] = a;
-        a = W.filmTangent[i]; a.x += t.x; a.y += t.y; a.z += t.z; W.filmTangent[i] = a;
-        a = W.filmBitangent[i]; a.x += bt.x; a.y += bt.y; a.z += bt.z; W.filmBitangent[i] = a;
-        W.filmCount[i] += 1u;
+    float4 fb = W.filmBeauty[i], fn = W.filmNormal[i], ft = W.filmTangent[i], fbt = W.filmBitangent[i];
+    uint32_t count = W.filmCount[i], paths = W.pathCount[i];
+    const uint32_t K = 1u << logK;
+    for (uint32_t k = 0; k < K; k++) {
+        const uint32_t p = (i << logK) + k;
+        paths += W.depth[p];
+        float4 r = W.rad[p];
+        r.x = clampf_(r.x, 0.f, 10.f); r.y = clampf_(r.y, 0.f, 10.f); r.z = clampf_(r.z, 0.f, 10.f);
+        if (!isnan(r.x) && !isnan(r.y) && !isnan(r.z)) {
+            fb.x += r.x; fb.y += r.y; fb.z += r.z;
+            const float4 n = W.aovN[p], t = W.aovT[p], bt = W.aovB[p];
+            fn.x += n.x; fn.y += n.y; fn.z += n.z;
+            ft.x += t.x; ft.y += t.y; ft.z += t.z;
+            fbt.x += bt.x; fbt.y += bt.y; fbt.z += bt.z;
+            count += 1u;
+        }
     }
+    W.filmBeauty[i] = fb; W.filmNormal[i] = fn; W.filmTangent[i] = ft; W.filmBitangent[i] = fbt;
+    W.filmCount[i] = count; W.pathCount[i] = paths;
 }
 
 // film read-back: mean, alpha = 1 (S/kernel.cu:137,461-463)

@@ -32,11 +32,13 @@ FAST = dict(rng_mode=RNG_FAST, env_mode=ENV_ALIAS, hit_mode=HIT_KEY, flags=FLAG_
 
 class Renderer:
     def __init__(self, device=0, rng_mode=RNG_FAST, env_mode=ENV_ALIAS, hit_mode=HIT_KEY, max_bounces=5,
-                 sample_offset=0, sample_stride=1, flags=FLAG_TERMINATE_DEAD_PATHS, seed=0):
+                 sample_offset=0, sample_stride=1, flags=FLAG_TERMINATE_DEAD_PATHS, seed=0, wave_spp=0,
+                 bvh_builder=_capi.BVH_HOST):
         self.L = _capi.load_library()
         if rng_mode == RNG_REFERENCE:
             flags &= ~FLAG_TERMINATE_DEAD_PATHS
-        self.cfg = _capi.ElevenConfig(device, rng_mode, env_mode, hit_mode, max_bounces, sample_offset, sample_stride, flags, seed)
+        self.cfg = _capi.ElevenConfig(device, rng_mode, env_mode, hit_mode, max_bounces, sample_offset, sample_stride, flags, seed,
+                                      wave_spp, bvh_builder)
         self.h = C.c_void_p()
         self._ck(self.L.eleven_init(C.byref(self.cfg), C.byref(self.h)))
         self.W = self.H = 0
