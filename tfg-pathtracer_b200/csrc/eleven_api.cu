@@ -190,7 +190,7 @@ static int allocWave(ElevenCtx* c) {
 #define A(field, type) if ((rc = devAlloc(c->waveAllocs, &W.field, n))) return rc;
 #define APX(field, type) if ((rc = devAlloc(c->waveAllocs, &W.field, npx))) return rc;
     A(rayO, float4) A(rayD, float4) A(thr, float4) A(rad, float4) A(hit, float4) A(aovN, float4) A(aovT, float4) A(aovB, float4)
-    A(depth, uint32_t) APX(rng, Xorwow)
+    A(depth, uint32_t) APX(rng, Xorwow) A(hitBucket, uint8_t)
     A(neeEnvDir, float4) A(neeEnvC, float4) A(neeLightDir, float4) A(neeLightC, float4) A(neeBrdfC, float4) A(neePos, float4) A(neeThrMul, float4)
     A(qCur, uint32_t) A(qNext, uint32_t) A(qNee, uint32_t)
     if ((rc = devAlloc(c->waveAllocs, &W.qBucket, n * EL_BUCKETS))) return rc;
@@ -234,6 +234,7 @@ extern "C" int eleven_scene_upload(ElevenCtx* c, const ElevenSceneDesc* d) {
     c->d_seqMat = nullptr; c->d_camera = nullptr;
     c->haveScene = false;
     DevScene& S = c->scene; memset(&S, 0, sizeof S);
+    S.byteMagic = 0x4B000000u;
     int rc;
 
     // triangles -> per-triangle material, BVH8, shading records
@@ -429,7 +430,7 @@ extern "C" int eleven_render(ElevenCtx* c, int spp) {
             std::swap(c->W.qCur, c->W.qNext);      // kernel arguments are captured at launch: the next bounce reads the list just written
             c->stats.kernel_launches += 5;
         }
-        k_accumulate<<<gridPix, 256, 0, c->stream>>>(c->W, logK);
+        k_accumulate<<<gridPaths, 256, 0, c->stream>>>(c->W, logK);
         mark(3);
         c->stats.kernel_launches += 2;
         c->samplesRendered += 1u << logK;

@@ -37,6 +37,7 @@ struct WaveState {
     float4* rayO; float4* rayD;          // origin / normalised direction
     float4* thr;  float4* rad;           // throughput ("reduction"), accumulated radiance ("light")
     float4* hit;                         // tri (as int bits), t, u, v
+    uint8_t* hitBucket;                  // per QUEUE position of the current bounce: shading bucket of the hit (written by k_extend's sink)
     float4* aovN; float4* aovT; float4* aovB;
     uint32_t* depth;                     // number of hit bounces so far ("i")
     Xorwow* rng;                         // per-pixel XORWOW state, persistent across samples (reference mode)
@@ -158,18 +159,17 @@ __global__ void __launch_bounds__(256) k_raygen(WaveState W, const __grid_consta
 __global__ void __launch_bounds__(128) k_classify(WaveState W, const __grid_constant__ DevScene S) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t n = W.cnt[CNT_CUR];
-    // static grid-stride partition: this kernel does ~3 dependent loads per entry, a single-address work-fetch atomic
-    // per 32 entries would be its bottleneck (ncu: 62 us at 5 % issue utilisation with dynamic fetch)
+    // static grid-stride partition: a single-address work-fetch atomic per 32 entries would be the bottleneck of a kernel
+    // that only streams 5 bytes per entry
     const uint32_t warpsTotal = gridDim.x * (blockDim.x >> 5);
     const uint32_t warpId = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     for (uint32_t base = warpId * 32u; base < n; base += warpsTotal * 32u) {
         const uint32_t qi = base + lane;
         const bool valid = qi < n;
         uint32_t pid = 0, bucket = EL_MISS_BUCKET;
-        if (valid) {
+        if (valid) {                                 // two coalesced streams, no dependent gather: k_extend's sink left the bucket at qi
             pid = W.qCur[qi];
-            const int tri = __float_as_int(W.hit[pid].x);
-            if (tri >= 0) bucket = min((uint32_t)__ldg(S.triMaterial + tri), (uint32_t)(EL_MISS_BUCKET - 1));
+            bucket = W.hitBucket[qi];
         }
         const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
         if (valid) {
@@ -195,8 +195,11 @@ __device__ __forceinline__ void appendWarpAggregated(uint32_t* q, uint32_t* coun
     q[base + __popc(mask & ((1u << lane) - 1u))] = value;
 }
 
+#ifndef EL_SHADE_MIN_CTAS
+#define EL_SHADE_MIN_CTAS 6      /* 80 registers, 24 warps/SM: the kernel waits on texture gathers (ncu: long_scoreboard), measured -11 % vs 91 registers */
+#endif
 template <bool FM>
-__global__ void __launch_bounds__(128) k_shade(WaveState W, const __grid_constant__ DevScene S, const __grid_constant__ RenderParams P) {
+__global__ void __launch_bounds__(128, EL_SHADE_MIN_CTAS) k_shade(WaveState W, const __grid_constant__ DevScene S, const __grid_constant__ RenderParams P) {
     const uint32_t lane = threadIdx.x & 31u;
     // the shading queue is the concatenation of the material buckets written by k_classify: consecutive entries share a
     // material (same textures, same branches), escaped rays come last
@@ -366,29 +369,45 @@ __global__ void k_advance(WaveState W, uint32_t lights, int phase) {
 }
 
 // ---- accumulate (S/kernel.cu:445-480) with sums instead of running means -------------------------------------------------
-// The K samples of a pixel are added in sample order, so the sums are the same floats for every K.
+// The K samples of a pixel are added in sample order, so the sums are the same floats for every K.  A block owns 256 >> logK
+// pixels = 256 consecutive paths: every thread loads ITS path's records (coalesced 16-byte loads; one thread per pixel
+// walking its K records strides the warp over K x 16 bytes and ran at a fifth of the HBM rate), stages the clamped values
+// in shared memory, and 4 threads per pixel (one per film pass) do the ordered sums.
 __global__ void __launch_bounds__(256) k_accumulate(WaveState W, uint32_t logK) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= W.nPixels) return;
-    float4 fb = W.filmBeauty[i], fn = W.filmNormal[i], ft = W.filmTangent[i], fbt = W.filmBitangent[i];
-    uint32_t count = W.filmCount[i], paths = W.pathCount[i];
-    const uint32_t K = 1u << logK;
-    for (uint32_t k = 0; k < K; k++) {
-        const uint32_t p = (i << logK) + k;
-        paths += W.depth[p];
+    __shared__ float sv[4][256][3];
+    __shared__ uint32_t sdepth[256];
+    __shared__ uint8_t sok[256];
+    const uint32_t tid = threadIdx.x;
+    const uint32_t nPaths = W.nPixels << logK;
+    const uint32_t p = blockIdx.x * 256u + tid;
+    if (p < nPaths) {
         float4 r = W.rad[p];
         r.x = clampf_(r.x, 0.f, 10.f); r.y = clampf_(r.y, 0.f, 10.f); r.z = clampf_(r.z, 0.f, 10.f);
-        if (!isnan(r.x) && !isnan(r.y) && !isnan(r.z)) {
-            fb.x += r.x; fb.y += r.y; fb.z += r.z;
-            const float4 n = W.aovN[p], t = W.aovT[p], bt = W.aovB[p];
-            fn.x += n.x; fn.y += n.y; fn.z += n.z;
-            ft.x += t.x; ft.y += t.y; ft.z += t.z;
-            fbt.x += bt.x; fbt.y += bt.y; fbt.z += bt.z;
-            count += 1u;
-        }
+        const bool ok = !isnan(r.x) && !isnan(r.y) && !isnan(r.z);
+        const float4 n = W.aovN[p], t = W.aovT[p], bt = W.aovB[p];
+        sv[0][tid][0] = r.x; sv[0][tid][1] = r.y; sv[0][tid][2] = r.z;
+        sv[1][tid][0] = n.x; sv[1][tid][1] = n.y; sv[1][tid][2] = n.z;
+        sv[2][tid][0] = t.x; sv[2][tid][1] = t.y; sv[2][tid][2] = t.z;
+        sv[3][tid][0] = bt.x; sv[3][tid][1] = bt.y; sv[3][tid][2] = bt.z;
+        sdepth[tid] = W.depth[p]; sok[tid] = ok ? 1 : 0;
     }
-    W.filmBeauty[i] = fb; W.filmNormal[i] = fn; W.filmTangent[i] = ft; W.filmBitangent[i] = fbt;
-    W.filmCount[i] = count; W.pathCount[i] = paths;
+    __syncthreads();
+    const uint32_t K = 1u << logK, pixPerBlock = 256u >> logK;
+    const uint32_t pass = tid & 3u;                                // film pass; 4 threads per pixel, 64 pixels per sweep
+    float4* film = pass == 0 ? W.filmBeauty : pass == 1 ? W.filmNormal : pass == 2 ? W.filmTangent : W.filmBitangent;
+    for (uint32_t lp = tid >> 2; lp < pixPerBlock; lp += 64u) {
+        const uint32_t pix = blockIdx.x * pixPerBlock + lp;
+        if (pix >= W.nPixels) break;
+        float4 f = film[pix];
+        uint32_t count = 0, paths = 0;
+        for (uint32_t k = 0; k < K; k++) {
+            const uint32_t q = (lp << logK) + k;
+            paths += sdepth[q];
+            if (sok[q]) { f.x += sv[pass][q][0]; f.y += sv[pass][q][1]; f.z += sv[pass][q][2]; count++; }
+        }
+        film[pix] = f;
+        if (pass == 0) { W.filmCount[pix] += count; W.pathCount[pix] += paths; }
+    }
 }
 
 // film read-back: mean, alpha = 1 (S/kernel.cu:137,461-463)

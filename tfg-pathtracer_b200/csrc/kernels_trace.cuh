@@ -21,19 +21,23 @@ struct ExtendSource {
         const uint32_t pid = W.qCur[qi];
         const float4 o = W.rayO[pid], d = W.rayD[pid];
         lr.ray.o = f3(o.x, o.y, o.z); lr.ray.d = f3(d.x, d.y, d.z);
-        lr.tmaxAny = INFINITY; lr.tag = pid;
+        lr.tmaxAny = INFINITY; lr.tag = qi;                              // the sink needs the queue position (hitBucket)
     }
 };
 struct ExtendSink {
-    const WaveState& W;
+    const WaveState& W; const DevScene& S;
     __device__ __forceinline__ void done(const LaneRay& lr, const HitRec& h) const {
-        W.hit[lr.tag] = make_float4(__int_as_float(h.tri), h.t, h.u, h.v);
+        const uint32_t pid = W.qCur[lr.tag];
+        W.hit[pid] = make_float4(__int_as_float(h.tri), h.t, h.u, h.v);
+        // shading bucket (material, escaped rays last) at the queue position: k_classify then streams qCur + hitBucket
+        // instead of chasing qCur -> hit -> triMaterial (3 dependent loads per entry: 4 % of the frame in round-1 ncu)
+        W.hitBucket[lr.tag] = h.tri < 0 ? (uint8_t)EL_MISS_BUCKET : (uint8_t)min((uint32_t)__ldg(S.triMaterial + h.tri), (uint32_t)(EL_MISS_BUCKET - 1));
     }
 };
 template <int MODE, bool COUNT>
 __global__ void __launch_bounds__(128) k_extend(const __grid_constant__ WaveState W, const __grid_constant__ DevScene S) {
     TraceCounters tc; tc.nodes = 0; tc.tris = 0; tc.keys = 0;
-    ExtendSource src{W}; ExtendSink sink{W};
+    ExtendSource src{W}; ExtendSink sink{W, S};
     traceQueue<MODE, COUNT, false>(S, W.cnt[CNT_CUR], &W.cnt[CNT_WORK_TRACE], src, sink, tc);
     if (COUNT) { atomicAdd(&W.stats[ST_NODES], (unsigned long long)tc.nodes); atomicAdd(&W.stats[ST_TRIS], (unsigned long long)tc.tris); atomicAdd(&W.stats[ST_KEYS], (unsigned long long)tc.keys); }
 }

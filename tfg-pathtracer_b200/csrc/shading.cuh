@@ -73,7 +73,9 @@ __device__ __forceinline__ F3 texelAt(const DevTex& t, const float* __restrict__
 __device__ __forceinline__ F3 texFromUV(const DevTex& t, const float* lut, float u, float v) {            // :110-112
     return texelAt(t, lut, (int)(u * t.width), (int)(v * t.height));
 }
-__device__ __forceinline__ F3 texBilinear(const DevTex& t, const float* lut, float u, float v) {          // :114-135
+// cold path (Texture::filter defaults to NO_FILTER, S/Texture.hpp:21): kept out of line, inlining it at the five fetch
+// sites was a third of k_shade's 100 KB of code and the kernel stalled on instruction fetch (ncu: no_instruction)
+__device__ __noinline__ F3 texBilinear(const DevTex& t, const float* lut, float u, float v) {          // :114-135
     const float x = u * t.width, y = v * t.height;
     const float t1x = floorf(x), t1y = floorf(y), t2x = t1x + 1, t2y = t1y + 1;
     const float a = (x - t1x) / (t2x - t1x), b = (y - t1y) / (t2y - t1y);

@@ -40,8 +40,11 @@ struct LaneRay {
 // (Folding the subtraction into the FMA constant saves the FADD but loses up to 1/512 of a cell crossing time in
 // ABSOLUTE t, which is not small against the other axes' planes when the ray is nearly parallel to an axis: measured
 // false negatives on rays through box corners, so the exact form stays.)
-__device__ __forceinline__ float byteMagic(uint32_t q4, uint32_t selector) {
-    return __uint_as_float(__byte_perm(q4, 0x4B000000u, selector)) - 8388608.0f;
+// `magic` holds 0x4B000000 but arrives as scene DATA (DevScene::byteMagic) so that it lives in a register: PRMT takes one immediate, and
+// with both the selector and the constant known, ptxas kept the constant as the immediate and re-materialised the selector
+// with a MOV in front of every PRMT (24 extra ALU-pipe instructions per node on the busiest pipe, SASS of round-1 v5).
+__device__ __forceinline__ float byteMagic(uint32_t q4, uint32_t magic, uint32_t selector) {
+    return __uint_as_float(__byte_perm(q4, magic, selector)) - 8388608.0f;
 }
 
 __device__ __forceinline__ float byteI2F(uint32_t q4, int j) { return (float)((q4 >> (8 * j)) & 0xffu); }   // I2F.U8 on the conversion pipe
@@ -51,6 +54,7 @@ __device__ __forceinline__ void traceQueue(const DevScene& S, uint32_t n, uint32
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t FULL = 0xffffffffu;
     const uint32_t ltMask = (1u << lane) - 1u;
+    const uint32_t magic = S.byteMagic;
 
     bool active = false, exhausted = (S.nodeCount == 0 && false);
     LaneRay lr; lr.tag = 0; lr.tmaxAny = INFINITY; lr.ray.o = f3(0.f); lr.ray.d = f3(0.f, 0.f, 1.f);
@@ -159,9 +163,9 @@ __device__ __forceinline__ void traceQueue(const DevScene& S, uint32_t n, uint32
                         const uint32_t sel = 0x7540u + (uint32_t)j;              // bytes: q_j, 0x00, 0x00, 0x4B
                         // pipe balancing (ncu: ALU pipe 65 % busy, XU 6 %): the near planes are decoded with PRMT + FADD
                         // (ALU + FMA pipes), the far planes with I2F (conversion unit), so neither pipe carries all 48
-                        const float tminx = fmaf(byteMagic(xmin, sel), ax, ox), tmaxx = fmaf(byteI2F(xmax, j), ax, ox);
-                        const float tminy = fmaf(byteMagic(ymin, sel), ay, oy), tmaxy = fmaf(byteI2F(ymax, j), ay, oy);
-                        const float tminz = fmaf(byteMagic(zmin, sel), az, oz), tmaxz = fmaf(byteI2F(zmax, j), az, oz);
+                        const float tminx = fmaf(byteMagic(xmin, magic, sel), ax, ox), tmaxx = fmaf(byteI2F(xmax, j), ax, ox);
+                        const float tminy = fmaf(byteMagic(ymin, magic, sel), ay, oy), tmaxy = fmaf(byteI2F(ymax, j), ay, oy);
+                        const float tminz = fmaf(byteMagic(zmin, magic, sel), az, oz), tmaxz = fmaf(byteI2F(zmax, j), az, oz);
                         const float cmin = fmaxf(fmaxf(tminx, tminy), fmaxf(tminz, 0.f));
                         const float cmax = fminf(fminf(tmaxx, tmaxy), fminf(tmaxz, tcullNode));
                         if (cmin <= cmax * 1.000001f) {          // relative slack for the rounding of the fused distances
