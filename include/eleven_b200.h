@@ -164,7 +164,7 @@ typedef struct ElevenStats {
     double   connect_ms;         /*   "   : shadow-ray + MIS kernels                         */
     double   other_ms;           /*   "   : raygen, queue bookkeeping, accumulate            */
     uint64_t extend_launches;    /* closest-hit kernel launches inside eleven_render         */
-    double   bvh_build_ms;       /* host wall time of the BVH8 build                         */
+    double   bvh_build_ms;       /* wall time of the BVH8 build (host or device builder)     */
     uint32_t bvh_nodes;          /* BVH8 node count                                          */
     uint32_t bvh_tri_slots;      /* triangle slots in leaf order                             */
     float    key_slack;          /* per-scene bound on |key - t| used for culling in HIT_KEY */
@@ -217,6 +217,11 @@ int  eleven_trace_closest(ElevenCtx* ctx, const float* rays, size_t n, ElevenHit
  * occlusion only (hits[i].tri = -1 or the first triangle found). Returns device ms in *ms. */
 int  eleven_trace_device(ElevenCtx* ctx, const float* d_rays, size_t n, ElevenHit* d_hits,
                          int any_hit, float* ms);
+
+/* Test hook for the acceleration structure (replaces nothing in the reference, whose BVH is a host object,
+ * S/BVH.hpp:50-62): copies the device-resident BVH8 to host buffers — nodes (80 B each, bvh8.h Node8), triangle slots in
+ * leaf order (48 B each, TriSlot) and the per-node culling slack.  Capacities in elements; counts are in ElevenStats. */
+int  eleven_bvh_download(ElevenCtx* ctx, void* nodes, size_t node_cap, void* slots, size_t slot_cap, float* node_slack);
 
 /* Multi-GPU plumbing: the film lives as per-pixel SUMS; these expose it so the
  * caller (one process per GPU) can all-reduce it with NCCL and resolve on the root. */

@@ -1,0 +1,91 @@
+"""Host-side validator of the device-resident BVH8 (bvh8.h layout), used on the output of BOTH builders (host:
+bvh8_build.cpp, device: bvh8_build_gpu.cuh).  Checks what the traversal kernel relies on:
+
+  * every triangle sits in exactly one leaf slot, slots of a node are contiguous (<= 24), internal children contiguous
+    in ascending slot order (rank = popcount of imask below the slot);
+  * every child box, decoded the way the kernel decodes it (p + q * 2^(e-127) in float32), encloses the boxes of all the
+    triangles below it;
+  * per-node slack >= the shift bound of every triangle below.
+Returns (sah_cost, depth, node_count): SAH cost = sum over child boxes of area x (1 for an internal child, #triangles for
+a leaf child) / root area.
+"""
+import numpy as np
+
+
+def _area(lo, hi):
+    d = np.maximum(hi - lo, 0)
+    return 2.0 * (d[0] * d[1] + d[0] * d[2] + d[1] * d[2])
+
+
+def validate_bvh8(nodes, slots, slack, tris):
+    n = len(tris)
+    assert len(slots) == n
+    assert (np.sort(slots["tri"]) == np.arange(n)).all(), "every triangle must appear in exactly one slot"
+    v = tris["vertices"][slots["tri"]].astype(np.float32)            # (n, 3, 3) in slot order
+    assert (slots["v0"] == v[:, 0]).all() and (slots["e1"] == v[:, 1] - v[:, 0]).all() and (slots["e2"] == v[:, 2] - v[:, 0]).all()
+    slo, shi = v.min(1), v.max(1)
+    if n == 0:
+        return 0.0, 0, len(nodes)
+    seen_nodes = np.zeros(len(nodes), bool)
+    seen_slots = np.zeros(n, bool)
+    sub_lo = np.full((len(nodes), 3), np.inf, np.float32)
+    sub_hi = np.full((len(nodes), 3), -np.inf, np.float32)
+    sub_shift = np.zeros(len(nodes), np.float32)
+    order, depth_of = [], {0: 1}
+    stack = [0]
+    cost, root_area = 0.0, None
+    boxes = {}
+    while stack:
+        ni = stack.pop()
+        assert not seen_nodes[ni], "node %d reached twice" % ni
+        seen_nodes[ni] = True
+        order.append(ni)
+        N = nodes[ni]
+        scale = (N["e"].astype(np.uint32) << 23).view(np.float32)
+        p = N["p"]
+        qlo = np.stack([N["qlox"], N["qloy"], N["qloz"]], 1).astype(np.float32)      # (8, 3)
+        qhi = np.stack([N["qhix"], N["qhiy"], N["qhiz"]], 1).astype(np.float32)
+        blo = (p[None, :] + qlo * scale[None, :]).astype(np.float32)
+        bhi = (p[None, :] + qhi * scale[None, :]).astype(np.float32)
+        tri_off_expected, rank = 0, 0
+        for s in range(8):
+            m = int(N["meta"][s])
+            if m == 0:
+                assert not (int(N["imask"]) >> s) & 1
+                continue
+            if (m >> 5) == 1 and (m & 31) >= 24:                       # internal child
+                assert (m & 31) == 24 + s and (int(N["imask"]) >> s) & 1
+                ci = int(N["childBase"]) + rank
+                rank += 1
+                assert 0 < ci < len(nodes)
+                boxes[ci] = (ni, blo[s], bhi[s])
+                depth_of[ci] = depth_of[ni] + 1
+                stack.append(ci)
+                cost += _area(blo[s], bhi[s])
+            else:
+                assert not (int(N["imask"]) >> s) & 1
+                cnt = {1: 1, 3: 2, 7: 3}[m >> 5]
+                off = m & 31
+                assert off == tri_off_expected, "leaf children must be packed in slot order"
+                tri_off_expected += cnt
+                a = int(N["triBase"]) + off
+                assert a + cnt <= n and not seen_slots[a:a + cnt].any()
+                seen_slots[a:a + cnt] = True
+                assert (blo[s] <= slo[a:a + cnt]).all() and (bhi[s] >= shi[a:a + cnt]).all(), "leaf box does not enclose its triangles (node %d slot %d)" % (ni, s)
+                sub_lo[ni] = np.minimum(sub_lo[ni], slo[a:a + cnt].min(0)); sub_hi[ni] = np.maximum(sub_hi[ni], shi[a:a + cnt].max(0))
+                sub_shift[ni] = max(sub_shift[ni], slots["shiftBound"][a:a + cnt].max())
+                cost += _area(blo[s], bhi[s]) * cnt
+        assert tri_off_expected <= 24
+        if ni == 0:
+            root_area = _area(blo[[s for s in range(8) if N["meta"][s]]].min(0), bhi[[s for s in range(8) if N["meta"][s]]].max(0))
+    assert seen_nodes.all(), "unreachable nodes"
+    assert seen_slots.all(), "triangle slots not referenced by any leaf"
+    for ni in reversed(order):                                        # children after parents in `order`: fold bottom-up
+        if ni == 0:
+            continue
+        parent, lo, hi = boxes[ni]
+        assert (lo <= sub_lo[ni]).all() and (hi >= sub_hi[ni]).all(), "internal child box does not enclose its subtree (node %d)" % ni
+        sub_lo[parent] = np.minimum(sub_lo[parent], sub_lo[ni]); sub_hi[parent] = np.maximum(sub_hi[parent], sub_hi[ni])
+        sub_shift[parent] = max(sub_shift[parent], sub_shift[ni])
+    assert (slack >= sub_shift).all(), "per-node slack below a triangle's shift bound"
+    return cost / max(root_area, 1e-30), max(depth_of.values()), len(nodes)

@@ -11,6 +11,7 @@ Bars (BASELINE.json north_star):
 import numpy as np
 import pytest
 
+import bvh_check
 import make_golden as MG
 import oracle_lib as O
 from tfg_pathtracer_b200 import renderer as R
@@ -57,6 +58,52 @@ def test_closest_hit_bit_exact(scenes, name):
     assert exact.mean() > 0.98, (exact.mean(), tie.sum(), slab.sum())
     assert (ours["tri"] >= 0).sum() > 1000
     r.close(); orc.close()
+
+
+@pytest.mark.parametrize("name", ["cornell", "clock", "grid"])
+def test_bvh8_of_both_builders_is_valid_and_device_build_is_hit_exact(scenes, name):
+    """the BVH8 built on the GPU.  Both trees are validated on the host (bvh_check), the device
+    tree's SAH cost is the host builder's (same algorithm, different leaf policy: within 10 %), it is deterministic, and
+    closest hits through it are the oracle's bit for bit (the result does not depend on the tree)."""
+    sc = scenes[name]
+    host = R.Renderer(**R.PARITY).render_setup(sc)
+    dev = R.Renderer(bvh_builder=R.BVH_DEVICE, **R.PARITY).render_setup(sc)
+    ch, dh, nh = bvh_check.validate_bvh8(*host.bvh(), sc.tris)
+    cd, dd, nd = bvh_check.validate_bvh8(*dev.bvh(), sc.tris)
+    assert cd <= 1.10 * ch, (cd, ch)
+    assert dd < 40
+    dev2 = R.Renderer(bvh_builder=R.BVH_DEVICE, **R.PARITY).render_setup(sc)
+    for a, b in zip(dev.bvh(), dev2.bvh()):
+        assert a.tobytes() == b.tobytes(), "device build must be deterministic"
+    assert abs(dev.stats()["key_slack"] - host.stats()["key_slack"]) <= 1e-6 * host.stats()["key_slack"]
+    orc = O.Oracle(sc)
+    rays = np.concatenate([MG.ray_batch(sc, 4096, 4096, 2048, seed=5), MG.ray_batch(sc)])
+    ref, brute = orc.trace(rays, mode=0), orc.trace(rays, mode=1)
+    exact, tie, slab, bad = classify_hits(dev.trace_closest(rays), ref, brute)
+    assert bad.sum() == 0 and exact.mean() > 0.98
+    oh = host.trace_closest(rays)
+    od = dev.trace_closest(rays)
+    assert oh.tobytes() == od.tobytes(), "closest hits must not depend on the builder"
+    # and a render through the device-built tree equals the render through the host-built one, bit for bit
+    host.render_cuda(2); dev.render_cuda(2)
+    assert (bits(host.film()) == bits(dev.film())).all()
+    for r in (host, dev, dev2):
+        r.close()
+    orc.close()
+
+
+def test_device_bvh_degenerate_inputs():
+    """Duplicated triangles (all centroids coincide: median split), a single triangle, 4 triangles."""
+    base = S.cornell_box(16, env_size=(8, 8))
+    for tris in (np.repeat(base.tris[:1], 37), base.tris[:1].copy(), base.tris[:4].copy(), np.concatenate([base.tris, base.tris, base.tris])):
+        sc = S.cornell_box(16, env_size=(8, 8))
+        sc.tris = np.ascontiguousarray(tris)
+        dev = R.Renderer(bvh_builder=R.BVH_DEVICE, **R.PARITY).render_setup(sc)
+        bvh_check.validate_bvh8(*dev.bvh(), sc.tris)
+        host = R.Renderer(**R.PARITY).render_setup(sc)
+        rays = MG.ray_batch(base, 512, 512, 256, seed=2)
+        assert host.trace_closest(rays).tobytes() == dev.trace_closest(rays).tobytes()
+        dev.close(); host.close()
 
 
 @pytest.mark.parametrize("name", ["cornell", "clock"])

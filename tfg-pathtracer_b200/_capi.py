@@ -56,6 +56,12 @@ class ElevenHit(C.Structure):
     _fields_ = [("tri", C.c_int32), ("t", C.c_float), ("u", C.c_float), ("v", C.c_float), ("key", C.c_float)]
 
 
+# bvh8.h: Node8 (80 B) and TriSlot (48 B) as they live on the device
+NODE8_DT = np.dtype([("p", "<f4", 3), ("e", "u1", 3), ("imask", "u1"), ("childBase", "<u4"), ("triBase", "<u4"), ("meta", "u1", 8),
+                     ("qlox", "u1", 8), ("qloy", "u1", 8), ("qloz", "u1", 8), ("qhix", "u1", 8), ("qhiy", "u1", 8), ("qhiz", "u1", 8)])
+SLOT_DT = np.dtype([("v0", "<f4", 3), ("e1", "<f4", 3), ("e2", "<f4", 3), ("tri", "<i4"), ("material", "<i4"), ("shiftBound", "<f4")])
+assert NODE8_DT.itemsize == 80 and SLOT_DT.itemsize == 48
+
 HIT_DT = np.dtype([("tri", "<i4"), ("t", "<f4"), ("u", "<f4"), ("v", "<f4"), ("key", "<f4")])
 
 
@@ -141,6 +147,7 @@ def load_library(path: str = LIB_PATH):
     L.eleven_device_upload.argtypes = [vp, vp, vp, sz]
     L.eleven_device_download.argtypes = [vp, vp, vp, sz]
     L.eleven_resolve_rgba8.argtypes = [vp, C.c_int, vp, sz]
+    L.eleven_bvh_download.argtypes = [vp, vp, sz, vp, sz, vp]
     if L.eleven_abi_version() != 2:
         raise RuntimeError("ABI version mismatch")
     _lib = L
@@ -152,5 +159,5 @@ EXPORTED_SYMBOLS = [
     "eleven_render", "eleven_get_film", "eleven_get_pathcount", "eleven_get_samples", "eleven_get_sample_counts", "eleven_get_stats",
     "eleven_film_reset", "eleven_set_camera", "eleven_trace_closest", "eleven_trace_device", "eleven_film_sums_device",
     "eleven_film_counts_device", "eleven_device_alloc", "eleven_device_free", "eleven_device_upload",
-    "eleven_device_download", "eleven_resolve_rgba8",
+    "eleven_device_download", "eleven_resolve_rgba8", "eleven_bvh_download",
 ]

@@ -20,6 +20,7 @@
 #include "bvh8.h"
 #include "kernels.cuh"
 #include "kernels_trace.cuh"
+#include "bvh8_build_gpu.cuh"
 
 using namespace eleven;
 
@@ -246,16 +247,41 @@ extern "C" int eleven_scene_upload(ElevenCtx* c, const ElevenSceneDesc* d) {
         if (m < 0 || (uint32_t)m >= d->materialCount) return fail(ELEVEN_ERR_ARG, "object material out of range");
         triMat[i] = m;
     }
-    Bvh8 bvh;
-    buildBvh8(d->tris, d->triCount, triMat.data(), bvh, (int)std::max(1u, std::thread::hardware_concurrency()));
-    if (bvh.maxDepth >= EL_STACK) return fail(ELEVEN_ERR_UNSUPPORTED, "BVH deeper than the traversal stack");
-    c->stats.bvh_build_ms = bvh.buildMs; c->stats.bvh_nodes = (uint32_t)bvh.nodes.size(); c->stats.bvh_tri_slots = (uint32_t)bvh.slots.size();
-    c->stats.key_slack = bvh.keySlack;
-    if ((rc = devUpload(c->sceneAllocs, &S.nodes, (const float4*)bvh.nodes.data(), bvh.nodes.size() * 5))) return rc;
-    if ((rc = devUpload(c->sceneAllocs, &S.slots, (const float4*)bvh.slots.data(), bvh.slots.size() * 3))) return rc;
-    if ((rc = devUpload(c->sceneAllocs, &S.nodeSlack, bvh.nodeSlack.data(), bvh.nodeSlack.size()))) return rc;
-    S.nodeCount = d->triCount ? (uint32_t)bvh.nodes.size() : 0u; S.triCount = d->triCount; S.keySlack = bvh.keySlack;
-    {
+    if ((rc = devUpload(c->sceneAllocs, &S.triMaterial, triMat.data(), triMat.size()))) return rc;
+    const bool deviceBuild = c->cfg.bvh_builder == ELEVEN_BVH_DEVICE && d->triCount > 0;
+    if (deviceBuild) {
+        // triangles go to the device once (152 B each); boxes, the BVH8, the triangle slots and the shading records are all
+        // produced there (bvh8_build_gpu.cuh)
+        ElevenTri* d_tris = nullptr;
+        cudaError_t e = cudaMalloc((void**)&d_tris, (size_t)d->triCount * sizeof(ElevenTri));
+        if (e != cudaSuccess) return fail(ELEVEN_ERR_NOMEM, std::string("cudaMalloc(triangles): ") + cudaGetErrorString(e));
+        e = cudaMemcpyAsync(d_tris, d->tris, (size_t)d->triCount * sizeof(ElevenTri), cudaMemcpyHostToDevice, c->stream);
+        gpubvh::DeviceBvh db; std::string berr;
+        const bool ok = e == cudaSuccess && gpubvh::buildBvh8Device(d_tris, S.triMaterial, d->triCount, c->stream, db, berr);
+        float4* st = nullptr;
+        if (ok && (rc = devAlloc(c->sceneAllocs, &st, (size_t)d->triCount * 9)) == 0) {
+            gpubvh::k_shadeTris<<<(d->triCount + 255) / 256, 256, 0, c->stream>>>(d_tris, d->triCount, (float*)st);
+            e = cudaStreamSynchronize(c->stream);
+        }
+        cudaFree(d_tris);
+        if (!ok) return fail(ELEVEN_ERR_CUDA, berr.empty() ? std::string("triangle upload: ") + cudaGetErrorString(e) : berr);
+        c->sceneAllocs.push_back(db.nodes); c->sceneAllocs.push_back(db.slots); c->sceneAllocs.push_back(db.nodeSlack);
+        if (rc) return rc;
+        if (e != cudaSuccess) return fail(ELEVEN_ERR_CUDA, std::string("k_shadeTris: ") + cudaGetErrorString(e));
+        if (db.maxDepth >= EL_STACK) return fail(ELEVEN_ERR_UNSUPPORTED, "BVH deeper than the traversal stack");
+        S.nodes = db.nodes; S.slots = db.slots; S.nodeSlack = db.nodeSlack; S.shadeTris = st;
+        S.nodeCount = db.nodeCount; S.triCount = d->triCount; S.keySlack = db.keySlack;
+        c->stats.bvh_build_ms = db.buildMs; c->stats.bvh_nodes = db.nodeCount; c->stats.bvh_tri_slots = db.slotCount; c->stats.key_slack = db.keySlack;
+    } else {
+        Bvh8 bvh;
+        buildBvh8(d->tris, d->triCount, triMat.data(), bvh, (int)std::max(1u, std::thread::hardware_concurrency()));
+        if (bvh.maxDepth >= EL_STACK) return fail(ELEVEN_ERR_UNSUPPORTED, "BVH deeper than the traversal stack");
+        c->stats.bvh_build_ms = bvh.buildMs; c->stats.bvh_nodes = (uint32_t)bvh.nodes.size(); c->stats.bvh_tri_slots = (uint32_t)bvh.slots.size();
+        c->stats.key_slack = bvh.keySlack;
+        if ((rc = devUpload(c->sceneAllocs, &S.nodes, (const float4*)bvh.nodes.data(), bvh.nodes.size() * 5))) return rc;
+        if ((rc = devUpload(c->sceneAllocs, &S.slots, (const float4*)bvh.slots.data(), bvh.slots.size() * 3))) return rc;
+        if ((rc = devUpload(c->sceneAllocs, &S.nodeSlack, bvh.nodeSlack.data(), bvh.nodeSlack.size()))) return rc;
+        S.nodeCount = d->triCount ? (uint32_t)bvh.nodes.size() : 0u; S.triCount = d->triCount; S.keySlack = bvh.keySlack;
         std::vector<float> st((size_t)d->triCount * 36);
         for (uint32_t i = 0; i < d->triCount; i++) {
             const ElevenTri& T = d->tris[i]; float* o = &st[(size_t)i * 36];
@@ -267,7 +293,6 @@ extern "C" int eleven_scene_upload(ElevenCtx* c, const ElevenSceneDesc* d) {
         if ((rc = devUpload(c->sceneAllocs, &S.shadeTris, (const float4*)st.data(), (size_t)d->triCount * 9))) return rc;
     }
     if ((rc = devUpload(c->sceneAllocs, &S.objectMaterial, d->objectMaterial, d->objectCount))) return rc;
-    if ((rc = devUpload(c->sceneAllocs, &S.triMaterial, triMat.data(), triMat.size()))) return rc;
     static_assert(sizeof(DevMaterial) == sizeof(ElevenMaterial), "material layout");
     for (uint32_t i = 0; i < d->materialCount; i++) {
         const ElevenMaterial& m = d->materials[i];
@@ -583,6 +608,20 @@ extern "C" int eleven_trace_closest(ElevenCtx* c, const float* rays, size_t n, E
     if (!rc && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = fail(ELEVEN_ERR_CUDA, "sync");
     cudaFree(d_rays); cudaFree(d_hits);
     return rc;
+}
+
+// Test hook: the acceleration structure as it lives on the device (Node8 80 B, TriSlot 48 B, per-node slack), so that
+// tests can validate the tree of either builder on the host.
+extern "C" int eleven_bvh_download(ElevenCtx* c, void* nodes, size_t nodeCap, void* slots, size_t slotCap, float* nodeSlack) {
+    if (!c) return fail(ELEVEN_ERR_ARG, "eleven_bvh_download: null context");
+    if (!c->haveScene) return fail(ELEVEN_ERR_STATE, "eleven_bvh_download: no scene uploaded");
+    if (nodeCap < c->stats.bvh_nodes || slotCap < c->stats.bvh_tri_slots) return fail(ELEVEN_ERR_ARG, "eleven_bvh_download: buffers too small (see ElevenStats bvh_nodes / bvh_tri_slots)");
+    CK(cudaSetDevice(c->cfg.device));
+    if (nodes) CK(cudaMemcpyAsync(nodes, c->scene.nodes, (size_t)c->stats.bvh_nodes * 80, cudaMemcpyDeviceToHost, c->stream));
+    if (slots) CK(cudaMemcpyAsync(slots, c->scene.slots, (size_t)c->stats.bvh_tri_slots * 48, cudaMemcpyDeviceToHost, c->stream));
+    if (nodeSlack) CK(cudaMemcpyAsync(nodeSlack, c->scene.nodeSlack, (size_t)c->stats.bvh_nodes * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return ELEVEN_OK;
 }
 
 // ---- device plumbing for the one-process-per-GPU driver ------------------------------------------------------------------

@@ -18,7 +18,7 @@ import numpy as np
 
 from . import _capi
 from . import scenes as S
-from ._capi import (ENV_ALIAS, ENV_CDF, FLAG_COUNTERS, FLAG_TERMINATE_DEAD_PATHS, FLAG_TIME_KERNELS, HIT_KEY, HIT_MIN_T,  # noqa: F401
+from ._capi import (BVH_DEVICE, BVH_HOST, ENV_ALIAS, ENV_CDF, FLAG_COUNTERS, FLAG_TERMINATE_DEAD_PATHS, FLAG_TIME_KERNELS, HIT_KEY, HIT_MIN_T,  # noqa: F401
                     PASS_BEAUTY, PASS_BITANGENT, PASS_NORMAL, PASS_TANGENT, RNG_FAST, RNG_REFERENCE)
 
 
@@ -113,6 +113,15 @@ class Renderer:
         hits = np.zeros(len(rays), _capi.HIT_DT)
         self._ck(self.L.eleven_trace_closest(self.h, rays.ctypes.data, len(rays), hits.ctypes.data))
         return hits
+
+    def bvh(self):
+        """(nodes, slots, node_slack) of the device-resident BVH8 (test hook, eleven_bvh_download)."""
+        st = self.stats()
+        nodes = np.zeros(st["bvh_nodes"], _capi.NODE8_DT)
+        slots = np.zeros(st["bvh_tri_slots"], _capi.SLOT_DT)
+        slack = np.zeros(st["bvh_nodes"], np.float32)
+        self._ck(self.L.eleven_bvh_download(self.h, nodes.ctypes.data, len(nodes), slots.ctypes.data, len(slots), slack.ctypes.data))
+        return nodes, slots, slack
 
     def resolve_rgba8(self, p=PASS_BEAUTY):
         a = np.empty((self.H, self.W, 4), np.uint8)
