@@ -485,6 +485,9 @@ static bool buildBvh8Device(const ElevenTri* d_tris, const int32_t* d_triMateria
     auto cleanup = [&]() { for (void* p : tmp) cudaFree(p); tmp.clear(); };
     auto alloc = [&](void** p, size_t bytes) -> cudaError_t { cudaError_t e = cudaMalloc(p, bytes ? bytes : 1); if (e == cudaSuccess) tmp.push_back(*p); return e; };
     const auto t0 = std::chrono::steady_clock::now();
+    auto msSince = [&](std::chrono::steady_clock::time_point a) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a).count(); };
+    const bool verbose = getenv("ELEVEN_BVH_VERBOSE") != nullptr;
+    double tAlloc = 0, tPrep = 0, tLevels = 0, tCollapse = 0;
 
     float4 *boxLo = nullptr, *boxHi = nullptr; uint32_t *idxA = nullptr, *idxB = nullptr, *ownA = nullptr, *ownB = nullptr;
     uint32_t *scene = nullptr, *counters = nullptr, *actA = nullptr, *actB = nullptr, *bins = nullptr;
@@ -498,6 +501,7 @@ static bool buildBvh8Device(const ElevenTri* d_tris, const int32_t* d_triMateria
     GB_CK(alloc((void**)&actA, maxActive * 4)); GB_CK(alloc((void**)&actB, maxActive * 4));
     GB_CK(alloc((void**)&bins, maxActive * NODE_BIN_WORDS * 4));
 
+    tAlloc = msSince(t0);
     const uint32_t sceneInit[SCENE_WORDS] = {EL_ENC_POS_INF, EL_ENC_POS_INF, EL_ENC_POS_INF, EL_ENC_NEG_INF, EL_ENC_NEG_INF, EL_ENC_NEG_INF, 0u, 0u};
     GB_CK(cudaMemcpyAsync(scene, sceneInit, sizeof sceneInit, cudaMemcpyHostToDevice, st));
     const int gridN = (int)((n + 255) / 256);
@@ -526,6 +530,7 @@ static bool buildBvh8Device(const ElevenTri* d_tris, const int32_t* d_triMateria
     const uint32_t zero = 0u;
     GB_CK(cudaMemcpyAsync(actA, &zero, 4, cudaMemcpyHostToDevice, st));
 
+    tPrep = msSince(t0) - tAlloc;
     uint32_t level = 0;
     while (activeCount > 0) {
         if (level > 96) { err = "device BVH build: depth guard exceeded"; cleanup(); return false; }
@@ -545,6 +550,7 @@ static bool buildBvh8Device(const ElevenTri* d_tris, const int32_t* d_triMateria
         activeCount = next; level++;
     }
     out.levels = level;
+    tLevels = msSince(t0) - tAlloc - tPrep;
 
     // ---- collapse + emission ------------------------------------------------------------------------------------------------
     Node8* out8 = nullptr; TriSlot* slots = nullptr; float* slack = nullptr; Item8 *itA = nullptr, *itB = nullptr;
@@ -582,6 +588,7 @@ static bool buildBvh8Device(const ElevenTri* d_tris, const int32_t* d_triMateria
         itemCount = next;
     }
     out.nodeCount = n8Base; out.slotCount = slotBase; out.maxDepth = depth;
+    tCollapse = msSince(t0) - tAlloc - tPrep - tLevels;
     if (out.slotCount != n) { err = "device BVH build: emitted " + std::to_string(out.slotCount) + " triangle slots for " + std::to_string(n) + " triangles"; cleanup(); return false; }
 
     // exact-size results (the worst-case buffers above are temporary)
@@ -595,7 +602,9 @@ static bool buildBvh8Device(const ElevenTri* d_tris, const int32_t* d_triMateria
     if (es != cudaSuccess) { cudaFree(rn); cudaFree(rs); cudaFree(rk); err = std::string("device BVH build: ") + cudaGetErrorString(es); cleanup(); return false; }
     out.nodes = (float4*)rn; out.slots = (float4*)rs; out.nodeSlack = (float*)rk;
     cleanup();
-    out.buildMs = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    out.buildMs = msSince(t0);
+    if (verbose) fprintf(stderr, "[eleven] device BVH: %u tris, %u levels, %u wide nodes, depth %u: alloc %.2f ms, prep %.2f, levels %.2f, collapse+alloc %.2f, copy+free %.2f, total %.2f ms\n",
+                         n, level, out.nodeCount, depth, tAlloc, tPrep, tLevels, tCollapse, out.buildMs - tAlloc - tPrep - tLevels - tCollapse, out.buildMs);
     return true;
 }
 #undef GB_CK

@@ -233,6 +233,37 @@ __global__ void __launch_bounds__(128, EL_SHADE_MIN_CTAS) k_shade(WaveState W, c
                 W.rad[pid] = r;
             } else {
                 const uint32_t depth = W.depth[pid];
+                // --- random numbers: 3 for the bounce, 3 for shade of which only the first is used.  Drawn FIRST:
+                //     they need only (pid, depth), and the environment sample's table + texel fetches (two dependent gathers into
+                //     ~200 MB) can then fly while the triangle and the texture maps are fetched
+                float b1, b2, b3, s1; uint32_t aliasBitsA = 0, aliasBitsB = 0, lightBits = 0;
+                if (P.rngMode == ELEVEN_RNG_REFERENCE) {
+                    Xorwow s = W.rng[pid];
+                    b1 = xorwowUniform(s); b2 = xorwowUniform(s); b3 = xorwowUniform(s);
+                    s1 = xorwowUniform(s); xorwowNext(s); xorwowNext(s);
+                    W.rng[pid] = s;
+                } else {
+                    const uint4 a = fastBits(P, pid, 2u + 2u * depth);
+                    b1 = u32ToUniform(a.x); b2 = u32ToUniform(a.y); b3 = u32ToUniform(a.z); s1 = u32ToUniform(a.w);
+                    const uint4 c = fastBits(P, pid, 3u + 2u * depth);
+                    aliasBitsA = c.x; aliasBitsB = c.y; lightBits = c.z;
+                }
+                // --- environment NEE, part 1: pick the texel (hdriLight, S/kernel.cu:236-242) and fetch it
+                const int EW = S.hdri.width, EH = S.hdri.height;
+                int texel;
+                if (P.envMode == ELEVEN_ENV_CDF) texel = cdfSearch(S.cdf, s1, EW * EH);
+                else {
+                    const uint32_t nT = (uint32_t)(EW * EH);
+                    const uint32_t k = P.rngMode == ELEVEN_RNG_REFERENCE ? min(nT - 1u, (uint32_t)(s1 * (float)nT)) : __umulhi(aliasBitsA, nT);
+                    const float xi = P.rngMode == ELEVEN_RNG_REFERENCE ? s1 * (float)nT - floorf(s1 * (float)nT) : u32ToUniform(aliasBitsB);
+                    const AliasEntry ae = S.alias[k];
+                    texel = xi <= ae.prob ? (int)k : (int)ae.alias;
+                }
+                const float sx = (float)(texel % EW), sy = (float)(texel / EW);
+                const float nu = sx / (float)EW, nv = sy / (float)EH;
+                float iu, iv; inverseTransformUV(S.hdri, nu, nv, iu, iv);
+                const float4 ev = envTexelRaw(S.hdri, (int)(iu * EW), (int)(iv * EH));
+
                 // --- hit attributes: Tri::hit's second half (S/Tri.hpp:70-157), exact arithmetic -----------------
                 const float t = hv.y, u = hv.z, v = hv.w;
                 const float4* tp = S.shadeTris + (size_t)tri * 9;
@@ -252,42 +283,15 @@ __global__ void __launch_bounds__(128, EL_SHADE_MIN_CTAS) k_shade(WaveState W, c
                 HitData hd;
                 generateHitData<FM>(S, m, hd, N, T, B, tUV.x, tUV.y);
 
-                // --- random numbers: 3 for the bounce, 3 for shade of which only the first is used
-                float b1, b2, b3, s1; uint32_t aliasBitsA = 0, aliasBitsB = 0, lightBits = 0;
-                if (P.rngMode == ELEVEN_RNG_REFERENCE) {
-                    Xorwow s = W.rng[pid];
-                    b1 = xorwowUniform(s); b2 = xorwowUniform(s); b3 = xorwowUniform(s);
-                    s1 = xorwowUniform(s); xorwowNext(s); xorwowNext(s);
-                    W.rng[pid] = s;
-                } else {
-                    const uint4 a = fastBits(P, pid, 2u + 2u * depth);
-                    b1 = u32ToUniform(a.x); b2 = u32ToUniform(a.y); b3 = u32ToUniform(a.z); s1 = u32ToUniform(a.w);
-                    const uint4 c = fastBits(P, pid, 3u + 2u * depth);
-                    aliasBitsA = c.x; aliasBitsB = c.y; lightBits = c.z;
-                }
                 const BrdfFrame bf = makeBrdfFrame<FM>(hd, ray.d);
                 const F3 L = disneySample<FM>(hd, bf, b1, b2, b3);
                 const F3 fB = disneyEval<FM>(hd, bf, L);
                 const float pB = disneyPdf<FM>(hd, bf, L);
 
-                // --- environment NEE set-up (hdriLight, S/kernel.cu:236-256) -----------------------------------
-                const int EW = S.hdri.width, EH = S.hdri.height;
-                int texel;
-                if (P.envMode == ELEVEN_ENV_CDF) texel = cdfSearch(S.cdf, s1, EW * EH);
-                else {
-                    const uint32_t nT = (uint32_t)(EW * EH);
-                    const uint32_t k = P.rngMode == ELEVEN_RNG_REFERENCE ? min(nT - 1u, (uint32_t)(s1 * (float)nT)) : __umulhi(aliasBitsA, nT);
-                    const float xi = P.rngMode == ELEVEN_RNG_REFERENCE ? s1 * (float)nT - floorf(s1 * (float)nT) : u32ToUniform(aliasBitsB);
-                    const AliasEntry ae = S.alias[k];
-                    texel = xi <= ae.prob ? (int)k : (int)ae.alias;
-                }
-                const float sx = (float)(texel % EW), sy = (float)(texel / EW);
-                const float nu = sx / (float)EW, nv = sy / (float)EH;
-                float iu, iv; inverseTransformUV(S.hdri, nu, nv, iu, iv);
+                // --- environment NEE, part 2 (hdriLight, S/kernel.cu:243-256) -----------------------------------
                 const F3 rsm = M<FM>::normalized(reverseSphericalMapping<FM>(iu, iv));
                 const F3 wE = f3(-rsm.x, -rsm.y, -rsm.z);
-                const float4 ev = envTexelRaw(S.hdri, (int)(iu * EW), (int)(iv * EH));
-                const float pE = hdriPdf<FM>(S, (int)(iu * EW), (int)(iv * EH));
+                const float pE = hdriPdf<FM>(S, ev, (int)(iv * EH));
                 const F3 fE = disneyEval<FM>(hd, bf, wE);
                 const float cE = fabsf(dot(wE, hd.normal));
                 const F3 CE = f3(M<FM>::div(fE.x * cE * ev.x, pE), M<FM>::div(fE.y * cE * ev.y, pE), M<FM>::div(fE.z * cE * ev.z, pE));

@@ -83,7 +83,7 @@ __device__ __noinline__ F3 texBilinear(const DevTex& t, const float* lut, float 
     const F3 v3 = texelAt(t, lut, (int)t1x, (int)t2y), v4 = texelAt(t, lut, (int)t2x, (int)t2y);
     return lerp3(lerp3(v1, v2, a), lerp3(v3, v4, a), b);
 }
-__device__ __forceinline__ F3 texFiltered(const DevTex& t, const float* lut, float u, float v) {          // :137-142
+__device__ __noinline__ F3 texFiltered(const DevTex& t, const float* lut, float u, float v) {          // :137-142 (cold: float or filtered maps)
     return t.filter == 0 ? texFromUV(t, lut, u, v) : texBilinear(t, lut, u, v);
 }
 
@@ -135,10 +135,9 @@ __device__ __forceinline__ int cdfSearch(const float* __restrict__ arr, float va
     }
     return to;
 }
-// S/HDRI.hpp:145-152
+// S/HDRI.hpp:145-152; dv = the texel at (x, y), fetched by the caller (k_shade issues that load early)
 template <bool FM>
-__device__ __forceinline__ float hdriPdf(const DevScene& S, int x, int y) {
-    const float4 dv = envTexelRaw(S.hdri, x, y);
+__device__ __forceinline__ float hdriPdf(const DevScene& S, float4 dv, int y) {
     const float theta = (((float)y / (float)S.hdri.height)) * EL_PI;
     const float num = ((dv.w) / S.radianceSum) * S.hdri.width * S.hdri.height;
     if (FM) return __fdividef(num, 2.0f * EL_PI * __sinf(theta));
@@ -290,15 +289,55 @@ __device__ __forceinline__ F3 disneySample(const HitData& hd, const BrdfFrame& f
 // ---- S/kernel.cu:54-119 generateHitData ---------------------------------------------------------------
 template <bool FM>
 __device__ __forceinline__ void generateHitData(const DevScene& S, const DevMaterial& m, HitData& hd, F3 normal, F3 tangent, F3 bitangent, float tu, float tv) {
-    hd.albedo = m.albedoTex < 0 ? f3(m.albedo[0], m.albedo[1], m.albedo[2]) : texFiltered(S.textures[m.albedoTex], S.lut, tu, tv);
-    hd.emission = m.emissionTex < 0 ? f3(m.emission[0], m.emission[1], m.emission[2]) : texFiltered(S.textures[m.emissionTex], S.lut, tu, tv);
-    hd.roughness = m.roughnessTex < 0 ? m.roughness : texFiltered(S.textures[m.roughnessTex], S.lut, tu, tv).x;
-    hd.metallic = m.metallicTex < 0 ? m.metallic : texFiltered(S.textures[m.metallicTex], S.lut, tu, tv).x;
-    if (m.normalTex < 0) hd.normal = normal;
-    else {
-        const F3 nc = texFromUV(S.textures[m.normalTex], S.lut, tu, tv);
-        const F3 ln = f3(nc.x * 2 - 1, nc.y * 2 - 1, nc.z * 2 - 1);
-        hd.normal = M<FM>::normalized(ln.x * tangent - ln.y * bitangent + ln.z * normal);
+    // Memory-level parallelism: the texel fetches are gathers into ~1 GB of maps (DRAM latency each).  Fetched one after
+    // the other, each behind the decode of the previous one, they were four of the five hottest stall sites of k_shade
+    // (ncu source view, round 1).  When every bound map is 8-bit and unfiltered (what the loader produces) all texel loads
+    // are issued back to back, then decoded.
+    const int ids[5] = {m.albedoTex, m.emissionTex, m.roughnessTex, m.metallicTex, m.normalTex};
+    bool batch = true;
+    uint32_t fmt[5];
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        fmt[k] = 0;
+        if (ids[k] >= 0) {
+            const DevTex& T = S.textures[ids[k]];
+            fmt[k] = T.format;
+            batch = batch && T.format != ELEVEN_TEX_F32_RGB && (k == 4 || T.filter == 0);
+        }
+    }
+    if (batch) {
+        uint32_t c[5];                             // texels kept as packed words until all five loads are in flight
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+            c[k] = 0u;
+            if (ids[k] >= 0) { const DevTex& T = S.textures[ids[k]]; c[k] = __ldg((const uint32_t*)T.data + texelIndex(T, (int)(tu * T.width), (int)(tv * T.height))); }
+        }
+        F3 val[5];
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+            const float* l = S.lut + (fmt[k] == ELEVEN_TEX_U8_SRGB ? 0 : 256);
+            val[k] = ids[k] >= 0 ? f3(__ldg(l + (c[k] & 0xffu)), __ldg(l + ((c[k] >> 8) & 0xffu)), __ldg(l + ((c[k] >> 16) & 0xffu))) : f3(0.f);
+        }
+        hd.albedo = ids[0] < 0 ? f3(m.albedo[0], m.albedo[1], m.albedo[2]) : val[0];
+        hd.emission = ids[1] < 0 ? f3(m.emission[0], m.emission[1], m.emission[2]) : val[1];
+        hd.roughness = ids[2] < 0 ? m.roughness : val[2].x;
+        hd.metallic = ids[3] < 0 ? m.metallic : val[3].x;
+        if (ids[4] < 0) hd.normal = normal;
+        else {
+            const F3 ln = f3(val[4].x * 2 - 1, val[4].y * 2 - 1, val[4].z * 2 - 1);
+            hd.normal = M<FM>::normalized(ln.x * tangent - ln.y * bitangent + ln.z * normal);
+        }
+    } else {
+        hd.albedo = m.albedoTex < 0 ? f3(m.albedo[0], m.albedo[1], m.albedo[2]) : texFiltered(S.textures[m.albedoTex], S.lut, tu, tv);
+        hd.emission = m.emissionTex < 0 ? f3(m.emission[0], m.emission[1], m.emission[2]) : texFiltered(S.textures[m.emissionTex], S.lut, tu, tv);
+        hd.roughness = m.roughnessTex < 0 ? m.roughness : texFiltered(S.textures[m.roughnessTex], S.lut, tu, tv).x;
+        hd.metallic = m.metallicTex < 0 ? m.metallic : texFiltered(S.textures[m.metallicTex], S.lut, tu, tv).x;
+        if (m.normalTex < 0) hd.normal = normal;
+        else {
+            const F3 nc = texFromUV(S.textures[m.normalTex], S.lut, tu, tv);
+            const F3 ln = f3(nc.x * 2 - 1, nc.y * 2 - 1, nc.z * 2 - 1);
+            hd.normal = M<FM>::normalized(ln.x * tangent - ln.y * bitangent + ln.z * normal);
+        }
     }
     hd.roughness = M<FM>::pow(hd.roughness, 2.2f);      // "linear to sRGB", applied to constants too (S/kernel.cu:103-104)
     hd.metallic = M<FM>::pow(hd.metallic, 2.2f);
