@@ -92,6 +92,23 @@ def test_bvh8_of_both_builders_is_valid_and_device_build_is_hit_exact(scenes, na
     orc.close()
 
 
+def test_device_bvh_chunked_binning_and_overflow_retry(scenes, monkeypatch):
+    """The device builder bins the active nodes of a level in chunks (bounded scratch) and sizes the wide-node buffers for
+    n/2 nodes, rebuilding with worst-case buffers on overflow.  Both paths must give the very same tree."""
+    sc = scenes["clock"]
+    ref = R.Renderer(bvh_builder=R.BVH_DEVICE, **R.PARITY).render_setup(sc)
+    want = [a.tobytes() for a in ref.bvh()]
+    ref.close()
+    for env in ({"ELEVEN_BVH_TEST_BIN_CHUNK": "97"}, {"ELEVEN_BVH_TEST_WIDE_DIV": "64"}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        r = R.Renderer(bvh_builder=R.BVH_DEVICE, **R.PARITY).render_setup(sc)
+        assert [a.tobytes() for a in r.bvh()] == want, env
+        r.close()
+        for k in env:
+            monkeypatch.delenv(k)
+
+
 def test_device_bvh_degenerate_inputs():
     """Duplicated triangles (all centroids coincide: median split), a single triangle, 4 triangles."""
     base = S.cornell_box(16, env_size=(8, 8))

@@ -169,22 +169,25 @@ __device__ __forceinline__ void binUpdate(uint32_t* b, const float* lo, const fl
 
 __global__ void __launch_bounds__(256) k_bin(const float4* __restrict__ boxLo, const float4* __restrict__ boxHi, const uint32_t* __restrict__ idx,
                                              const uint32_t* __restrict__ owner, const Node2G* __restrict__ nodes, uint32_t* __restrict__ bins,
-                                             uint32_t n, float pad) {
+                                             uint32_t n, float pad, int slotBase, int slotCount) {
     __shared__ uint32_t sb[NODE_BIN_WORDS];
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t b0 = blockIdx.x * blockDim.x, b1 = min(n, b0 + blockDim.x) - 1u;
     const uint32_t nodeA = owner[b0], nodeB = owner[b1];
     const bool priv = nodeA == nodeB;                                // the block lies inside one node: bins in shared memory
+    // the active nodes of a level are binned in chunks of `slotCount` nodes (bounded scratch): this launch serves the nodes
+    // whose slot lies in [slotBase, slotBase + slotCount)
     if (priv) {
-        if (nodes[nodeA].binSlot < 0) return;                        // ... which is not being split: nothing to do for the block
+        const int sA = nodes[nodeA].binSlot - slotBase;
+        if (nodes[nodeA].binSlot < 0 || sA < 0 || sA >= slotCount) return;   // ... which is not being split in this chunk: nothing to do for the block
         for (uint32_t w = threadIdx.x; w < NODE_BIN_WORDS; w += blockDim.x) { const uint32_t k = w % BIN_WORDS; sb[w] = k < 3 ? EL_ENC_POS_INF : (k < 6 ? EL_ENC_NEG_INF : 0u); }
         __syncthreads();
     }
     if (i < n) {
         const uint32_t o = priv ? nodeA : owner[i];
         const Node2G& N = nodes[o];
-        const int slot = N.binSlot;
-        if (slot >= 0) {
+        const int slot = N.binSlot - slotBase;
+        if (N.binSlot >= 0 && slot >= 0 && slot < slotCount) {
             const uint32_t t = idx[i];
             const float4 l = boxLo[t], h = boxHi[t];
             const float lo[3] = {l.x - pad, l.y - pad, l.z - pad}, hi[3] = {h.x + pad, h.y + pad, h.z + pad};
@@ -200,7 +203,7 @@ __global__ void __launch_bounds__(256) k_bin(const float4* __restrict__ boxLo, c
     }
     if (priv) {
         __syncthreads();
-        uint32_t* g = bins + (size_t)nodes[nodeA].binSlot * NODE_BIN_WORDS;
+        uint32_t* g = bins + (size_t)(nodes[nodeA].binSlot - slotBase) * NODE_BIN_WORDS;
         for (uint32_t w = threadIdx.x; w < NODE_BIN_WORDS; w += blockDim.x) {
             const uint32_t k = w % BIN_WORDS, v = sb[w];
             if (k < 3) { if (v != EL_ENC_POS_INF) atomicMin(&g[w], v); }
@@ -212,12 +215,13 @@ __global__ void __launch_bounds__(256) k_bin(const float4* __restrict__ boxLo, c
 }
 
 __global__ void __launch_bounds__(128) k_split(Node2G* __restrict__ nodes, const uint32_t* __restrict__ bins, const uint32_t* __restrict__ active,
-                                               uint32_t activeCount, uint32_t* __restrict__ nextActive, uint32_t* __restrict__ counters, int forceMedian) {
-    const uint32_t ai = blockIdx.x * blockDim.x + threadIdx.x;
+                                               uint32_t activeCount, uint32_t* __restrict__ nextActive, uint32_t* __restrict__ counters, int forceMedian,
+                                               int slotBase) {
+    const uint32_t ai = blockIdx.x * blockDim.x + threadIdx.x;       // index inside the chunk; `active` points at the chunk
     if (ai >= activeCount) return;
     const uint32_t ni = active[ai];
     Node2G N = nodes[ni];
-    const uint32_t* B = bins + (size_t)N.binSlot * NODE_BIN_WORDS;
+    const uint32_t* B = bins + (size_t)(N.binSlot - slotBase) * NODE_BIN_WORDS;
     float bestCost = INFINITY; int bestAxis = -1, bestSplit = -1;
     if (!forceMedian) {
         for (int a = 0; a < 3; a++) {
@@ -477,31 +481,62 @@ struct DeviceBvh {
     double buildMs = 0.0;
 };
 
-#define GB_CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { err = std::string(#call) + ": " + cudaGetErrorString(e_); cleanup(); return false; } } while (0)
+// Build scratch: ONE device allocation carved into the builder's arrays, owned by the context and kept for the next build.
+// (cudaMalloc / cudaFree of the ~20 separate multi-GB buffers of the first version cost 5-10x the kernels: 155 ms + 190-590 ms
+// against 56 ms of kernels for 10 M triangles.)
+struct BuildArena { char* base = nullptr; size_t bytes = 0; };
+
+enum { BIN_CHUNK_NODES = 131072 };   // nodes binned per launch: 131 072 x 1 536 B = 201 MB of bins whatever the scene
+
+#define GB_CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { err = std::string(#call) + ": " + cudaGetErrorString(e_); return false; } } while (0)
 
 // d_tris: the scene's triangles already on the device; d_triMaterial: per-triangle material.  n > 0.
-static bool buildBvh8Device(const ElevenTri* d_tris, const int32_t* d_triMaterial, uint32_t n, cudaStream_t st, DeviceBvh& out, std::string& err) {
-    std::vector<void*> tmp;
-    auto cleanup = [&]() { for (void* p : tmp) cudaFree(p); tmp.clear(); };
-    auto alloc = [&](void** p, size_t bytes) -> cudaError_t { cudaError_t e = cudaMalloc(p, bytes ? bytes : 1); if (e == cudaSuccess) tmp.push_back(*p); return e; };
+static bool buildBvh8Device(const ElevenTri* d_tris, const int32_t* d_triMaterial, uint32_t n, cudaStream_t st, BuildArena& arena, DeviceBvh& out, std::string& err) {
     const auto t0 = std::chrono::steady_clock::now();
     auto msSince = [&](std::chrono::steady_clock::time_point a) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a).count(); };
     const bool verbose = getenv("ELEVEN_BVH_VERBOSE") != nullptr;
+
+    for (int attempt = 0; attempt < 2; attempt++) {
     double tAlloc = 0, tPrep = 0, tLevels = 0, tCollapse = 0;
-
-    float4 *boxLo = nullptr, *boxHi = nullptr; uint32_t *idxA = nullptr, *idxB = nullptr, *ownA = nullptr, *ownB = nullptr;
-    uint32_t *scene = nullptr, *counters = nullptr, *actA = nullptr, *actB = nullptr, *bins = nullptr;
-    Node2G* nodes = nullptr;
-    GB_CK(alloc((void**)&boxLo, (size_t)n * 16)); GB_CK(alloc((void**)&boxHi, (size_t)n * 16));
-    GB_CK(alloc((void**)&idxA, (size_t)n * 4)); GB_CK(alloc((void**)&idxB, (size_t)n * 4));
-    GB_CK(alloc((void**)&ownA, (size_t)n * 4)); GB_CK(alloc((void**)&ownB, (size_t)n * 4));
-    GB_CK(alloc((void**)&scene, SCENE_WORDS * 4)); GB_CK(alloc((void**)&counters, C_COUNT * 4));
+    const auto tA = std::chrono::steady_clock::now();
+    // wide nodes: one per ~4.6 triangles in practice; n + 1 is the worst case (second attempt, after an overflow)
+    // (ELEVEN_BVH_TEST_WIDE_DIV / ELEVEN_BVH_TEST_BIN_CHUNK: test knobs that force the overflow retry and the chunked binning on small scenes)
+    const char* eDiv = getenv("ELEVEN_BVH_TEST_WIDE_DIV"); const char* eChunk = getenv("ELEVEN_BVH_TEST_BIN_CHUNK");
+    const size_t wideDiv = eDiv ? std::max(2, atoi(eDiv)) : 2, binChunk = eChunk ? std::max(1, atoi(eChunk)) : (size_t)BIN_CHUNK_NODES;
+    const size_t wideCap = attempt == 0 ? std::min<size_t>((size_t)n + 1, (size_t)n / wideDiv + (eDiv ? 2 : 1024)) : (size_t)n + 1;
     const size_t maxNodes = 2 * (size_t)n + 2, maxActive = (size_t)n / (MAX_LEAF + 1) + 2;
-    GB_CK(alloc((void**)&nodes, maxNodes * sizeof(Node2G)));
-    GB_CK(alloc((void**)&actA, maxActive * 4)); GB_CK(alloc((void**)&actB, maxActive * 4));
-    GB_CK(alloc((void**)&bins, maxActive * NODE_BIN_WORDS * 4));
+    const size_t binNodes = std::min<size_t>(maxActive, binChunk);
+    size_t scanBytes = 0;
+    GB_CK(cub::DeviceScan::ExclusiveSum(nullptr, scanBytes, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)wideCap, st));
 
-    tAlloc = msSince(t0);
+    float4 *boxLo, *boxHi; uint32_t *idxA, *idxB, *ownA, *ownB, *scene, *counters, *actA, *actB, *bins; Node2G* nodes;
+    Node8* out8; TriSlot* slots; float* slack; Item8 *itA, *itB; int32_t* childAt; uint32_t *nInt, *nTri, *offInt, *offTri; void* scanTmp;
+    auto layout = [&](char* base) -> size_t {
+        size_t off = 0;
+        auto take = [&](size_t bytes) -> char* { off = (off + 255) & ~(size_t)255; char* r = base ? base + off : nullptr; off += bytes; return r; };
+        boxLo = (float4*)take((size_t)n * 16); boxHi = (float4*)take((size_t)n * 16);
+        idxA = (uint32_t*)take((size_t)n * 4); idxB = (uint32_t*)take((size_t)n * 4); ownA = (uint32_t*)take((size_t)n * 4); ownB = (uint32_t*)take((size_t)n * 4);
+        scene = (uint32_t*)take(SCENE_WORDS * 4); counters = (uint32_t*)take(C_COUNT * 4);
+        nodes = (Node2G*)take(maxNodes * sizeof(Node2G));
+        actA = (uint32_t*)take(maxActive * 4); actB = (uint32_t*)take(maxActive * 4);
+        bins = (uint32_t*)take(binNodes * NODE_BIN_WORDS * 4);
+        out8 = (Node8*)take(wideCap * sizeof(Node8)); slots = (TriSlot*)take((size_t)n * sizeof(TriSlot)); slack = (float*)take(wideCap * 4);
+        itA = (Item8*)take(wideCap * sizeof(Item8)); itB = (Item8*)take(wideCap * sizeof(Item8));
+        childAt = (int32_t*)take(wideCap * 8 * 4);
+        nInt = (uint32_t*)take(wideCap * 4); nTri = (uint32_t*)take(wideCap * 4); offInt = (uint32_t*)take(wideCap * 4); offTri = (uint32_t*)take(wideCap * 4);
+        scanTmp = take(scanBytes);
+        return off;
+    };
+    const size_t need = layout(nullptr);
+    if (arena.bytes < need) {
+        if (arena.base) cudaFree(arena.base);
+        arena.base = nullptr; arena.bytes = 0;
+        GB_CK(cudaMalloc((void**)&arena.base, need));
+        arena.bytes = need;
+    }
+    layout(arena.base);
+    tAlloc = msSince(tA);
+
     const uint32_t sceneInit[SCENE_WORDS] = {EL_ENC_POS_INF, EL_ENC_POS_INF, EL_ENC_POS_INF, EL_ENC_NEG_INF, EL_ENC_NEG_INF, EL_ENC_NEG_INF, 0u, 0u};
     GB_CK(cudaMemcpyAsync(scene, sceneInit, sizeof sceneInit, cudaMemcpyHostToDevice, st));
     const int gridN = (int)((n + 255) / 256);
@@ -529,16 +564,19 @@ static bool buildBvh8Device(const ElevenTri* d_tris, const int32_t* d_triMateria
     GB_CK(cudaMemcpyAsync(counters, cnt, sizeof cnt, cudaMemcpyHostToDevice, st));
     const uint32_t zero = 0u;
     GB_CK(cudaMemcpyAsync(actA, &zero, 4, cudaMemcpyHostToDevice, st));
+    tPrep = msSince(tA) - tAlloc;
 
-    tPrep = msSince(t0) - tAlloc;
     uint32_t level = 0;
     while (activeCount > 0) {
-        if (level > 96) { err = "device BVH build: depth guard exceeded"; cleanup(); return false; }
-        const size_t words = (size_t)activeCount * NODE_BIN_WORDS;
-        k_initBins<<<(unsigned)((words + 255) / 256), 256, 0, st>>>(bins, words);
+        if (level > 96) { err = "device BVH build: depth guard exceeded"; return false; }
         k_centroid<<<gridN, 256, 0, st>>>(boxLo, boxHi, idxA, ownA, nodes, n);
-        k_bin<<<gridN, 256, 0, st>>>(boxLo, boxHi, idxA, ownA, nodes, bins, n, pad);
-        k_split<<<(activeCount + 127) / 128, 128, 0, st>>>(nodes, bins, actA, activeCount, actB, counters, level >= 48 ? 1 : 0);
+        for (uint32_t c0 = 0; c0 < activeCount; c0 += (uint32_t)binNodes) {
+            const uint32_t cn = std::min<uint32_t>((uint32_t)binNodes, activeCount - c0);
+            const size_t words = (size_t)cn * NODE_BIN_WORDS;
+            k_initBins<<<(unsigned)((words + 255) / 256), 256, 0, st>>>(bins, words);
+            k_bin<<<gridN, 256, 0, st>>>(boxLo, boxHi, idxA, ownA, nodes, bins, n, pad, (int)c0, (int)cn);
+            k_split<<<(cn + 127) / 128, 128, 0, st>>>(nodes, bins, actA + c0, cn, actB, counters, level >= 48 ? 1 : 0, (int)c0);
+        }
         k_partition<<<gridN, 256, 0, st>>>(boxLo, boxHi, idxA, ownA, idxB, ownB, nodes, n);
         k_retire<<<(activeCount + 255) / 256, 256, 0, st>>>(nodes, actA, activeCount);
         uint32_t next = 0;
@@ -550,62 +588,60 @@ static bool buildBvh8Device(const ElevenTri* d_tris, const int32_t* d_triMateria
         activeCount = next; level++;
     }
     out.levels = level;
-    tLevels = msSince(t0) - tAlloc - tPrep;
+    tLevels = msSince(tA) - tAlloc - tPrep;
 
     // ---- collapse + emission ------------------------------------------------------------------------------------------------
-    Node8* out8 = nullptr; TriSlot* slots = nullptr; float* slack = nullptr; Item8 *itA = nullptr, *itB = nullptr;
-    int32_t* childAt = nullptr; uint32_t *nInt = nullptr, *nTri = nullptr, *offInt = nullptr, *offTri = nullptr; void* scanTmp = nullptr;
-    const size_t maxN8 = (size_t)n + 1;
-    GB_CK(alloc((void**)&out8, maxN8 * sizeof(Node8))); GB_CK(alloc((void**)&slots, (size_t)n * sizeof(TriSlot)));
-    GB_CK(alloc((void**)&slack, maxN8 * 4)); GB_CK(alloc((void**)&itA, maxN8 * sizeof(Item8))); GB_CK(alloc((void**)&itB, maxN8 * sizeof(Item8)));
-    GB_CK(alloc((void**)&childAt, maxN8 * 8 * 4));
-    GB_CK(alloc((void**)&nInt, maxN8 * 4)); GB_CK(alloc((void**)&nTri, maxN8 * 4)); GB_CK(alloc((void**)&offInt, maxN8 * 4)); GB_CK(alloc((void**)&offTri, maxN8 * 4));
-    size_t scanBytes = 0;
-    GB_CK(cub::DeviceScan::ExclusiveSum(nullptr, scanBytes, nInt, offInt, (int)maxN8, st));
-    GB_CK(alloc(&scanTmp, scanBytes));
     Item8 first; first.n2 = 0; first.n8 = 0; first.depth = 1;
     GB_CK(cudaMemcpyAsync(itA, &first, sizeof first, cudaMemcpyHostToDevice, st));
     uint32_t itemCount = 1, n8Base = 1, slotBase = 0, depth = 0;
+    bool overflow = false;
     while (itemCount > 0) {
         depth++;
         const unsigned grid = (itemCount + 127) / 128;
         k_collapseGather<<<grid, 128, 0, st>>>(nodes, itA, itemCount, childAt, nInt, nTri);
         GB_CK(cub::DeviceScan::ExclusiveSum(scanTmp, scanBytes, nInt, offInt, (int)itemCount, st));
         GB_CK(cub::DeviceScan::ExclusiveSum(scanTmp, scanBytes, nTri, offTri, (int)itemCount, st));
-        k_collapseEmit<<<grid, 128, 0, st>>>(nodes, idxA, d_tris, d_triMaterial, boxLo, itA, itemCount, childAt, offInt, offTri, n8Base, slotBase,
-                                             itB, out8, slots, slack);
         uint32_t last[4];
         GB_CK(cudaMemcpyAsync(&last[0], offInt + itemCount - 1, 4, cudaMemcpyDeviceToHost, st));
         GB_CK(cudaMemcpyAsync(&last[1], nInt + itemCount - 1, 4, cudaMemcpyDeviceToHost, st));
         GB_CK(cudaMemcpyAsync(&last[2], offTri + itemCount - 1, 4, cudaMemcpyDeviceToHost, st));
         GB_CK(cudaMemcpyAsync(&last[3], nTri + itemCount - 1, 4, cudaMemcpyDeviceToHost, st));
         GB_CK(cudaStreamSynchronize(st));
-        GB_CK(cudaGetLastError());
         const uint32_t next = last[0] + last[1];
+        if ((size_t)n8Base + next > wideCap || (size_t)slotBase + last[2] + last[3] > n) { overflow = true; break; }   // before anything is written out of bounds
+        k_collapseEmit<<<grid, 128, 0, st>>>(nodes, idxA, d_tris, d_triMaterial, boxLo, itA, itemCount, childAt, offInt, offTri, n8Base, slotBase,
+                                             itB, out8, slots, slack);
+        GB_CK(cudaGetLastError());
         n8Base += next; slotBase += last[2] + last[3];
-        if ((size_t)n8Base > maxN8 || slotBase > n) { err = "device BVH build: collapse overflow"; cleanup(); return false; }
         std::swap(itA, itB);
         itemCount = next;
     }
+    if (overflow) {
+        if (attempt == 0 && wideCap < (size_t)n + 1) continue;       // more wide nodes than n/2: rebuild with worst-case buffers
+        err = "device BVH build: collapse overflow"; return false;
+    }
+    GB_CK(cudaStreamSynchronize(st));
     out.nodeCount = n8Base; out.slotCount = slotBase; out.maxDepth = depth;
-    tCollapse = msSince(t0) - tAlloc - tPrep - tLevels;
-    if (out.slotCount != n) { err = "device BVH build: emitted " + std::to_string(out.slotCount) + " triangle slots for " + std::to_string(n) + " triangles"; cleanup(); return false; }
+    tCollapse = msSince(tA) - tAlloc - tPrep - tLevels;
+    if (out.slotCount != n) { err = "device BVH build: emitted " + std::to_string(out.slotCount) + " triangle slots for " + std::to_string(n) + " triangles"; return false; }
 
-    // exact-size results (the worst-case buffers above are temporary)
+    // exact-size results (the arena is scratch)
     void *rn = nullptr, *rs = nullptr, *rk = nullptr;
     cudaError_t e1 = cudaMalloc(&rn, (size_t)out.nodeCount * sizeof(Node8)), e2 = cudaMalloc(&rs, (size_t)n * sizeof(TriSlot)), e3 = cudaMalloc(&rk, (size_t)out.nodeCount * 4);
-    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) { cudaFree(rn); cudaFree(rs); cudaFree(rk); err = "device BVH build: out of memory"; cleanup(); return false; }
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) { cudaFree(rn); cudaFree(rs); cudaFree(rk); err = "device BVH build: out of memory"; return false; }
     cudaMemcpyAsync(rn, out8, (size_t)out.nodeCount * sizeof(Node8), cudaMemcpyDeviceToDevice, st);
     cudaMemcpyAsync(rs, slots, (size_t)n * sizeof(TriSlot), cudaMemcpyDeviceToDevice, st);
     cudaMemcpyAsync(rk, slack, (size_t)out.nodeCount * 4, cudaMemcpyDeviceToDevice, st);
     cudaError_t es = cudaStreamSynchronize(st);
-    if (es != cudaSuccess) { cudaFree(rn); cudaFree(rs); cudaFree(rk); err = std::string("device BVH build: ") + cudaGetErrorString(es); cleanup(); return false; }
+    if (es != cudaSuccess) { cudaFree(rn); cudaFree(rs); cudaFree(rk); err = std::string("device BVH build: ") + cudaGetErrorString(es); return false; }
     out.nodes = (float4*)rn; out.slots = (float4*)rs; out.nodeSlack = (float*)rk;
-    cleanup();
     out.buildMs = msSince(t0);
-    if (verbose) fprintf(stderr, "[eleven] device BVH: %u tris, %u levels, %u wide nodes, depth %u: alloc %.2f ms, prep %.2f, levels %.2f, collapse+alloc %.2f, copy+free %.2f, total %.2f ms\n",
-                         n, level, out.nodeCount, depth, tAlloc, tPrep, tLevels, tCollapse, out.buildMs - tAlloc - tPrep - tLevels - tCollapse, out.buildMs);
+    if (verbose) fprintf(stderr, "[eleven] device BVH: %u tris, %u levels, %u wide nodes, depth %u, scratch %.0f MB: alloc %.2f ms, prep %.2f, levels %.2f, collapse %.2f, results %.2f, total %.2f ms\n",
+                         n, level, out.nodeCount, depth, need / 1048576.0, tAlloc, tPrep, tLevels, tCollapse, msSince(tA) - tAlloc - tPrep - tLevels - tCollapse, out.buildMs);
     return true;
+    }
+    err = "device BVH build: unreachable";
+    return false;
 }
 #undef GB_CK
 

@@ -54,6 +54,7 @@ struct ElevenCtx {
     ElevenCamera* d_camera = nullptr;
     std::vector<cudaEvent_t> evPool;
     ElevenStats stats;
+    gpubvh::BuildArena bvhArena;                 // device BVH build scratch, kept for re-builds
 };
 
 extern "C" int eleven_abi_version(void) { return ELEVEN_ABI_VERSION; }
@@ -106,6 +107,7 @@ extern "C" void eleven_destroy(ElevenCtx* c) {
     cudaSetDevice(c->cfg.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     freeAll(c->sceneAllocs); freeAll(c->waveAllocs);
+    if (c->bvhArena.base) cudaFree(c->bvhArena.base);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     for (cudaEvent_t e : c->evPool) cudaEventDestroy(e);
@@ -257,7 +259,7 @@ extern "C" int eleven_scene_upload(ElevenCtx* c, const ElevenSceneDesc* d) {
         if (e != cudaSuccess) return fail(ELEVEN_ERR_NOMEM, std::string("cudaMalloc(triangles): ") + cudaGetErrorString(e));
         e = cudaMemcpyAsync(d_tris, d->tris, (size_t)d->triCount * sizeof(ElevenTri), cudaMemcpyHostToDevice, c->stream);
         gpubvh::DeviceBvh db; std::string berr;
-        const bool ok = e == cudaSuccess && gpubvh::buildBvh8Device(d_tris, S.triMaterial, d->triCount, c->stream, db, berr);
+        const bool ok = e == cudaSuccess && gpubvh::buildBvh8Device(d_tris, S.triMaterial, d->triCount, c->stream, c->bvhArena, db, berr);
         float4* st = nullptr;
         if (ok && (rc = devAlloc(c->sceneAllocs, &st, (size_t)d->triCount * 9)) == 0) {
             gpubvh::k_shadeTris<<<(d->triCount + 255) / 256, 256, 0, c->stream>>>(d_tris, d->triCount, (float*)st);
