@@ -291,7 +291,7 @@ def main():
         stage = rt.stats()
         rt.close()
     # ---- timed: e2e ---------------------------------------------------------------------------------------
-    host_film = np.empty((H, W, 4), np.float32)
+    host_film = r.pinned_array((H, W, 4), np.float32)                 # page-locked host buffer for the per-step film read-back
     r.reset()
     barrier()
     t1 = time.perf_counter()

@@ -227,6 +227,10 @@ int  eleven_bvh_download(ElevenCtx* ctx, void* nodes, size_t node_cap, void* slo
  * caller (one process per GPU) can all-reduce it with NCCL and resolve on the root. */
 int  eleven_film_sums_device(ElevenCtx* ctx, int pass, void** d_ptr, size_t* n_floats);
 int  eleven_film_counts_device(ElevenCtx* ctx, void** d_ptr, size_t* n_uints);
+/* Page-locked host memory for film read-backs / ray batches: copies to and from it run at PCIe/C2C rate instead of going
+ * through the driver's staging buffer (the reference's host film buffers are pageable `new float[]`, S/main.cpp:44-49). */
+int  eleven_host_alloc(ElevenCtx* ctx, size_t bytes, void** h_ptr);
+int  eleven_host_free(ElevenCtx* ctx, void* h_ptr);
 int  eleven_device_alloc(ElevenCtx* ctx, size_t bytes, void** d_ptr);
 int  eleven_device_free(ElevenCtx* ctx, void* d_ptr);
 int  eleven_device_upload(ElevenCtx* ctx, void* d_dst, const void* h_src, size_t bytes);

@@ -148,6 +148,8 @@ def load_library(path: str = LIB_PATH):
     L.eleven_device_download.argtypes = [vp, vp, vp, sz]
     L.eleven_resolve_rgba8.argtypes = [vp, C.c_int, vp, sz]
     L.eleven_bvh_download.argtypes = [vp, vp, sz, vp, sz, vp]
+    L.eleven_host_alloc.argtypes = [vp, sz, C.POINTER(vp)]
+    L.eleven_host_free.argtypes = [vp, vp]
     if L.eleven_abi_version() != 2:
         raise RuntimeError("ABI version mismatch")
     _lib = L
@@ -159,5 +161,6 @@ EXPORTED_SYMBOLS = [
     "eleven_render", "eleven_get_film", "eleven_get_pathcount", "eleven_get_samples", "eleven_get_sample_counts", "eleven_get_stats",
     "eleven_film_reset", "eleven_set_camera", "eleven_trace_closest", "eleven_trace_device", "eleven_film_sums_device",
     "eleven_film_counts_device", "eleven_device_alloc", "eleven_device_free", "eleven_device_upload",
-    "eleven_device_download", "eleven_resolve_rgba8", "eleven_bvh_download",
+    "eleven_device_download", "eleven_resolve_rgba8", "eleven_bvh_download", "eleven_host_alloc",
+    "eleven_host_free",
 ]

@@ -646,6 +646,18 @@ extern "C" int eleven_device_alloc(ElevenCtx* c, size_t bytes, void** p) {
     if (e != cudaSuccess) return fail(ELEVEN_ERR_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
     return ELEVEN_OK;
 }
+extern "C" int eleven_host_alloc(ElevenCtx* c, size_t bytes, void** p) {
+    if (!c || !p) return fail(ELEVEN_ERR_ARG, "eleven_host_alloc: null argument");
+    CK(cudaSetDevice(c->cfg.device));
+    cudaError_t e = cudaMallocHost(p, std::max<size_t>(bytes, 1));
+    if (e != cudaSuccess) return fail(ELEVEN_ERR_NOMEM, std::string("cudaMallocHost: ") + cudaGetErrorString(e));
+    return ELEVEN_OK;
+}
+extern "C" int eleven_host_free(ElevenCtx* c, void* p) {
+    if (!c) return fail(ELEVEN_ERR_ARG, "eleven_host_free: null context");
+    CK(cudaFreeHost(p));
+    return ELEVEN_OK;
+}
 extern "C" int eleven_device_free(ElevenCtx* c, void* p) {
     if (!c) return fail(ELEVEN_ERR_ARG, "eleven_device_free: null context");
     CK(cudaSetDevice(c->cfg.device)); CK(cudaFree(p)); return ELEVEN_OK;

@@ -66,15 +66,16 @@ int main(int argc, char** argv) {
                s.materials.size(), s.textures.size(), s.lights.size(), argv[3]);
         return 0;
     }
-    if (argc < 4) { fprintf(stderr, "usage: eleven <scene_path> <#samples> <output.bmp> [--mode fast|parity] [--gpus N] [--slice K] [--raw file.f32]\n"); return 2; }
+    if (argc < 4) { fprintf(stderr, "usage: eleven <scene_path> <#samples> <output.bmp> [--mode fast|parity] [--gpus N] [--slice K] [--bvh device|host] [--raw file.f32]\n"); return 2; }
     const std::string scenePath = argv[1], outPath = argv[3];
     const int spp = atoi(argv[2]);
-    bool fast = true; int gpus = 1, slice = 16; const char* rawPath = nullptr;
+    bool fast = true, deviceBvh = true; int gpus = 1, slice = 16; const char* rawPath = nullptr;
     for (int i = 4; i < argc; i++) {
         if (!strcmp(argv[i], "--mode") && i + 1 < argc) fast = strcmp(argv[++i], "parity") != 0;
         else if (!strcmp(argv[i], "--gpus") && i + 1 < argc) gpus = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--slice") && i + 1 < argc) slice = std::max(1, atoi(argv[++i]));
         else if (!strcmp(argv[i], "--raw") && i + 1 < argc) rawPath = argv[++i];
+        else if (!strcmp(argv[i], "--bvh") && i + 1 < argc) deviceBvh = strcmp(argv[++i], "host") != 0;
         else { fprintf(stderr, "eleven: unknown option %s\n", argv[i]); return 2; }
     }
     if (spp <= 0 || gpus < 1) { fprintf(stderr, "eleven: bad sample or GPU count\n"); return 2; }
@@ -96,6 +97,7 @@ int main(int argc, char** argv) {
         j.cfg.rng_mode = fast ? ELEVEN_RNG_FAST : ELEVEN_RNG_REFERENCE; j.cfg.env_mode = fast ? ELEVEN_ENV_ALIAS : ELEVEN_ENV_CDF;
         j.cfg.hit_mode = ELEVEN_HIT_KEY; j.cfg.flags = fast ? (ELEVEN_FLAG_TERMINATE_DEAD_PATHS | ELEVEN_FLAG_SKIP_NULL_NEE | ELEVEN_FLAG_FAST_MATH) : 0u;
         j.cfg.sample_offset = (uint32_t)g; j.cfg.sample_stride = (uint32_t)gpus;
+        j.cfg.bvh_builder = deviceBvh ? ELEVEN_BVH_DEVICE : ELEVEN_BVH_HOST;
         j.spp = spp / gpus + (g < spp % gpus ? 1 : 0);          // global sample s goes to device s % gpus
     }
     t0 = nowS();

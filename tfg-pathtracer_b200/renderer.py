@@ -27,7 +27,8 @@ class ElevenError(RuntimeError):
 
 
 PARITY = dict(rng_mode=RNG_REFERENCE, env_mode=ENV_CDF, hit_mode=HIT_KEY, flags=0)
-FAST = dict(rng_mode=RNG_FAST, env_mode=ENV_ALIAS, hit_mode=HIT_KEY, flags=FLAG_TERMINATE_DEAD_PATHS | _capi.FLAG_SKIP_NULL_NEE | _capi.FLAG_FAST_MATH)
+FAST = dict(rng_mode=RNG_FAST, env_mode=ENV_ALIAS, hit_mode=HIT_KEY, flags=FLAG_TERMINATE_DEAD_PATHS | _capi.FLAG_SKIP_NULL_NEE | _capi.FLAG_FAST_MATH,
+            bvh_builder=BVH_DEVICE)
 
 
 class Renderer:
@@ -43,6 +44,7 @@ class Renderer:
         self._ck(self.L.eleven_init(C.byref(self.cfg), C.byref(self.h)))
         self.W = self.H = 0
         self._keep = None
+        self._pinned = []
 
     def _ck(self, rc):
         if rc != 0:
@@ -50,6 +52,9 @@ class Renderer:
 
     def close(self):
         if getattr(self, "h", None):
+            for p in getattr(self, "_pinned", []):
+                self.L.eleven_host_free(self.h, p)
+            self._pinned = []
             self.L.eleven_destroy(self.h)
             self.h = None
 
@@ -148,6 +153,15 @@ class Renderer:
         ms = C.c_float()
         self._ck(self.L.eleven_trace_device(self.h, d_rays, n, d_hits, 1 if any_hit else 0, C.byref(ms)))
         return ms.value
+
+    def pinned_array(self, shape, dtype=np.float32):
+        """numpy array over page-locked host memory (eleven_host_alloc); freed by close()."""
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        self._ck(self.L.eleven_host_alloc(self.h, n, C.byref(p)))
+        self._pinned.append(p)
+        buf = (C.c_char * n).from_address(p.value)
+        return np.frombuffer(buf, dtype=dtype).reshape(shape)
 
     def film_sums_ptr(self, p=PASS_BEAUTY):
         ptr, n = C.c_void_p(), C.c_size_t()

@@ -36,7 +36,7 @@ def run(name, sc, nrays):
     out = {"scene": name, "tris": int(len(sc.tris)), "rays": int(len(rays))}
     hits = {}
     for label, builder in (("host", R.BVH_HOST), ("device", R.BVH_DEVICE)):
-        r = R.Renderer(bvh_builder=builder, **R.FAST)
+        r = R.Renderer(**dict(R.FAST, bvh_builder=builder))
         t0 = time.time()
         r.render_setup(sc)
         upload_s = time.time() - t0
