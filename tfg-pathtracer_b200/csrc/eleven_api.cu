@@ -417,6 +417,11 @@ extern "C" int eleven_render(ElevenCtx* c, int spp) {
     const int gridPix = (int)((n + 255) / 256);
     c->P.sampleStride = c->cfg.sample_stride;
     const int gridPersist = c->numSMs * 8;             // 148 SMs x 8 CTAs of 128 threads: a multiple of the SM count
+    // traversal kernels: as many CTAs per SM as their register count admits (k_extend 64 registers -> 8, shadow 56 -> 9);
+    // ELEVEN_GRID_EXTEND / ELEVEN_GRID_SHADOW override the CTAs per SM (tuning knobs)
+    static const int ctasExtend = getenv("ELEVEN_GRID_EXTEND") ? std::max(1, atoi(getenv("ELEVEN_GRID_EXTEND"))) : 8;
+    static const int ctasShadow = getenv("ELEVEN_GRID_SHADOW") ? std::max(1, atoi(getenv("ELEVEN_GRID_SHADOW"))) : 8;
+    const int gridExtend = c->numSMs * ctasExtend, gridShadow = c->numSMs * ctasShadow;
     const bool count = (c->cfg.flags & ELEVEN_FLAG_COUNTERS) != 0;
     const bool timeK = (c->cfg.flags & ELEVEN_FLAG_TIME_KERNELS) != 0;
     const bool fastMath = (c->cfg.flags & ELEVEN_FLAG_FAST_MATH) != 0;
@@ -441,7 +446,7 @@ extern "C" int eleven_render(ElevenCtx* c, int spp) {
         else k_raygen<false><<<gridPaths, 256, 0, c->stream>>>(c->W, c->scene, c->P);
         mark(3);
         for (uint32_t b = 0; b < c->cfg.max_bounces; b++) {
-            if (count) launchExtend<true>(c, gridPersist); else launchExtend<false>(c, gridPersist);
+            if (count) launchExtend<true>(c, gridExtend); else launchExtend<false>(c, gridExtend);
             mark(0);
             k_classify<<<gridPersist, 128, 0, c->stream>>>(c->W, c->scene);
             if (fastMath) k_shade<true><<<gridPersist, 128, 0, c->stream>>>(c->W, c->scene, c->P);
@@ -449,7 +454,7 @@ extern "C" int eleven_render(ElevenCtx* c, int spp) {
             mark(1);
             k_advance<<<1, 32, 0, c->stream>>>(c->W, c->scene.lightCount, 0);
             mark(3);
-            c->stats.kernel_launches += count ? launchConnect<true>(c, gridPersist) : launchConnect<false>(c, gridPersist);
+            c->stats.kernel_launches += count ? launchConnect<true>(c, gridShadow) : launchConnect<false>(c, gridShadow);
             mark(2);
             k_advance<<<1, 32, 0, c->stream>>>(c->W, c->scene.lightCount, 1);
             mark(3);

@@ -14,6 +14,10 @@
 
 namespace eleven {
 
+#ifndef EL_EXTEND_MIN_CTAS
+#define EL_EXTEND_MIN_CTAS 8      /* 64 registers, 8 CTAs per SM; measured equal to 72 registers x 7 CTAs, and 93 registers x 5 CTAs (no bound) is 13 % slower */
+#endif
+
 // ---- extension rays -----------------------------------------------------------------------------------------------------
 struct ExtendSource {
     const WaveState& W;
@@ -35,7 +39,7 @@ struct ExtendSink {
     }
 };
 template <int MODE, bool COUNT>
-__global__ void __launch_bounds__(128) k_extend(const __grid_constant__ WaveState W, const __grid_constant__ DevScene S) {
+__global__ void __launch_bounds__(128, EL_EXTEND_MIN_CTAS) k_extend(const __grid_constant__ WaveState W, const __grid_constant__ DevScene S) {
     TraceCounters tc; tc.nodes = 0; tc.tris = 0; tc.keys = 0;
     ExtendSource src{W}; ExtendSink sink{W, S};
     traceQueue<MODE, COUNT, false>(S, W.cnt[CNT_CUR], &W.cnt[CNT_WORK_TRACE], src, sink, tc);
