@@ -124,7 +124,7 @@ struct DevScene {
     const float* lights;          // n x 6
     uint32_t lightCount, triCount, nodeCount;
     float keySlack;
-    uint32_t byteMagic;           // 0x4B000000, passed as DATA so that the compiler keeps it in a register (trace_engine.cuh: byteMagic)
+    uint32_t byteMagic;           // 0x47000000, passed as DATA so that the compiler keeps it in a register (trace_engine.cuh: byteMagic15)
     DevCamera cam;
 };
 

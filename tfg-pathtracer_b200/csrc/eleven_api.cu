@@ -237,7 +237,7 @@ extern "C" int eleven_scene_upload(ElevenCtx* c, const ElevenSceneDesc* d) {
     c->d_seqMat = nullptr; c->d_camera = nullptr;
     c->haveScene = false;
     DevScene& S = c->scene; memset(&S, 0, sizeof S);
-    S.byteMagic = 0x4B000000u;
+    S.byteMagic = 0x47000000u;
     int rc;
 
     // triangles -> per-triangle material, BVH8, shading records

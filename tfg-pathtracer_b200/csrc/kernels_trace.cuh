@@ -15,7 +15,7 @@
 namespace eleven {
 
 #ifndef EL_EXTEND_MIN_CTAS
-#define EL_EXTEND_MIN_CTAS 8      /* 64 registers, 8 CTAs per SM; measured equal to 72 registers x 7 CTAs, and 93 registers x 5 CTAs (no bound) is 13 % slower */
+#define EL_EXTEND_MIN_CTAS 7      /* <= 72 registers, 7 CTAs per SM: no spills; 64 registers x 8 CTAs measured equal (but spills in KEY mode), no bound (93 registers x 5 CTAs) is 13 % slower */
 #endif
 
 // ---- extension rays -----------------------------------------------------------------------------------------------------

@@ -36,15 +36,16 @@ struct LaneRay {
     uint32_t tag;              /* opaque to the engine (path id / ray index) */
 };
 
-// float(byte j of q4) without the conversion pipe: 0x4B000000 | b is 2^23 + b exactly (one PRMT + one FADD).
-// (Folding the subtraction into the FMA constant saves the FADD but loses up to 1/512 of a cell crossing time in
-// ABSOLUTE t, which is not small against the other axes' planes when the ray is nearly parallel to an axis: measured
-// false negatives on rays through box corners, so the exact form stays.)
-// `magic` holds 0x4B000000 but arrives as scene DATA (DevScene::byteMagic) so that it lives in a register: PRMT takes one immediate, and
-// with both the selector and the constant known, ptxas kept the constant as the immediate and re-materialised the selector
-// with a MOV in front of every PRMT (24 extra ALU-pipe instructions per node on the busiest pipe, SASS of round-1 v5).
-__device__ __forceinline__ float byteMagic(uint32_t q4, uint32_t magic, uint32_t selector) {
-    return __uint_as_float(__byte_perm(q4, magic, selector)) - 8388608.0f;
+// 2^15 + (byte j of q4) as a float with ONE instruction and no conversion pipe: PRMT drops the byte into mantissa bits 8..15
+// of 0x47000000 (= 2^15, ulp 2^-8).  The 2^15 is folded into the FMA's addend once per node and axis (oN = o - 2^15 a), so a
+// near plane costs PRMT + FFMA.  (Round 1 used 0x4B000000|b = 2^23 + b and an FADD per byte: folding THAT offset loses half a
+// cell, because 2^23 a is 2^15 cells away; 2^15 a is 128 node widths away and its rounding, <= 2^-9 cell, is covered by moving
+// oN towards the ray origin by 2^-23 |oN|, i.e. the near planes only ever move outwards.)
+// `magic` holds 0x47000000 but arrives as scene DATA (DevScene::byteMagic) so that it lives in a register: PRMT takes one
+// immediate, and with both the selector and the constant known, ptxas kept the constant as the immediate and re-materialised
+// the selector with a MOV in front of every PRMT (24 extra ALU-pipe instructions per node on the busiest pipe).
+__device__ __forceinline__ float byteMagic15(uint32_t q4, uint32_t magic, uint32_t selector) {
+    return __uint_as_float(__byte_perm(q4, magic, selector));
 }
 
 __device__ __forceinline__ float byteI2F(uint32_t q4, int j) { return (float)((q4 >> (8 * j)) & 0xffu); }   // I2F.U8 on the conversion pipe
@@ -144,6 +145,9 @@ __device__ __forceinline__ void traceQueue(const DevScene& S, uint32_t n, uint32
                 const float ay = __uint_as_float(((eim >> 8) & 0xffu) << 23) * idy;
                 const float az = __uint_as_float(((eim >> 16) & 0xffu) << 23) * idz;
                 const float ox = (n0.x - o.x) * idx, oy = (n0.y - o.y) * idy, oz = (n0.z - o.z) * idz;
+                // addends of the near planes: o - 2^15 a, nudged towards the ray origin by its own rounding bound (see byteMagic15)
+                const float oxN0 = fmaf(-32768.f, ax, ox), oyN0 = fmaf(-32768.f, ay, oy), ozN0 = fmaf(-32768.f, az, oz);
+                const float oxN = fmaf(-fabsf(oxN0), 1.1920929e-7f, oxN0), oyN = fmaf(-fabsf(oyN0), 1.1920929e-7f, oyN0), ozN = fmaf(-fabsf(ozN0), 1.1920929e-7f, ozN0);
                 uint32_t hitmask = 0;
 #pragma unroll
                 for (int half = 0; half < 2; half++) {
@@ -160,12 +164,12 @@ __device__ __forceinline__ void traceQueue(const DevScene& S, uint32_t n, uint32
                     const uint32_t zmin = dz < 0.f ? qhiz : qloz, zmax = dz < 0.f ? qloz : qhiz;
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
-                        const uint32_t sel = 0x7540u + (uint32_t)j;              // bytes: q_j, 0x00, 0x00, 0x4B
-                        // pipe balancing (ncu: ALU pipe 65 % busy, XU 6 %): the near planes are decoded with PRMT + FADD
-                        // (ALU + FMA pipes), the far planes with I2F (conversion unit), so neither pipe carries all 48
-                        const float tminx = fmaf(byteMagic(xmin, magic, sel), ax, ox), tmaxx = fmaf(byteI2F(xmax, j), ax, ox);
-                        const float tminy = fmaf(byteMagic(ymin, magic, sel), ay, oy), tmaxy = fmaf(byteI2F(ymax, j), ay, oy);
-                        const float tminz = fmaf(byteMagic(zmin, magic, sel), az, oz), tmaxz = fmaf(byteI2F(zmax, j), az, oz);
+                        const uint32_t sel = 0x7504u + ((uint32_t)j << 4);       // bytes: 0x00, q_j, 0x00, 0x47
+                        // pipe balancing (ncu: ALU pipe 65 % busy, XU 6 %): the near planes are decoded with PRMT (ALU pipe, the
+                        // offset folded into the FMA), the far planes with I2F (conversion unit), so neither pipe carries all 48
+                        const float tminx = fmaf(byteMagic15(xmin, magic, sel), ax, oxN), tmaxx = fmaf(byteI2F(xmax, j), ax, ox);
+                        const float tminy = fmaf(byteMagic15(ymin, magic, sel), ay, oyN), tmaxy = fmaf(byteI2F(ymax, j), ay, oy);
+                        const float tminz = fmaf(byteMagic15(zmin, magic, sel), az, ozN), tmaxz = fmaf(byteI2F(zmax, j), az, oz);
                         const float cmin = fmaxf(fmaxf(tminx, tminy), fmaxf(tminz, 0.f));
                         const float cmax = fminf(fminf(tmaxx, tmaxy), fminf(tmaxz, tcullNode));
                         if (cmin <= cmax * 1.000001f) {          // relative slack for the rounding of the fused distances
