@@ -128,14 +128,14 @@ def get_scene(args, need_dir):
 
 
 # ------------------------------------------------------------------------------------------------------
-def run_reference(args, rank):
+def run_reference(args, rank, out):
     if rank != 0:
         return
     binp = os.path.join(ROOT, "oracle", "_ref", "eleven_ref_headless_fast")
     base = {"impl": "reference", "metric": "samples_per_second", "unit": "pixel-samples/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic"}
     if not os.path.exists(binp):
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/eleven_ref_headless_fast not built (needs /root/reference at build time)"}))
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/eleven_ref_headless_fast not built (needs /root/reference at build time)"}), file=out, flush=True)
         return
     flat, sdir = get_scene(args, need_dir=True)
     spp_w, spp_t = args.warmup * args.ref_spp_per_step, args.steps * args.ref_spp_per_step
@@ -146,7 +146,7 @@ def run_reference(args, rank):
     wall = time.time() - t0
     clocks = sm.stop()
     if p.returncode != 0:
-        print(json.dumps({"impl": "reference", "unavailable": "reference run failed rc=%d: %s" % (p.returncode, (p.stderr or p.stdout)[-300:].replace("\n", " "))}))
+        print(json.dumps({"impl": "reference", "unavailable": "reference run failed rc=%d: %s" % (p.returncode, (p.stderr or p.stdout)[-300:].replace("\n", " "))}), file=out, flush=True)
         return
     info = json.loads(open(os.path.join(CACHE, "ref_out.json")).read())
     v = info["samples_per_s"]
@@ -160,7 +160,7 @@ def run_reference(args, rank):
                  "reference": {"load_ms": info["load_ms"], "setup_ms": info["setup_ms"], "render_ms": info["render_ms"], "kpaths_per_s": info["kpaths_per_s"],
                                "hit_bounces": info["hit_bounces"], "wall_s": wall},
                  "clocks": clocks, "gpu_launches": spp_t + spp_w})
-    print(json.dumps(base))
+    print(json.dumps(base), file=out, flush=True)
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -208,8 +208,13 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE line, the JSON: anything native libraries print to fd 1 (NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    json_out = os.fdopen(json_fd, "w")
     if args.impl == "reference":
-        run_reference(args, rank)
+        run_reference(args, rank, json_out)
         return
 
     import torch
@@ -334,7 +339,9 @@ def main():
             "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "ClockCC0 stand-in (125281 tris, 12x%d^2 8-bit maps, 4096x2048 HDRI, defocus) %dx%d, %d spp/step/GPU, mode=%s" % (args.tex, W, H, S_, args.mode),
                        "spp_per_step": S_, "parallelism": "sample-split x%d, scene replicated, 1 NCCL reduce of film sums per step" % world,
-                       "l2": "inputs larger than L2 (textures 805 MB + HDRI 134 MB + 0.7 GB wave state vs 126 MB L2); no flush needed"},
+                       "l2": "inputs larger than L2 (textures 805 MB + HDRI 134 MB + 12 GB wave state vs 126 MB L2); no flush needed",
+                       "wave_spp": "auto (16 samples of every pixel in flight per wave)" if (args.wave_spp == 0 and args.mode == "fast") else (args.wave_spp if args.mode == "fast" else 1),
+                       "timing": "host clock between device synchronisations (barrier + cudaDeviceSynchronize on both sides), max over ranks; kernel times from CUDA events on the context's stream"},
             "mrays_per_s": rays_total / dt / 1e6,
             "frame_spp_per_s": S_ * args.steps * world / dt,
             "e2e": {"value": total / dt_e2e, "unit": "pixel-samples/s", "h2d_bytes_per_step": 56, "d2h_bytes_per_step": W * H * 16},
@@ -351,7 +358,7 @@ def main():
         }
         if not args.no_cpu_baseline and world == 1:
             out["cpu_baseline"] = cpu_baseline(args, flat)
-        print(json.dumps(out))
+        print(json.dumps(out), file=json_out, flush=True)
     r.close()
     if world > 1:
         dist.barrier()

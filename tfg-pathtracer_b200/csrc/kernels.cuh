@@ -142,9 +142,7 @@ __global__ void __launch_bounds__(256) k_raygen(WaveState W, const __grid_consta
     W.rayD[i] = make_float4(ray.d.x, ray.d.y, ray.d.z, 0.f);
     W.thr[i] = make_float4(1.f, 1.f, 1.f, 0.f);
     W.rad[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-    W.aovN[i] = z; W.aovT[i] = z; W.aovB[i] = z;
-    W.depth[i] = 0u;
+    W.depth[i] = 0u;                 // the first-hit AOVs are written by k_shade at depth 0; k_accumulate reads them only where depth > 0
     W.qCur[i] = i;
     if (i == 0) {
         W.cnt[CNT_CUR] = nPaths; W.cnt[CNT_NEXT] = 0u; W.cnt[CNT_NEE] = 0u;
@@ -388,12 +386,14 @@ __global__ void __launch_bounds__(256) k_accumulate(WaveState W, uint32_t logK) 
         float4 r = W.rad[p];
         r.x = clampf_(r.x, 0.f, 10.f); r.y = clampf_(r.y, 0.f, 10.f); r.z = clampf_(r.z, 0.f, 10.f);
         const bool ok = !isnan(r.x) && !isnan(r.y) && !isnan(r.z);
-        const float4 n = W.aovN[p], t = W.aovT[p], bt = W.aovB[p];
+        const uint32_t dep = W.depth[p];
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 n = dep ? W.aovN[p] : z, t = dep ? W.aovT[p] : z, bt = dep ? W.aovB[p] : z;     // camera ray escaped: AOVs are 0 (S/kernel.cu:388-391)
         sv[0][tid][0] = r.x; sv[0][tid][1] = r.y; sv[0][tid][2] = r.z;
         sv[1][tid][0] = n.x; sv[1][tid][1] = n.y; sv[1][tid][2] = n.z;
         sv[2][tid][0] = t.x; sv[2][tid][1] = t.y; sv[2][tid][2] = t.z;
         sv[3][tid][0] = bt.x; sv[3][tid][1] = bt.y; sv[3][tid][2] = bt.z;
-        sdepth[tid] = W.depth[p]; sok[tid] = ok ? 1 : 0;
+        sdepth[tid] = dep; sok[tid] = ok ? 1 : 0;
     }
     __syncthreads();
     const uint32_t K = 1u << logK, pixPerBlock = 256u >> logK;
