@@ -73,6 +73,9 @@ typedef struct ElevenConfig {
 #define ELEVEN_FLAG_TIME_KERNELS         4u  /* CUDA-event timing around every pipeline stage (ElevenStats *_ms)   */
 #define ELEVEN_FLAG_FAST_MATH           16u  /* shading with MUFU reciprocal/rsqrt/sin/cos/log2/exp2 and float intermediates, like the
                                               * reference's shipping -use_fast_math build; geometry (t,u,v,key) stays bit-exact */
+#define ELEVEN_FLAG_ANYHIT_LIGHT_SHADOWS 32u  /* point-light shadow rays stop at the first occluder with t < |L - P| instead of taking the
+                                              * reference's closest hit and comparing |hit.position - P| (S/kernel.cu:193-197): differs only
+                                              * where an occluder lies within the shadow-terminator shift + 1 mm of the light itself */
 #define ELEVEN_FLAG_SKIP_NULL_NEE        8u  /* no env shadow ray when its contribution is 0 whatever it hits (no point
                                               * lights, no emission, BRDF 0 towards the sample): same image, fewer rays */
 

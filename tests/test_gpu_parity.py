@@ -235,6 +235,20 @@ def test_wave_spp_does_not_change_the_film(scenes):
         R.Renderer(**dict(R.FAST, wave_spp=3))
 
 
+def test_anyhit_light_shadows_equal_closest_hit_light_shadows(scenes):
+    """ELEVEN_FLAG_ANYHIT_LIGHT_SHADOWS: point-light shadow rays stop at the first occluder in front of the light instead of
+    taking the reference's closest hit (S/kernel.cu:193-197).  Same random numbers, so the film is identical except where
+    an occluder sits within the shadow-terminator shift + 1 mm of the light itself."""
+    sc = scenes["cornell"]
+    base = dict(R.FAST); base["flags"] &= ~R._capi.FLAG_ANYHIT_LIGHT_SHADOWS
+    a = R.Renderer(**base).render_setup(sc); a.render_cuda(16)
+    b = R.Renderer(**R.FAST).render_setup(sc); b.render_cuda(16)
+    fa, fb = a.film()[..., :3], b.film()[..., :3]
+    assert (bits(fa) == bits(fb)).all(-1).mean() >= 0.999
+    assert a.stats()["rays_shadow_light"] == b.stats()["rays_shadow_light"] > 0
+    a.close(); b.close()
+
+
 def test_env_alias_matches_cdf_distribution(scenes):
     sc = scenes["clock"]
     a = R.Renderer(rng_mode=R.RNG_FAST, env_mode=R.ENV_CDF, flags=0).render_setup(sc); a.render_cuda(96)

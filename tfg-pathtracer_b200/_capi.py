@@ -21,7 +21,7 @@ RNG_REFERENCE, RNG_FAST = 0, 1
 ENV_CDF, ENV_ALIAS = 0, 1
 HIT_KEY, HIT_MIN_T = 0, 1
 BVH_HOST, BVH_DEVICE = 0, 1
-FLAG_TERMINATE_DEAD_PATHS, FLAG_COUNTERS, FLAG_TIME_KERNELS, FLAG_SKIP_NULL_NEE, FLAG_FAST_MATH = 1, 2, 4, 8, 16
+FLAG_TERMINATE_DEAD_PATHS, FLAG_COUNTERS, FLAG_TIME_KERNELS, FLAG_SKIP_NULL_NEE, FLAG_FAST_MATH, FLAG_ANYHIT_LIGHT_SHADOWS = 1, 2, 4, 8, 16, 32
 
 
 class ElevenConfig(C.Structure):

@@ -403,7 +403,7 @@ template <bool COUNT>
 static int launchConnect(ElevenCtx* c, int grid) {
     if (c->scene.lightCount == 0) { k_shadowEnv<false, COUNT><<<grid, 128, 0, c->stream>>>(c->W, c->scene); return 1; }
     k_shadowEnv<true, COUNT><<<grid, 128, 0, c->stream>>>(c->W, c->scene);
-    if (c->cfg.hit_mode == ELEVEN_HIT_KEY) k_shadowLight<ELEVEN_HIT_KEY, COUNT><<<grid, 128, 0, c->stream>>>(c->W, c->scene);
+    if (c->cfg.hit_mode == ELEVEN_HIT_KEY && !(c->cfg.flags & ELEVEN_FLAG_ANYHIT_LIGHT_SHADOWS)) k_shadowLight<ELEVEN_HIT_KEY, COUNT><<<grid, 128, 0, c->stream>>>(c->W, c->scene);
     else k_shadowLight<ELEVEN_HIT_MIN_T, COUNT><<<grid, 128, 0, c->stream>>>(c->W, c->scene);
     return 2;
 }

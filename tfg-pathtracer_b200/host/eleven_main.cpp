@@ -95,7 +95,7 @@ int main(int argc, char** argv) {
         j.device = g; j.desc = &desc;
         j.cfg.device = g; j.cfg.max_bounces = 5;
         j.cfg.rng_mode = fast ? ELEVEN_RNG_FAST : ELEVEN_RNG_REFERENCE; j.cfg.env_mode = fast ? ELEVEN_ENV_ALIAS : ELEVEN_ENV_CDF;
-        j.cfg.hit_mode = ELEVEN_HIT_KEY; j.cfg.flags = fast ? (ELEVEN_FLAG_TERMINATE_DEAD_PATHS | ELEVEN_FLAG_SKIP_NULL_NEE | ELEVEN_FLAG_FAST_MATH) : 0u;
+        j.cfg.hit_mode = ELEVEN_HIT_KEY; j.cfg.flags = fast ? (ELEVEN_FLAG_TERMINATE_DEAD_PATHS | ELEVEN_FLAG_SKIP_NULL_NEE | ELEVEN_FLAG_FAST_MATH | ELEVEN_FLAG_ANYHIT_LIGHT_SHADOWS) : 0u;
         j.cfg.sample_offset = (uint32_t)g; j.cfg.sample_stride = (uint32_t)gpus;
         j.cfg.bvh_builder = deviceBvh ? ELEVEN_BVH_DEVICE : ELEVEN_BVH_HOST;
         j.spp = spp / gpus + (g < spp % gpus ? 1 : 0);          // global sample s goes to device s % gpus

@@ -27,7 +27,7 @@ class ElevenError(RuntimeError):
 
 
 PARITY = dict(rng_mode=RNG_REFERENCE, env_mode=ENV_CDF, hit_mode=HIT_KEY, flags=0)
-FAST = dict(rng_mode=RNG_FAST, env_mode=ENV_ALIAS, hit_mode=HIT_KEY, flags=FLAG_TERMINATE_DEAD_PATHS | _capi.FLAG_SKIP_NULL_NEE | _capi.FLAG_FAST_MATH,
+FAST = dict(rng_mode=RNG_FAST, env_mode=ENV_ALIAS, hit_mode=HIT_KEY, flags=FLAG_TERMINATE_DEAD_PATHS | _capi.FLAG_SKIP_NULL_NEE | _capi.FLAG_FAST_MATH | _capi.FLAG_ANYHIT_LIGHT_SHADOWS,
             bvh_builder=BVH_DEVICE)
 
 
