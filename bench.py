@@ -344,6 +344,7 @@ def main():
                        "timing": "host clock between device synchronisations (barrier + cudaDeviceSynchronize on both sides), max over ranks; kernel times from CUDA events on the context's stream"},
             "mrays_per_s": rays_total / dt / 1e6,
             "frame_spp_per_s": S_ * args.steps * world / dt,
+            "kpaths_per_s_rank0": st["hit_bounces"] / (dt * 1e3),          # the reference's own unit: hit bounces per millisecond (S/main.cpp:172-179), this rank
             "e2e": {"value": total / dt_e2e, "unit": "pixel-samples/s", "h2d_bytes_per_step": 56, "d2h_bytes_per_step": W * H * 16},
             "gpu_launches": int(st["kernel_launches"] - launches0),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,

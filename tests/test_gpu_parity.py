@@ -249,6 +249,20 @@ def test_anyhit_light_shadows_equal_closest_hit_light_shadows(scenes):
     a.close(); b.close()
 
 
+def test_packed_material_maps_do_not_change_the_film(scenes, monkeypatch):
+    """The four 8-bit maps of a material are interleaved into one 8-byte record per texel at upload (DevPackedMaps): one
+    gather per hit instead of four.  Same texel bytes through the same decode tables: the film must be bit-identical."""
+    sc = scenes["clock"]
+    a = R.Renderer(**R.PARITY).render_setup(sc); a.render_cuda(3)
+    monkeypatch.setenv("ELEVEN_NO_PACKED_MAPS", "1")
+    b = R.Renderer(**R.PARITY).render_setup(sc); b.render_cuda(3)
+    monkeypatch.delenv("ELEVEN_NO_PACKED_MAPS")
+    fa, fb = a.get_buffers()[0], b.get_buffers()[0]
+    for p in fa:
+        assert (bits(fa[p]) == bits(fb[p])).all()
+    a.close(); b.close()
+
+
 def test_env_alias_matches_cdf_distribution(scenes):
     sc = scenes["clock"]
     a = R.Renderer(rng_mode=R.RNG_FAST, env_mode=R.ENV_CDF, flags=0).render_setup(sc); a.render_cuda(96)

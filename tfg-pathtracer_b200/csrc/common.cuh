@@ -103,6 +103,17 @@ struct DevMaterial {         // ElevenMaterial
     float roughness, metallic, clearcoatGloss, clearcoat, anisotropic, eta, transmission, specular, specularTint, sheenTint, subsurface, sheen;
 };
 
+// One texel record for the four maps of a material (albedo rgb, roughness r | normal rgb, metallic r), built at upload when the
+// maps are 8-bit, unfiltered and share size / tiling / offset: ONE 8-byte gather per hit instead of four 4-byte gathers into
+// four 64 MB arrays (k_shade is bound by exactly those DRAM sectors on bounce rays).
+struct DevPackedMaps {
+    const uint2* data;       // nullptr: the material's maps are fetched one by one
+    int32_t width, height;
+    float xTile, yTile, xOffset, yOffset;
+    uint32_t albedoFormat, pad_;   // ELEVEN_TEX_U8_SRGB / _LINEAR of the albedo map (the other three are decoded by their own format too)
+    uint32_t roughFormat, metalFormat, normalFormat, pad2_;
+};
+
 struct DevCamera { uint32_t xRes, yRes; float focalLength, sensorWidth, sensorHeight, aperture, focusDistance; float rot[3]; float pos[3]; uint32_t bokeh; };
 
 struct AliasEntry { float prob; uint32_t alias; };
@@ -116,6 +127,7 @@ struct DevScene {
     const int32_t* triMaterial;   // per triangle (original index): material id, for the material-sorted shading queue
     const DevMaterial* materials;
     const DevTex* textures;
+    const DevPackedMaps* packed;  // per material
     const float* lut;             // [2][256]: sRGB (gamma 2.2f) then linear (gamma 1.0f) fastPow tables
     DevTex hdri;                  // float4 texels: rgb + (r+g)+b
     const float* cdf;             // W*H+1

@@ -176,10 +176,9 @@ static int uploadTexture(ElevenCtx* c, const ElevenTexture& t, DevTex& out, bool
     return ELEVEN_OK;
 }
 
+static int allocWaveK(ElevenCtx* c);
+
 static int allocWave(ElevenCtx* c) {
-    freeAll(c->waveAllocs);
-    WaveState& W = c->W; memset(&W, 0, sizeof W);
-    W.nPixels = c->nPixels;
     // samples per pixel in flight: as many as keep a wave within 2^25 paths (~12 GB of wave state), at most 16
     c->maxLogK = 0;
     if (c->cfg.rng_mode == ELEVEN_RNG_FAST) {
@@ -187,6 +186,19 @@ static int allocWave(ElevenCtx* c) {
         else while (c->maxLogK < 4 && ((uint64_t)c->nPixels << (c->maxLogK + 1)) <= (1ull << 25)) c->maxLogK++;
     }
     if (((uint64_t)c->nPixels << c->maxLogK) > 0x7fffffffull) return fail(ELEVEN_ERR_ARG, "wave_spp x resolution exceeds 2^31 paths");
+    // an automatic width that does not fit the device's free memory is halved until it does (the image does not depend on it)
+    for (;;) {
+        const int rc = allocWaveK(c);
+        if (rc != ELEVEN_ERR_NOMEM || c->cfg.wave_spp != 0 || c->maxLogK == 0) return rc;
+        cudaGetLastError();
+        c->maxLogK--;
+    }
+}
+
+static int allocWaveK(ElevenCtx* c) {
+    freeAll(c->waveAllocs);
+    WaveState& W = c->W; memset(&W, 0, sizeof W);
+    W.nPixels = c->nPixels;
     W.pathCapacity = c->nPixels << c->maxLogK;
     const size_t n = W.pathCapacity, npx = c->nPixels;
     int rc = 0;
@@ -305,6 +317,36 @@ extern "C" int eleven_scene_upload(ElevenCtx* c, const ElevenSceneDesc* d) {
     std::vector<DevTex> texs(d->textureCount);
     for (uint32_t i = 0; i < d->textureCount; i++) if ((rc = uploadTexture(c, d->textures[i], texs[i], false))) return rc;
     if ((rc = devUpload(c->sceneAllocs, &S.textures, texs.data(), texs.size()))) return rc;
+    {   // packed map records (DevPackedMaps): materials whose four maps are 8-bit, unfiltered and congruent
+        std::vector<DevPackedMaps> packed(d->materialCount);
+        memset(packed.data(), 0, packed.size() * sizeof(DevPackedMaps));
+        for (uint32_t i = 0; i < d->materialCount && !getenv("ELEVEN_NO_PACKED_MAPS"); i++) {
+            const ElevenMaterial& m = d->materials[i];
+            const int32_t ids[4] = {m.albedoTextureID, m.roughnessTextureID, m.metallicTextureID, m.normalTextureID};
+            bool ok = true;
+            for (int k = 0; k < 4 && ok; k++) {
+                if (ids[k] < 0) { ok = false; break; }
+                const ElevenTexture& t = d->textures[ids[k]], &t0 = d->textures[ids[0]];
+                ok = t.format != ELEVEN_TEX_F32_RGB && (k == 3 || t.filter == 0) && t.width == t0.width && t.height == t0.height &&
+                     t.xTile == t0.xTile && t.yTile == t0.yTile && t.xOffset == t0.xOffset && t.yOffset == t0.yOffset;
+            }
+            if (!ok) continue;
+            const ElevenTexture& t0 = d->textures[ids[0]];
+            const size_t n = (size_t)t0.width * t0.height;
+            const uint8_t* src[4]; for (int k = 0; k < 4; k++) src[k] = (const uint8_t*)d->textures[ids[k]].data;
+            std::vector<uint2> rec(n);
+            for (size_t p = 0; p < n; p++) {
+                rec[p].x = (uint32_t)src[0][3 * p] | ((uint32_t)src[0][3 * p + 1] << 8) | ((uint32_t)src[0][3 * p + 2] << 16) | ((uint32_t)src[1][3 * p] << 24);
+                rec[p].y = (uint32_t)src[3][3 * p] | ((uint32_t)src[3][3 * p + 1] << 8) | ((uint32_t)src[3][3 * p + 2] << 16) | ((uint32_t)src[2][3 * p] << 24);
+            }
+            const uint2* dp = nullptr;
+            if ((rc = devUpload(c->sceneAllocs, &dp, rec.data(), n))) return rc;
+            DevPackedMaps& P = packed[i];
+            P.data = dp; P.width = t0.width; P.height = t0.height; P.xTile = t0.xTile; P.yTile = t0.yTile; P.xOffset = t0.xOffset; P.yOffset = t0.yOffset;
+            P.albedoFormat = d->textures[ids[0]].format; P.roughFormat = d->textures[ids[1]].format; P.metalFormat = d->textures[ids[2]].format; P.normalFormat = d->textures[ids[3]].format;
+        }
+        if ((rc = devUpload(c->sceneAllocs, &S.packed, packed.data(), packed.size()))) return rc;
+    }
     float lut[512]; buildLut(lut);
     if ((rc = devUpload(c->sceneAllocs, &S.lut, lut, 512))) return rc;
 

@@ -277,9 +277,10 @@ __global__ void __launch_bounds__(128, EL_SHADE_MIN_CTAS) k_shade(WaveState W, c
                 const F3 uv0 = f3(q7.x, q7.y, 0.f), uv1 = f3(q7.z, q7.w, 0.f), uv2 = f3(q8.x, q8.y, 0.f);
                 const F3 tUV = baryLerp(uv0, uv1, uv2, u, v);
                 const int objectID = __float_as_int(q8.z);
-                const DevMaterial& m = S.materials[S.objectMaterial[objectID]];
+                const int mid = S.objectMaterial[objectID];
+                const DevMaterial& m = S.materials[mid];
                 HitData hd;
-                generateHitData<FM>(S, m, hd, N, T, B, tUV.x, tUV.y);
+                generateHitData<FM>(S, m, S.packed[mid], hd, N, T, B, tUV.x, tUV.y);
 
                 const BrdfFrame bf = makeBrdfFrame<FM>(hd, ray.d);
                 const F3 L = disneySample<FM>(hd, bf, b1, b2, b3);

@@ -288,7 +288,29 @@ __device__ __forceinline__ F3 disneySample(const HitData& hd, const BrdfFrame& f
 
 // ---- S/kernel.cu:54-119 generateHitData ---------------------------------------------------------------
 template <bool FM>
-__device__ __forceinline__ void generateHitData(const DevScene& S, const DevMaterial& m, HitData& hd, F3 normal, F3 tangent, F3 bitangent, float tu, float tv) {
+__device__ __forceinline__ void generateHitData(const DevScene& S, const DevMaterial& m, const DevPackedMaps& pk, HitData& hd, F3 normal, F3 tangent, F3 bitangent, float tu, float tv) {
+    if (pk.data) {                                                   // all four maps in one 8-byte record (see DevPackedMaps)
+        DevTex g; g.data = nullptr; g.width = pk.width; g.height = pk.height; g.xTile = pk.xTile; g.yTile = pk.yTile; g.xOffset = pk.xOffset; g.yOffset = pk.yOffset;
+        g.format = 0; g.filter = 0;
+        const uint2 c = __ldg(pk.data + texelIndex(g, (int)(tu * pk.width), (int)(tv * pk.height)));
+        const float* la = S.lut + (pk.albedoFormat == ELEVEN_TEX_U8_SRGB ? 0 : 256);
+        const float* lr = S.lut + (pk.roughFormat == ELEVEN_TEX_U8_SRGB ? 0 : 256);
+        const float* lm = S.lut + (pk.metalFormat == ELEVEN_TEX_U8_SRGB ? 0 : 256);
+        const float* ln_ = S.lut + (pk.normalFormat == ELEVEN_TEX_U8_SRGB ? 0 : 256);
+        hd.albedo = f3(__ldg(la + (c.x & 0xffu)), __ldg(la + ((c.x >> 8) & 0xffu)), __ldg(la + ((c.x >> 16) & 0xffu)));
+        hd.roughness = __ldg(lr + (c.x >> 24));
+        const F3 nc = f3(__ldg(ln_ + (c.y & 0xffu)), __ldg(ln_ + ((c.y >> 8) & 0xffu)), __ldg(ln_ + ((c.y >> 16) & 0xffu)));
+        hd.metallic = __ldg(lm + (c.y >> 24));
+        hd.emission = m.emissionTex < 0 ? f3(m.emission[0], m.emission[1], m.emission[2]) : texFiltered(S.textures[m.emissionTex], S.lut, tu, tv);
+        const F3 ln = f3(nc.x * 2 - 1, nc.y * 2 - 1, nc.z * 2 - 1);
+        hd.normal = M<FM>::normalized(ln.x * tangent - ln.y * bitangent + ln.z * normal);
+        hd.roughness = M<FM>::pow(hd.roughness, 2.2f);
+        hd.metallic = M<FM>::pow(hd.metallic, 2.2f);
+        hd.clearcoatGloss = m.clearcoatGloss; hd.clearcoat = m.clearcoat; hd.anisotropic = m.anisotropic; hd.eta = m.eta;
+        hd.transmission = m.transmission; hd.specular = m.specular; hd.specularTint = m.specularTint; hd.sheenTint = m.sheenTint;
+        hd.subsurface = m.subsurface; hd.sheen = m.sheen;
+        return;
+    }
     // Memory-level parallelism: the texel fetches are gathers into ~1 GB of maps (DRAM latency each).  Fetched one after
     // the other, each behind the decode of the previous one, they were four of the five hottest stall sites of k_shade
     // (ncu source view, round 1).  When every bound map is 8-bit and unfiltered (what the loader produces) all texel loads
