@@ -204,9 +204,11 @@ static int allocWaveK(ElevenCtx* c) {
     int rc = 0;
 #define A(field, type) if ((rc = devAlloc(c->waveAllocs, &W.field, n))) return rc;
 #define APX(field, type) if ((rc = devAlloc(c->waveAllocs, &W.field, npx))) return rc;
-    A(rayO, float4) A(rayD, float4) A(thr, float4) A(rad, float4) A(hit, float4) A(aovN, float4) A(aovT, float4) A(aovB, float4)
-    A(depth, uint32_t) APX(rng, Xorwow) A(hitBucket, uint8_t)
-    A(neeEnvDir, float4) A(neeEnvC, float4) A(neeLightDir, float4) A(neeLightC, float4) A(neeBrdfC, float4) A(neePos, float4) A(neeThrMul, float4)
+    if ((rc = devAlloc(c->waveAllocs, &W.ray, n * 2))) return rc;
+    if ((rc = devAlloc(c->waveAllocs, &W.nee, n * NEE_STRIDE))) return rc;
+    if ((rc = devAlloc(c->waveAllocs, &W.tr, n * 2))) return rc;
+    A(hit, float4) A(aovN, float4) A(aovT, float4) A(aovB, float4)
+    APX(rng, Xorwow) A(hitBucket, uint8_t)
     A(qCur, uint32_t) A(qNext, uint32_t) A(qNee, uint32_t)
     if ((rc = devAlloc(c->waveAllocs, &W.qBucket, n * EL_BUCKETS))) return rc;
     APX(filmBeauty, float4) APX(filmNormal, float4) APX(filmTangent, float4) APX(filmBitangent, float4) APX(filmCount, uint32_t) APX(pathCount, uint32_t)
@@ -391,7 +393,12 @@ extern "C" int eleven_scene_upload(ElevenCtx* c, const ElevenSceneDesc* d) {
 
     c->width = d->camera.xRes; c->height = d->camera.yRes;
     const uint32_t nPix = c->width * c->height;
-    if (nPix != c->nPixels || !c->W.rayO) { c->nPixels = nPix; if ((rc = allocWave(c))) return rc; }
+    if (nPix != c->nPixels || !c->W.ray) { c->nPixels = nPix; if ((rc = allocWave(c))) return rc; }
+    c->W.sceneHasEmission = 0u;
+    for (uint32_t i = 0; i < d->materialCount; i++) {
+        const ElevenMaterial& m = d->materials[i];
+        if (m.emissionTextureID >= 0 || m.emission[0] != 0.f || m.emission[1] != 0.f || m.emission[2] != 0.f) c->W.sceneHasEmission = 1u;
+    }
     if (c->cfg.rng_mode == ELEVEN_RNG_REFERENCE && !c->d_seqMat) {
         std::vector<uint32_t> flat; buildSeqMats(flat, 32);
         const uint32_t* p = nullptr;

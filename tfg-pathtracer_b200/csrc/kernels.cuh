@@ -34,21 +34,17 @@ enum { ST_RAYS_EXT = 0, ST_RAYS_ENV = 1, ST_RAYS_LIGHT = 2, ST_NODES = 3, ST_TRI
 
 struct WaveState {
     // per path (index = film index * K + k)
-    float4* rayO; float4* rayD;          // origin / normalised direction
-    float4* thr;  float4* rad;           // throughput ("reduction"), accumulated radiance ("light")
+    float4* ray;                         // 2 x float4 = one 32-byte sector per path: (origin.xyz, depth bits), (normalised direction.xyz, 0);
+                                         // depth = number of hit bounces so far ("i")
+    float4* tr;                          // 2 x float4 = one sector per path: throughput ("reduction"), accumulated radiance ("light")
     float4* hit;                         // tri (as int bits), t, u, v
     uint8_t* hitBucket;                  // per QUEUE position of the current bounce: shading bucket of the hit (written by k_extend's sink)
     float4* aovN; float4* aovT; float4* aovB;
-    uint32_t* depth;                     // number of hit bounces so far ("i")
     Xorwow* rng;                         // per-pixel XORWOW state, persistent across samples (reference mode)
     // NEE records written by shade, consumed by connect
-    float4* neeEnvDir;                   // w_e.xyz, p_e
-    float4* neeEnvC;                     // C_e.xyz, p_b
-    float4* neeLightDir;                 // w_l.xyz, dist
-    float4* neeLightC;                   // C_p.xyz, p_p
-    float4* neeBrdfC;                    // C_b.xyz, -
-    float4* neePos;                      // hit position P
-    float4* neeThrMul;                   // f*cos/p_b (throughput update factor)
+    float4* nee;                         // NEE_STRIDE x float4 = one 128-byte line per path (NEE_*): the records every hit writes come
+                                         // first, so a scene without emission and point lights touches two full sectors
+    uint32_t sceneHasEmission;           // any material with emission: NEE_BRDF_C is written / read
     // queues
     uint32_t* qCur; uint32_t* qNext; uint32_t* qNee;
     uint32_t* qBucket;                   // EL_BUCKETS x pathCapacity: the shading queue, sorted by material (k_classify)
@@ -60,6 +56,17 @@ struct WaveState {
     uint32_t nPixels;
     uint32_t pathCapacity;               // nPixels * largest K: stride of the qBucket rows
 };
+
+// slots of a path's NEE line
+enum { NEE_ENV_DIR = 0,                  // w_e.xyz, p_e        } sector 0: all the environment shadow ray needs
+       NEE_POS = 1,                      // hit position P      }
+       NEE_ENV_C = 2,                    // C_e.xyz, p_b        } sector 1: the rest of the MIS combination
+       NEE_THR_MUL = 3,                  // f*cos/p_b (throughput update factor)
+       NEE_BRDF_C = 4,                   // C_b.xyz (only with emission)
+       NEE_LIGHT_DIR = 5,                // w_l.xyz, dist (only with point lights)
+       NEE_LIGHT_C = 6,                  // C_p.xyz, p_p
+       NEE_STRIDE = 8 };
+__device__ __forceinline__ float4& neeRec(const WaveState& W, uint32_t pid, int k) { return W.nee[(size_t)pid * NEE_STRIDE + k]; }
 
 struct RenderParams {
     uint32_t rngMode, envMode, hitMode, maxBounces, flags;
@@ -138,11 +145,10 @@ __global__ void __launch_bounds__(256) k_raygen(WaveState W, const __grid_consta
         r5 = S.cam.bokeh ? u32ToUniform(fastBits(P, i, 1u).x) : 0.5f;
     }
     const Ray ray = cameraRay<FM>(S.cam, P.rot, x, y, r1, r2, r3, r4, r5);
-    W.rayO[i] = make_float4(ray.o.x, ray.o.y, ray.o.z, 0.f);
-    W.rayD[i] = make_float4(ray.d.x, ray.d.y, ray.d.z, 0.f);
-    W.thr[i] = make_float4(1.f, 1.f, 1.f, 0.f);
-    W.rad[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    W.depth[i] = 0u;                 // the first-hit AOVs are written by k_shade at depth 0; k_accumulate reads them only where depth > 0
+    W.ray[2 * (size_t)i] = make_float4(ray.o.x, ray.o.y, ray.o.z, __uint_as_float(0u));   // depth 0: the first-hit AOVs are written by k_shade at depth 0, k_accumulate reads them only where depth > 0
+    W.ray[2 * (size_t)i + 1] = make_float4(ray.d.x, ray.d.y, ray.d.z, 0.f);
+    W.tr[2 * (size_t)i] = make_float4(1.f, 1.f, 1.f, 0.f);
+    W.tr[2 * (size_t)i + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
     W.qCur[i] = i;
     if (i == 0) {
         W.cnt[CNT_CUR] = nPaths; W.cnt[CNT_NEXT] = 0u; W.cnt[CNT_NEE] = 0u;
@@ -219,18 +225,18 @@ __global__ void __launch_bounds__(128, EL_SHADE_MIN_CTAS) k_shade(WaveState W, c
             pid = W.qBucket[(size_t)b * W.pathCapacity + (qi - prefix[b])];
             const float4 hv = W.hit[pid];
             const int tri = __float_as_int(hv.x);
-            const float4 o4 = W.rayO[pid], d4 = W.rayD[pid];
+            const float4 o4 = W.ray[2 * (size_t)pid], d4 = W.ray[2 * (size_t)pid + 1];
             Ray ray; ray.o = f3(o4.x, o4.y, o4.z); ray.d = f3(d4.x, d4.y, d4.z);
-            const float4 thr4 = W.thr[pid];
+            const float4 thr4 = W.tr[2 * (size_t)pid];
             const F3 thr = f3(thr4.x, thr4.y, thr4.z);
             if (tri < 0) {
                 // escaped: light += env(dir) * reduction (S/kernel.cu:414-419)
                 const F3 e = envLookup(S, ray.d);
-                float4 r = W.rad[pid];
+                float4 r = W.tr[2 * (size_t)pid + 1];
                 r.x += e.x * thr.x; r.y += e.y * thr.y; r.z += e.z * thr.z;
-                W.rad[pid] = r;
+                W.tr[2 * (size_t)pid + 1] = r;
             } else {
-                const uint32_t depth = W.depth[pid];
+                const uint32_t depth = __float_as_uint(o4.w);
                 // --- random numbers: 3 for the bounce, 3 for shade of which only the first is used.  Drawn FIRST:
                 //     they need only (pid, depth), and the environment sample's table + texel fetches (two dependent gathers into
                 //     ~200 MB) can then fly while the triangle and the texture maps are fetched
@@ -315,15 +321,15 @@ __global__ void __launch_bounds__(128, EL_SHADE_MIN_CTAS) k_shade(WaveState W, c
                 const F3 mulB = f3(M<FM>::div(fB.x * cB, pB), M<FM>::div(fB.y * cB, pB), M<FM>::div(fB.z * cB, pB));
                 const F3 CB = hd.emission * mulB;
 
-                W.neeEnvDir[pid] = make_float4(wE.x, wE.y, wE.z, pE);
-                W.neeEnvC[pid] = make_float4(CE.x, CE.y, CE.z, pB);
+                neeRec(W, pid, NEE_ENV_DIR) = make_float4(wE.x, wE.y, wE.z, pE);
+                neeRec(W, pid, NEE_ENV_C) = make_float4(CE.x, CE.y, CE.z, pB);
+                neeRec(W, pid, NEE_POS) = make_float4(Pp.x, Pp.y, Pp.z, 0.f);
+                neeRec(W, pid, NEE_THR_MUL) = make_float4(mulB.x, mulB.y, mulB.z, 0.f);
+                if (W.sceneHasEmission) neeRec(W, pid, NEE_BRDF_C) = make_float4(CB.x, CB.y, CB.z, 0.f);
                 if (S.lightCount > 0) {
-                    W.neeLightDir[pid] = make_float4(wL.x, wL.y, wL.z, dist);
-                    W.neeLightC[pid] = make_float4(CP.x, CP.y, CP.z, pP);
+                    neeRec(W, pid, NEE_LIGHT_DIR) = make_float4(wL.x, wL.y, wL.z, dist);
+                    neeRec(W, pid, NEE_LIGHT_C) = make_float4(CP.x, CP.y, CP.z, pP);
                 }
-                W.neeBrdfC[pid] = make_float4(CB.x, CB.y, CB.z, 0.f);
-                W.neePos[pid] = make_float4(Pp.x, Pp.y, Pp.z, 0.f);
-                W.neeThrMul[pid] = make_float4(mulB.x, mulB.y, mulB.z, 0.f);
                 if (depth == 0) {                                   // first-hit AOVs (S/kernel.cu:436-440)
                     W.aovN[pid] = make_float4(N.x, N.y, N.z, 0.f);
                     W.aovT[pid] = make_float4(T.x, T.y, T.z, 0.f);
@@ -331,15 +337,14 @@ __global__ void __launch_bounds__(128, EL_SHADE_MIN_CTAS) k_shade(WaveState W, c
                 }
                 // next ray: Ray(P + L*0.001, L) (S/kernel.cu:442)
                 const Ray nr = makeRay(ex::madd(Pp, L, 0.001f), L);
-                W.rayO[pid] = make_float4(nr.o.x, nr.o.y, nr.o.z, 0.f);
-                W.rayD[pid] = make_float4(nr.d.x, nr.d.y, nr.d.z, 0.f);
-                W.depth[pid] = depth + 1u;
+                W.ray[2 * (size_t)pid] = make_float4(nr.o.x, nr.o.y, nr.o.z, __uint_as_float(depth + 1u));
+                W.ray[2 * (size_t)pid + 1] = make_float4(nr.d.x, nr.d.y, nr.d.z, 0.f);
                 toNee = true;
                 if ((P.flags & ELEVEN_FLAG_SKIP_NULL_NEE) && S.lightCount == 0 && isfinite(pE) &&
                     CE.x == 0.f && CE.y == 0.f && CE.z == 0.f && CB.x == 0.f && CB.y == 0.f && CB.z == 0.f) {
                     // the MIS sum is w1*0 + 0 + w3*0 whatever the shadow ray finds (e.g. the environment sample lies below
                     // the surface): no shadow ray, apply the throughput factor here
-                    W.thr[pid] = make_float4(thr.x * mulB.x, thr.y * mulB.y, thr.z * mulB.z, 0.f);
+                    W.tr[2 * (size_t)pid] = make_float4(thr.x * mulB.x, thr.y * mulB.y, thr.z * mulB.z, 0.f);
                     toNee = false;
                 }
                 toNext = depth + 1u < P.maxBounces;
@@ -384,10 +389,10 @@ __global__ void __launch_bounds__(256) k_accumulate(WaveState W, uint32_t logK) 
     const uint32_t nPaths = W.nPixels << logK;
     const uint32_t p = blockIdx.x * 256u + tid;
     if (p < nPaths) {
-        float4 r = W.rad[p];
+        float4 r = W.tr[2 * (size_t)p + 1];
         r.x = clampf_(r.x, 0.f, 10.f); r.y = clampf_(r.y, 0.f, 10.f); r.z = clampf_(r.z, 0.f, 10.f);
         const bool ok = !isnan(r.x) && !isnan(r.y) && !isnan(r.z);
-        const uint32_t dep = W.depth[p];
+        const uint32_t dep = __float_as_uint(W.ray[2 * (size_t)p].w);
         const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
         const float4 n = dep ? W.aovN[p] : z, t = dep ? W.aovT[p] : z, bt = dep ? W.aovB[p] : z;     // camera ray escaped: AOVs are 0 (S/kernel.cu:388-391)
         sv[0][tid][0] = r.x; sv[0][tid][1] = r.y; sv[0][tid][2] = r.z;

@@ -23,7 +23,7 @@ struct ExtendSource {
     const WaveState& W;
     __device__ __forceinline__ void load(uint32_t qi, LaneRay& lr) const {
         const uint32_t pid = W.qCur[qi];
-        const float4 o = W.rayO[pid], d = W.rayD[pid];
+        const float4 o = W.ray[2 * (size_t)pid], d = W.ray[2 * (size_t)pid + 1];
         lr.ray.o = f3(o.x, o.y, o.z); lr.ray.d = f3(d.x, d.y, d.z);
         lr.tmaxAny = INFINITY; lr.tag = qi;                              // the sink needs the queue position (hitBucket)
     }
@@ -49,26 +49,27 @@ __global__ void __launch_bounds__(128, EL_EXTEND_MIN_CTAS) k_extend(const __grid
 // ---- MIS combination (shade, S/kernel.cu:351-357) --------------------------------------------------------------------------
 // hdriPdf is DEFINED as 0 when the environment shadow ray is occluded (the reference leaves it uninitialised).
 __device__ __forceinline__ void misCombine(const WaveState& W, uint32_t pid, bool lights, bool envOccluded, bool lightOccluded) {
-    const float4 ed = W.neeEnvDir[pid], ec = W.neeEnvC[pid], bc = W.neeBrdfC[pid];
+    const float4 ed = neeRec(W, pid, NEE_ENV_DIR), ec = neeRec(W, pid, NEE_ENV_C);
+    const float4 bc = W.sceneHasEmission ? neeRec(W, pid, NEE_BRDF_C) : make_float4(0.f, 0.f, 0.f, 0.f);
     const float pB = ec.w;
     const float pE = envOccluded ? 0.f : ed.w;
     const F3 CE = envOccluded ? f3(0.f) : f3(ec.x, ec.y, ec.z);
     float pP = 0.f; F3 CP = f3(0.f);
     if (lights) {
-        const float4 lc = W.neeLightC[pid];
+        const float4 lc = neeRec(W, pid, NEE_LIGHT_C);
         pP = lc.w;
         if (!lightOccluded) CP = f3(lc.x, lc.y, lc.z);
     }
     const float sum = pE + pP + pB;
     const float w1 = pE / sum, w2 = pP / sum, w3 = pB / sum;
-    const float4 thr4 = W.thr[pid];
+    const float4 thr4 = W.tr[2 * (size_t)pid];
     const F3 thr = f3(thr4.x, thr4.y, thr4.z);
     const F3 mix = f3(w1 * CE.x + w2 * CP.x + w3 * bc.x, w1 * CE.y + w2 * CP.y + w3 * bc.y, w1 * CE.z + w2 * CP.z + w3 * bc.z);
-    float4 r = W.rad[pid];
+    float4 r = W.tr[2 * (size_t)pid + 1];
     r.x += thr.x * mix.x; r.y += thr.y * mix.y; r.z += thr.z * mix.z;
-    W.rad[pid] = r;
-    const float4 tm = W.neeThrMul[pid];
-    W.thr[pid] = make_float4(thr.x * tm.x, thr.y * tm.y, thr.z * tm.z, 0.f);
+    W.tr[2 * (size_t)pid + 1] = r;
+    const float4 tm = neeRec(W, pid, NEE_THR_MUL);
+    W.tr[2 * (size_t)pid] = make_float4(thr.x * tm.x, thr.y * tm.y, thr.z * tm.z, 0.f);
 }
 
 // ---- environment shadow rays --------------------------------------------------------------------------------------------------
@@ -76,7 +77,7 @@ struct ShadowEnvSource {
     const WaveState& W;
     __device__ __forceinline__ void load(uint32_t qi, LaneRay& lr) const {
         const uint32_t pid = W.qNee[qi];
-        const float4 p = W.neePos[pid], e = W.neeEnvDir[pid];
+        const float4 p = neeRec(W, pid, NEE_POS), e = neeRec(W, pid, NEE_ENV_DIR);
         const F3 w = f3(e.x, e.y, e.z);
         lr.ray = makeRay(ex::madd(f3(p.x, p.y, p.z), w, 0.001f), w);      // Ray(point + newDir*0.001, newDir), S/kernel.cu:246
         lr.tmaxAny = INFINITY; lr.tag = pid;
@@ -87,7 +88,7 @@ struct ShadowEnvSink {
     const WaveState& W;
     __device__ __forceinline__ void done(const LaneRay& lr, const HitRec& h) const {
         const bool occluded = h.tri >= 0;
-        if (LIGHTS) { if (occluded) { float4 e = W.neeEnvDir[lr.tag]; e.w = -1.f; W.neeEnvDir[lr.tag] = e; } }   // p_e < 0 marks "occluded" for the light stage
+        if (LIGHTS) { if (occluded) { float4 e = neeRec(W, lr.tag, NEE_ENV_DIR); e.w = -1.f; neeRec(W, lr.tag, NEE_ENV_DIR) = e; } }   // p_e < 0 marks "occluded" for the light stage
         else misCombine(W, lr.tag, false, occluded, false);
     }
 };
@@ -105,7 +106,7 @@ struct ShadowLightSource {
     const WaveState& W;
     __device__ __forceinline__ void load(uint32_t qi, LaneRay& lr) const {
         const uint32_t pid = W.qNee[qi];
-        const float4 p = W.neePos[pid], l = W.neeLightDir[pid];
+        const float4 p = neeRec(W, pid, NEE_POS), l = neeRec(W, pid, NEE_LIGHT_DIR);
         const F3 w = f3(l.x, l.y, l.z);
         lr.ray = makeRay(ex::madd(f3(p.x, p.y, p.z), w, 0.001f), w);      // S/kernel.cu:192
         lr.tmaxAny = HITMODE == ELEVEN_HIT_KEY ? INFINITY : l.w - 0.001f;
@@ -120,13 +121,13 @@ struct ShadowLightSink {
         bool occluded = h.tri >= 0;
         if (HITMODE == ELEVEN_HIT_KEY && occluded) {
             // the reference takes the CLOSEST hit and compares |hit.position - point| with the light distance (S/kernel.cu:193-197)
-            const float4 p = W.neePos[pid];
+            const float4 p = neeRec(W, pid, NEE_POS);
             const TriGeom g = loadTriGeom(S.shadeTris, h.tri);
             F3 sn;
             const F3 hp = hitPosition(lr.ray, g, h.t, h.u, h.v, sn);
-            occluded = length(hp - f3(p.x, p.y, p.z)) < W.neeLightDir[pid].w;
+            occluded = length(hp - f3(p.x, p.y, p.z)) < neeRec(W, pid, NEE_LIGHT_DIR).w;
         }
-        const bool envOccluded = W.neeEnvDir[pid].w < 0.f;
+        const bool envOccluded = neeRec(W, pid, NEE_ENV_DIR).w < 0.f;
         misCombine(W, pid, true, envOccluded, occluded);
     }
 };
