@@ -160,30 +160,48 @@ __global__ void __launch_bounds__(256) k_raygen(WaveState W, const __grid_consta
 
 
 // ---- classify: bucket the traced paths by material (escaped rays last) for a coherent shading queue ------------------
+// Two coalesced streams in (k_extend's sink left each path's bucket at its queue position), one scattered stream out.
+// A CTA takes chunks of 2 048 entries: ranks inside the chunk come from shared-memory counters (warp-aggregated), the
+// chunk then reserves its space in the 8 global buckets with 8 atomics.  (One global atomic per warp and bucket made
+// 2.6 M same-address atomics per launch the bottleneck: 0.74 ms for 33 M entries at 6 % issue utilisation and 12 % DRAM.)
+enum { EL_CLASSIFY_PER_THREAD = 16 };
 __global__ void __launch_bounds__(128) k_classify(WaveState W, const __grid_constant__ DevScene S) {
+    __shared__ uint32_t shist[EL_BUCKETS], sbase[EL_BUCKETS];
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t n = W.cnt[CNT_CUR];
-    // static grid-stride partition: a single-address work-fetch atomic per 32 entries would be the bottleneck of a kernel
-    // that only streams 5 bytes per entry
-    const uint32_t warpsTotal = gridDim.x * (blockDim.x >> 5);
-    const uint32_t warpId = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    for (uint32_t base = warpId * 32u; base < n; base += warpsTotal * 32u) {
-        const uint32_t qi = base + lane;
-        const bool valid = qi < n;
-        uint32_t pid = 0, bucket = EL_MISS_BUCKET;
-        if (valid) {                                 // two coalesced streams, no dependent gather: k_extend's sink left the bucket at qi
-            pid = W.qCur[qi];
-            bucket = W.hitBucket[qi];
+    const uint32_t chunk = 128u * EL_CLASSIFY_PER_THREAD;
+    for (uint32_t c0 = blockIdx.x * chunk; c0 < n; c0 += gridDim.x * chunk) {        // static partition: no work-fetch atomic
+        if (threadIdx.x < EL_BUCKETS) shist[threadIdx.x] = 0u;
+        __syncthreads();
+        uint32_t pid[EL_CLASSIFY_PER_THREAD], key[EL_CLASSIFY_PER_THREAD];            // key = bucket | rank << 3
+#pragma unroll
+        for (int k = 0; k < EL_CLASSIFY_PER_THREAD; k++) {
+            const uint32_t qi = c0 + (uint32_t)k * 128u + threadIdx.x;
+            const bool valid = qi < n;
+            uint32_t bucket = EL_MISS_BUCKET;
+            pid[k] = 0u;
+            if (valid) { pid[k] = W.qCur[qi]; bucket = W.hitBucket[qi]; }
+            const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+            key[k] = 0xffffffffu;
+            if (valid) {
+                const uint32_t peers = __match_any_sync(vmask, bucket);
+                const uint32_t leader = __ffs(peers) - 1u;
+                uint32_t pos = 0;
+                if (lane == leader) pos = atomicAdd(&shist[bucket], (uint32_t)__popc(peers));
+                pos = __shfl_sync(peers, pos, leader) + __popc(peers & ((1u << lane) - 1u));
+                key[k] = bucket | (pos << 3);
+            }
         }
-        const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
-        if (valid) {
-            const uint32_t peers = __match_any_sync(vmask, bucket);
-            const uint32_t leader = __ffs(peers) - 1u;
-            uint32_t pos = 0;
-            if (lane == leader) pos = atomicAdd(&W.cnt[CNT_BUCKET0 + bucket], (uint32_t)__popc(peers));
-            pos = __shfl_sync(peers, pos, leader);
-            W.qBucket[(size_t)bucket * W.pathCapacity + pos + __popc(peers & ((1u << lane) - 1u))] = pid;
+        __syncthreads();
+        if (threadIdx.x < EL_BUCKETS) sbase[threadIdx.x] = shist[threadIdx.x] ? atomicAdd(&W.cnt[CNT_BUCKET0 + threadIdx.x], shist[threadIdx.x]) : 0u;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < EL_CLASSIFY_PER_THREAD; k++) {
+            if (key[k] == 0xffffffffu) continue;
+            const uint32_t bucket = key[k] & 7u;
+            W.qBucket[(size_t)bucket * W.pathCapacity + sbase[bucket] + (key[k] >> 3)] = pid[k];
         }
+        __syncthreads();
     }
 }
 
