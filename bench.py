@@ -200,6 +200,7 @@ def main():
     ap.add_argument("--cpu-rows", type=int, default=1080)
     ap.add_argument("--cpu-spp", type=int, default=8)
     ap.add_argument("--wave-spp", type=int, default=0, help="samples of every pixel in flight per wave (0 = auto)")
+    ap.add_argument("--bvh", default="", choices=["", "device", "host"], help="BVH8 builder (default: the mode's own: device for fast, host for parity)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mode", default="fast", choices=["fast", "parity"])
     ap.add_argument("--hit-mode", default="key", choices=["key", "min_t"], help="closest-hit ordering: the reference key (default) or classic min t")
@@ -237,6 +238,8 @@ def main():
     off, stride, _ = D.sample_plan(args.spp_per_step * world, rank, world)
     if args.mode == "fast":
         mode["wave_spp"] = args.wave_spp
+    if args.bvh:
+        mode["bvh_builder"] = R.BVH_DEVICE if args.bvh == "device" else R.BVH_HOST
     r = R.Renderer(device=local, sample_offset=off, sample_stride=stride, **mode).render_setup(sc)
     setup_s = time.time() - t0
     film, counts = D.film_tensors(r, "cuda:%d" % local)

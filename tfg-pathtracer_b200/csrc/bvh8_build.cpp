@@ -12,6 +12,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstring>
+#include <functional>
 #include <future>
 #include <thread>
 
@@ -180,6 +181,45 @@ void buildBvh8(const ElevenTri* tris, uint32_t n, const int32_t* triMaterial, Bv
     if (n > 0) B.build(0, 0, (int)n, 0);
     else { B.nodes[0].box = scene; B.nodes[0].left = B.nodes[0].right = -1; B.nodes[0].first = 0; B.nodes[0].count = 0; }
 
+    // ---- optional: SAH-optimal collapse (Ylitie, Karras, Laine 2017, section 3.1) -----------------------------------------------
+    // C(n, i) = lowest SAH cost of the subtree of binary node n when it may occupy i child slots of its wide parent:
+    //   leaf:      C(n, i) = A_n * count * c_tri
+    //   internal:  D(n, j) = min_{0<k<j} C(l, k) + C(r, j-k);  C(n, 1) = D(n, 8) + A_n * c_node;  C(n, i) = min(D(n, i), C(n, i-1))
+    // Children are allocated after their parent, so a descending index sweep is a post-order.
+    const char* optEnv = getenv("ELEVEN_BVH_COLLAPSE");
+    const bool optimal = !(optEnv && !strcmp(optEnv, "greedy"));     // default; "greedy" = open the largest child (round-1 first version)
+    const float cNode = getenv("ELEVEN_COST_NODE") ? (float)atof(getenv("ELEVEN_COST_NODE")) : 3.0f;
+    struct Dp { float c[9]; uint8_t k[9]; };     // k[j] for j >= 2: split of D(n, j), or 0 = "take C(n, j-1)"; k[1] = split of D(n, 8)
+    std::vector<Dp> dp;
+    if (optimal && n > 0) {
+        const int nn = B.nodeCount.load();
+        dp.resize(nn);
+        for (int i = nn - 1; i >= 0; i--) {
+            const Node2& N = B.nodes[i]; Dp& d = dp[i];
+            const float area = N.box.area();
+            if (isLeaf2(N) || N.left < 0) { for (int j = 0; j < 9; j++) { d.c[j] = area * (float)N.count * COST_TRI; d.k[j] = 0; } continue; }
+            const Dp &L = dp[N.left], &R = dp[N.right];
+            float D[9]; uint8_t K[9];
+            for (int j = 2; j <= 8; j++) {
+                D[j] = INFINITY; K[j] = 1;
+                for (int k = 1; k < j; k++) { const float v = L.c[std::min(k, 7)] + R.c[std::min(j - k, 7)]; if (v < D[j]) { D[j] = v; K[j] = (uint8_t)k; } }
+            }
+            d.c[0] = INFINITY; d.k[0] = 0;
+            d.c[1] = D[8] + area * cNode; d.k[1] = K[8];
+            for (int j = 2; j <= 7; j++) { if (D[j] < d.c[j - 1]) { d.c[j] = D[j]; d.k[j] = K[j]; } else { d.c[j] = d.c[j - 1]; d.k[j] = 0; } }
+            d.c[8] = d.c[7]; d.k[8] = 0;
+        }
+    }
+    // children of the wide node rooted at binary node m when it may use j slots
+    std::function<void(int, int, int*, int&)> expand = [&](int m, int j, int* ch, int& nc) {
+        const Node2& M = B.nodes[m];
+        if (isLeaf2(M) || M.left < 0 || j == 1) { ch[nc++] = m; return; }
+        while (j > 1 && dp[m].k[j] == 0) j--;
+        if (j == 1) { ch[nc++] = m; return; }
+        const int k = dp[m].k[j];
+        expand(M.left, k, ch, nc); expand(M.right, j - k, ch, nc);
+    };
+
     // ---- collapse to 8-wide, breadth-first so that a node's internal children are contiguous ---------
     struct Item { int n2; uint32_t n8; uint32_t depth; };
     std::vector<Item> queue; queue.reserve(n / 4 + 16);
@@ -192,8 +232,9 @@ void buildBvh8(const ElevenTri* tris, uint32_t n, const int32_t* triMaterial, Bv
         const Node2& root = B.nodes[it.n2];
         int ch[8]; int nc = 0;
         if (isLeaf2(root) || root.left < 0) { if (root.count > 0) ch[nc++] = it.n2; }
+        else if (optimal) { const int k = dp[it.n2].k[1]; expand(root.left, k, ch, nc); expand(root.right, 8 - k, ch, nc); }
         else { ch[nc++] = root.left; ch[nc++] = root.right; }
-        while (nc < 8) {                                   // open the internal child with the largest area
+        while (!optimal && nc < 8) {                       // greedy: open the internal child with the largest area
             int best = -1; float bestA = -1;
             for (int i = 0; i < nc; i++) { const Node2& c = B.nodes[ch[i]]; if (!isLeaf2(c)) { float a = c.box.area(); if (a > bestA) { bestA = a; best = i; } } }
             if (best < 0) break;
