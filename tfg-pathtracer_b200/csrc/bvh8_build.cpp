@@ -32,7 +32,8 @@ struct Box {
 
 struct Node2 { Box box; int left, right, first, count, span; };   // leaf iff count > 0; span = triangles in the subtree
 
-static const int   BINS = 16;
+static const int   MAXBINS = 64;
+static int BINS = 16;            // ELEVEN_BVH_BINS (experiments); 16 is what the device builder uses
 #ifndef EL_MAX_LEAF
 #define EL_MAX_LEAF 3
 #endif
@@ -63,7 +64,7 @@ struct Builder {
         for (int a = 0; a < 3; a++) {
             float lo = cb.lo[a], ext = cb.hi[a] - cb.lo[a];
             if (!(ext > 0)) continue;
-            Box bb[BINS]; int bc[BINS];
+            Box bb[MAXBINS]; int bc[MAXBINS];
             for (int k = 0; k < BINS; k++) { bb[k].reset(); bc[k] = 0; }
             float scale = BINS / ext;
             for (int i = first; i < first + count; i++) {
@@ -71,7 +72,7 @@ struct Builder {
                 int k = std::min(BINS - 1, std::max(0, (int)((cen[3 * t + a] - lo) * scale)));
                 bc[k]++; bb[k].grow(tbox[t]);
             }
-            float rightArea[BINS]; int rightCount[BINS];
+            float rightArea[MAXBINS]; int rightCount[MAXBINS];
             Box acc; acc.reset(); int c = 0;
             for (int k = BINS - 1; k > 0; k--) { acc.grow(bb[k]); c += bc[k]; rightArea[k] = acc.area(); rightCount[k] = c; }
             acc.reset(); c = 0;
@@ -134,6 +135,7 @@ void buildBvh8(const ElevenTri* tris, uint32_t n, const int32_t* triMaterial, Bv
     out.nodes.clear(); out.slots.clear(); out.keySlack = 0; out.maxDepth = 0;
     for (int a = 0; a < 3; a++) { out.boundsLo[a] = 0; out.boundsHi[a] = 0; }
     if (threads < 1) threads = 1;
+    if (const char* e = getenv("ELEVEN_BVH_BINS")) BINS = std::max(2, std::min(MAXBINS, atoi(e)));
 
     Builder B; B.tris = tris; B.n = n; B.threads = threads; B.liveTasks = 0;
     B.tbox.resize(n); B.cen.resize(3 * (size_t)n); B.idx.resize(n);
