@@ -245,9 +245,23 @@ def main():
     film, counts = D.film_tensors(r, "cuda:%d" % local)
     S_ = args.spp_per_step
 
+    red_events = []
+
     def step():
-        r.render_cuda(S_)
-        D.reduce_film(film, counts, 0)
+        r.render_cuda(S_)                       # blocking; its device time is measured by CUDA events on the context's stream (ElevenStats.render_ms)
+        if world > 1:                           # the one exchange step, timed by CUDA events on torch's stream (where NCCL is enqueued)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            D.reduce_film(film, counts, 0)
+            e1.record()
+            red_events.append((e0, e1))
+
+    def device_ms(render_ms0):
+        """Device time of the steps since `render_ms0`: render (context-stream events) + reduce (torch-stream events)."""
+        torch.cuda.synchronize()
+        ms = r.stats()["render_ms"] - render_ms0 + sum(a.elapsed_time(b) for a, b in red_events)
+        red_events.clear()
+        return ms
 
     def barrier():
         torch.cuda.synchronize()
@@ -279,13 +293,16 @@ def main():
     if rank == 0:
         sampler.start()
     r.reset()
-    launches0 = r.stats()["kernel_launches"]
+    st0 = r.stats()
+    launches0 = st0["kernel_launches"]
+    red_events.clear()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step()
     barrier()
-    dt = time.perf_counter() - t0
+    dt_host = time.perf_counter() - t0
+    dt = device_ms(st0["render_ms"]) * 1e-3                              # CUDA events; max over ranks below
     st = r.stats()
     # ---- timed: stage breakdown for the roofline (separate pass so that the events do not perturb `value`) ------
     tk_cfg = dict(mode)
@@ -301,6 +318,7 @@ def main():
     # ---- timed: e2e ---------------------------------------------------------------------------------------
     host_film = r.pinned_array((H, W, 4), np.float32)                 # page-locked host buffer for the per-step film read-back
     r.reset()
+    red_events.clear()
     barrier()
     t1 = time.perf_counter()
     for k in range(args.steps):
@@ -313,9 +331,9 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
 
     if world > 1:
-        t = torch.tensor([dt, dt_e2e], device="cuda:%d" % local, dtype=torch.float64)
+        t = torch.tensor([dt, dt_e2e, dt_host], device="cuda:%d" % local, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt, dt_e2e = float(t[0]), float(t[1])
+        dt, dt_e2e, dt_host = float(t[0]), float(t[1]), float(t[2])
         rays = torch.tensor([st["rays_extension"], st["rays_shadow_env"], st["rays_shadow_light"]], device="cuda:%d" % local, dtype=torch.float64)
         dist.all_reduce(rays)
         rays_total = float(rays.sum())
@@ -339,12 +357,13 @@ def main():
                 traffic = None
         out = {
             "metric": "samples_per_second", "value": value, "unit": "pixel-samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "ms_per_step": dt / args.steps * 1e3, "ms_per_step_host": dt_host / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "ClockCC0 stand-in (125281 tris, 12x%d^2 8-bit maps, 4096x2048 HDRI, defocus) %dx%d, %d spp/step/GPU, mode=%s" % (args.tex, W, H, S_, args.mode),
                        "spp_per_step": S_, "parallelism": "sample-split x%d, scene replicated, 1 NCCL reduce of film sums per step" % world,
                        "l2": "inputs larger than L2 (textures 805 MB + HDRI 134 MB + 12 GB wave state vs 126 MB L2); no flush needed",
                        "wave_spp": "auto (16 samples of every pixel in flight per wave)" if (args.wave_spp == 0 and args.mode == "fast") else (args.wave_spp if args.mode == "fast" else 1),
-                       "timing": "host clock between device synchronisations (barrier + cudaDeviceSynchronize on both sides), max over ranks; kernel times from CUDA events on the context's stream"},
+                       "timing": "value: CUDA events, max over ranks (render: events on the context's stream around every eleven_render; NCCL reduce: events on torch's stream), "
+                                 "bracketed by barrier + cudaDeviceSynchronize; ms_per_step_host and e2e: host clock between the same synchronisations"},
             "mrays_per_s": rays_total / dt / 1e6,
             "frame_spp_per_s": S_ * args.steps * world / dt,
             "kpaths_per_s_rank0": st["hit_bounces"] / (dt * 1e3),          # the reference's own unit: hit bounces per millisecond (S/main.cpp:172-179), this rank

@@ -226,6 +226,12 @@ int  eleven_trace_device(ElevenCtx* ctx, const float* d_rays, size_t n, ElevenHi
  * leaf order (48 B each, TriSlot) and the per-node culling slack.  Capacities in elements; counts are in ElevenStats. */
 int  eleven_bvh_download(ElevenCtx* ctx, void* nodes, size_t node_cap, void* slots, size_t slot_cap, float* node_slack);
 
+/* Test hook: the host BVH8 builder on its own (replaces BVH::build, S/BVH.hpp:187-330).  No GPU, no context.  Buffers may be
+ * NULL to query the sizes: counts[0] = nodes, counts[1] = triangle slots.  threads <= 0: all host cores. */
+int  eleven_bvh_build_host(const ElevenTri* tris, uint32_t n, const int32_t* tri_material, int threads,
+                           void* nodes, size_t node_cap, void* slots, size_t slot_cap, float* node_slack,
+                           uint32_t* counts, float* key_slack);
+
 /* Multi-GPU plumbing: the film lives as per-pixel SUMS; these expose it so the
  * caller (one process per GPU) can all-reduce it with NCCL and resolve on the root. */
 int  eleven_film_sums_device(ElevenCtx* ctx, int pass, void** d_ptr, size_t* n_floats);

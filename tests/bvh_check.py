@@ -1,8 +1,9 @@
 """Host-side validator of the device-resident BVH8 (bvh8.h layout), used on the output of BOTH builders (host:
 bvh8_build.cpp, device: bvh8_build_gpu.cuh).  Checks what the traversal kernel relies on:
 
-  * every triangle sits in exactly one leaf slot, slots of a node are contiguous (<= 24), internal children contiguous
-    in ascending slot order (rank = popcount of imask below the slot);
+  * every triangle sits in exactly one leaf slot, slots of a node are contiguous (<= 24) and packed in triMask bit order
+    (slot of bit b = triBase + popcount(triMask below b)), internal children contiguous in ascending slot order
+    (rank = popcount of imask below the slot);
   * every child box, decoded the way the kernel decodes it (p + q * 2^(e-127) in float32), encloses the boxes of all the
     triangles below it;
   * per-node slack >= the shift bound of every triangle below.
@@ -48,13 +49,15 @@ def validate_bvh8(nodes, slots, slack, tris):
         blo = (p[None, :] + qlo * scale[None, :]).astype(np.float32)
         bhi = (p[None, :] + qhi * scale[None, :]).astype(np.float32)
         tri_off_expected, rank = 0, 0
+        tri_mask, imask = int(N["triMask"]), int(N["imask"])
+        assert tri_mask >> 24 == 0
+        assert N["slack"] == slack[ni], "Node8::slack must repeat the per-node slack array"
+        used = []
         for s in range(8):
-            m = int(N["meta"][s])
-            if m == 0:
-                assert not (int(N["imask"]) >> s) & 1
-                continue
-            if (m >> 5) == 1 and (m & 31) >= 24:                       # internal child
-                assert (m & 31) == 24 + s and (int(N["imask"]) >> s) & 1
+            unary = (tri_mask >> (3 * s)) & 7
+            if (imask >> s) & 1:                                        # internal child
+                assert unary == 0, "a child is internal or a leaf, not both"
+                used.append(s)
                 ci = int(N["childBase"]) + rank
                 rank += 1
                 assert 0 < ci < len(nodes)
@@ -62,11 +65,11 @@ def validate_bvh8(nodes, slots, slack, tris):
                 depth_of[ci] = depth_of[ni] + 1
                 stack.append(ci)
                 cost += _area(blo[s], bhi[s])
-            else:
-                assert not (int(N["imask"]) >> s) & 1
-                cnt = {1: 1, 3: 2, 7: 3}[m >> 5]
-                off = m & 31
-                assert off == tri_off_expected, "leaf children must be packed in slot order"
+            elif unary:
+                used.append(s)
+                cnt = {1: 1, 3: 2, 7: 3}[unary]
+                off = bin(tri_mask & ((1 << (3 * s)) - 1)).count("1")    # the kernel's rank: popcount of triMask below the bit
+                assert off == tri_off_expected
                 tri_off_expected += cnt
                 a = int(N["triBase"]) + off
                 assert a + cnt <= n and not seen_slots[a:a + cnt].any()
@@ -77,7 +80,7 @@ def validate_bvh8(nodes, slots, slack, tris):
                 cost += _area(blo[s], bhi[s]) * cnt
         assert tri_off_expected <= 24
         if ni == 0:
-            root_area = _area(blo[[s for s in range(8) if N["meta"][s]]].min(0), bhi[[s for s in range(8) if N["meta"][s]]].max(0))
+            root_area = _area(blo[used].min(0), bhi[used].max(0))
     assert seen_nodes.all(), "unreachable nodes"
     assert seen_slots.all(), "triangle slots not referenced by any leaf"
     for ni in reversed(order):                                        # children after parents in `order`: fold bottom-up

@@ -57,7 +57,7 @@ class ElevenHit(C.Structure):
 
 
 # bvh8.h: Node8 (80 B) and TriSlot (48 B) as they live on the device
-NODE8_DT = np.dtype([("p", "<f4", 3), ("e", "u1", 3), ("imask", "u1"), ("childBase", "<u4"), ("triBase", "<u4"), ("meta", "u1", 8),
+NODE8_DT = np.dtype([("p", "<f4", 3), ("e", "u1", 3), ("imask", "u1"), ("childBase", "<u4"), ("triBase", "<u4"), ("triMask", "<u4"), ("slack", "<f4"),
                      ("qlox", "u1", 8), ("qloy", "u1", 8), ("qloz", "u1", 8), ("qhix", "u1", 8), ("qhiy", "u1", 8), ("qhiz", "u1", 8)])
 SLOT_DT = np.dtype([("v0", "<f4", 3), ("e1", "<f4", 3), ("e2", "<f4", 3), ("tri", "<i4"), ("material", "<i4"), ("shiftBound", "<f4")])
 assert NODE8_DT.itemsize == 80 and SLOT_DT.itemsize == 48
@@ -150,6 +150,7 @@ def load_library(path: str = LIB_PATH):
     L.eleven_bvh_download.argtypes = [vp, vp, sz, vp, sz, vp]
     L.eleven_host_alloc.argtypes = [vp, sz, C.POINTER(vp)]
     L.eleven_host_free.argtypes = [vp, vp]
+    L.eleven_bvh_build_host.argtypes = [vp, C.c_uint32, vp, C.c_int, vp, sz, vp, sz, vp, vp, vp]
     if L.eleven_abi_version() != 2:
         raise RuntimeError("ABI version mismatch")
     _lib = L
@@ -162,5 +163,22 @@ EXPORTED_SYMBOLS = [
     "eleven_film_reset", "eleven_set_camera", "eleven_trace_closest", "eleven_trace_device", "eleven_film_sums_device",
     "eleven_film_counts_device", "eleven_device_alloc", "eleven_device_free", "eleven_device_upload",
     "eleven_device_download", "eleven_resolve_rgba8", "eleven_bvh_download", "eleven_host_alloc",
-    "eleven_host_free",
+    "eleven_host_free", "eleven_bvh_build_host",
 ]
+
+
+def bvh_build_host(tris, tri_material=None, threads=0):
+    """(nodes, slots, node_slack, key_slack) from the HOST BVH8 builder alone (eleven_bvh_build_host): no GPU, no context."""
+    L = load_library()
+    tris = np.ascontiguousarray(tris)
+    n = len(tris)
+    mat = None if tri_material is None else np.ascontiguousarray(tri_material, np.int32)
+    counts = np.zeros(2, np.uint32)
+    ks = np.zeros(1, np.float32)
+    L.eleven_bvh_build_host(tris.ctypes.data, n, None if mat is None else mat.ctypes.data, threads, None, 0, None, 0, None, counts.ctypes.data, ks.ctypes.data)
+    nodes, slots, slack = np.zeros(int(counts[0]), NODE8_DT), np.zeros(int(counts[1]), SLOT_DT), np.zeros(int(counts[0]), np.float32)
+    rc = L.eleven_bvh_build_host(tris.ctypes.data, n, None if mat is None else mat.ctypes.data, threads, nodes.ctypes.data, len(nodes),
+                                 slots.ctypes.data, len(slots), slack.ctypes.data, counts.ctypes.data, ks.ctypes.data)
+    if rc != 0:
+        raise RuntimeError("eleven_bvh_build_host: %s" % L.eleven_last_error().decode())
+    return nodes, slots, slack, float(ks[0])

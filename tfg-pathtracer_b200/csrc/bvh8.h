@@ -19,14 +19,21 @@
 namespace eleven {
 
 /* 80 bytes = 5 x 16-byte loads.
- * child box i: lo = p + 2^e * qlo[i], hi = p + 2^e * qhi[i] (per axis).
- * meta[i]: 0 = empty; internal child: 0b001xxxxx with xxxxx = 24 + slot; leaf: top 3 bits = unary triangle
- * count (1 -> 001, 2 -> 011, 3 -> 111), low 5 bits = first triangle's offset from triBase (0..23). */
+ * child box i: lo = p + 2^e * qlo[i], hi = p + 2^e * qhi[i] (per axis); child i sits in octant slot i.
+ * imask: bit i set = child i is an internal node (its node index = childBase + popcount(imask below i)).
+ * triMask: bit 3*i + k set = child i is a leaf holding more than k triangles (<= 3 per leaf).  The triangles of a node
+ *   are contiguous in memory in (slot, k) order: the slot of bit b is triBase + popcount(triMask below b).  The fixed
+ *   3-bits-per-child positions let the traversal turn its 8-bit child hit mask into the triangle mask with one table
+ *   look-up and one AND (round 1 stored an (offset, unary count) byte per child and spent 5 ALU-pipe instructions per
+ *   child on `count << offset`: the ALU pipe was the limiter of the node test).
+ * slack: largest TriSlot::shiftBound below this node (the same value as Bvh8::nodeSlack[i], inside the node so that the
+ *   KEY-mode cull needs no second load). */
 struct alignas(16) Node8 {
     float   px, py, pz;
     uint8_t ex, ey, ez, imask;
     uint32_t childBase, triBase;
-    uint8_t meta[8];
+    uint32_t triMask;
+    float    slack;
     uint8_t qlox[8], qloy[8];
     uint8_t qloz[8], qhix[8];
     uint8_t qhiy[8], qhiz[8];

@@ -284,7 +284,7 @@ void buildBvh8(const ElevenTri* tris, uint32_t n, const int32_t* triMaterial, Bv
             }
             if (isLeaf2(c)) {
                 uint32_t cnt = (uint32_t)c.count;               // <= 3
-                N.meta[s] = (uint8_t)((((1u << cnt) - 1u) << 5) | triOff);
+                N.triMask |= ((1u << cnt) - 1u) << (3 * s);
                 for (uint32_t k = 0; k < cnt; k++) {
                     int t = B.idx[c.first + k];
                     const ElevenTri& T = tris[t];
@@ -297,7 +297,6 @@ void buildBvh8(const ElevenTri* tris, uint32_t n, const int32_t* triMaterial, Bv
                 }
                 triOff += cnt;
             } else {
-                N.meta[s] = (uint8_t)((1u << 5) | (24u + (uint32_t)s));
                 N.imask |= (uint8_t)(1u << s);
             }
         }
@@ -315,6 +314,7 @@ void buildBvh8(const ElevenTri* tris, uint32_t n, const int32_t* triMaterial, Bv
             for (int k = root.first; k < root.first + root.span; k++) ms = std::max(ms, triShift[B.idx[k]]);
             if (out.nodeSlack.size() <= it.n8) out.nodeSlack.resize(it.n8 + 1, 0.f);
             out.nodeSlack[it.n8] = ms;
+            out.nodes[it.n8].slack = ms;
         }
     }
     out.nodeSlack.resize(out.nodes.size(), 0.f);

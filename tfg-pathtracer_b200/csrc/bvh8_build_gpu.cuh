@@ -456,7 +456,7 @@ __global__ void __launch_bounds__(128) k_collapseEmit(const Node2G* __restrict__
     Node8 N; memset(&N, 0, sizeof N);
     N.px = root.lo[0]; N.py = root.lo[1]; N.pz = root.lo[2];
     N.ex = quantExpDev(root.hi[0] - root.lo[0]); N.ey = quantExpDev(root.hi[1] - root.lo[1]); N.ez = quantExpDev(root.hi[2] - root.lo[2]);
-    N.childBase = childBase; N.triBase = triBase;
+    N.childBase = childBase; N.triBase = triBase; N.slack = root.maxShift;
     const uint8_t ebits[3] = {N.ex, N.ey, N.ez};
     const float pf3[3] = {N.px, N.py, N.pz};
     uint8_t* qlo[3] = {N.qlox, N.qloy, N.qloz}; uint8_t* qhi[3] = {N.qhix, N.qhiy, N.qhiz};
@@ -477,7 +477,7 @@ __global__ void __launch_bounds__(128) k_collapseEmit(const Node2G* __restrict__
         }
         if (c.left < 0) {
             const uint32_t cnt = c.count;                            // 1..3
-            N.meta[s] = (uint8_t)((((1u << cnt) - 1u) << 5) | triOff);
+            N.triMask |= ((1u << cnt) - 1u) << (3 * s);
             uint32_t t3[3];
             for (uint32_t k = 0; k < cnt; k++) t3[k] = idx[c.first + k];
             // arrival order of the partition atomics is not deterministic: emit in triangle-id order
@@ -496,7 +496,6 @@ __global__ void __launch_bounds__(128) k_collapseEmit(const Node2G* __restrict__
             }
             triOff += cnt;
         } else {
-            N.meta[s] = (uint8_t)((1u << 5) | (24u + (uint32_t)s));
             N.imask |= (uint8_t)(1u << s);
             Item8 ni; ni.n2 = (uint32_t)c2; ni.n8 = childBase + rank; ni.depth = it.depth + 1u;     // internal children contiguous in ascending slot order
             nextItems[itemBase + rank] = ni;

@@ -680,6 +680,25 @@ extern "C" int eleven_bvh_download(ElevenCtx* c, void* nodes, size_t nodeCap, vo
     return ELEVEN_OK;
 }
 
+// Test hook: the HOST builder on its own (bvh8_build.cpp; replaces BVH::build, S/BVH.hpp:187-330).  Needs no GPU and no context,
+// so the tree layout the kernels walk is checked by the CPU test-suite too.  counts = {nodes, slots}; returns ELEVEN_ERR_ARG with
+// the counts filled in when a buffer is too small.
+extern "C" int eleven_bvh_build_host(const ElevenTri* tris, uint32_t n, const int32_t* triMaterial, int threads,
+                                     void* nodes, size_t nodeCap, void* slots, size_t slotCap, float* nodeSlack,
+                                     uint32_t* counts, float* keySlack) {
+    if ((!tris && n) || !counts) return fail(ELEVEN_ERR_ARG, "eleven_bvh_build_host: null argument");
+    Bvh8 bvh;
+    buildBvh8(tris, n, triMaterial, bvh, threads > 0 ? threads : (int)std::max(1u, std::thread::hardware_concurrency()));
+    counts[0] = (uint32_t)bvh.nodes.size(); counts[1] = (uint32_t)bvh.slots.size();
+    if (keySlack) *keySlack = bvh.keySlack;
+    if ((nodes && nodeCap < bvh.nodes.size()) || (slots && slotCap < bvh.slots.size()) || (nodeSlack && nodeCap < bvh.nodes.size()))
+        return fail(ELEVEN_ERR_ARG, "eleven_bvh_build_host: buffers too small (counts returned)");
+    if (nodes) memcpy(nodes, bvh.nodes.data(), bvh.nodes.size() * sizeof(Node8));
+    if (slots) memcpy(slots, bvh.slots.data(), bvh.slots.size() * sizeof(TriSlot));
+    if (nodeSlack) memcpy(nodeSlack, bvh.nodeSlack.data(), bvh.nodeSlack.size() * sizeof(float));
+    return ELEVEN_OK;
+}
+
 // ---- device plumbing for the one-process-per-GPU driver ------------------------------------------------------------------
 extern "C" int eleven_film_sums_device(ElevenCtx* c, int pass, void** p, size_t* nFloats) {
     if (!c || !p || !nFloats) return fail(ELEVEN_ERR_ARG, "eleven_film_sums_device: null argument");

@@ -50,17 +50,59 @@ __device__ __forceinline__ float byteMagic15(uint32_t q4, uint32_t magic, uint32
 
 __device__ __forceinline__ float byteI2F(uint32_t q4, int j) { return (float)((q4 >> (8 * j)) & 0xffu); }   // I2F.U8 on the conversion pipe
 
+#ifndef EL_SAT
+#define EL_SAT 1               /* near planes through FFMA.SAT on a per-ray power-of-two time scale (see traceQueue) */
+#endif
+// a * b + c clamped to [0, 1] in the FMA pipe (FFMA.SAT): the `max(tmin, 0)` of the slab test for free
+__device__ __forceinline__ float fmaSat(float a, float b, float c) {
+#if EL_SAT
+    float r; asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r;
+#else
+    return fmaxf(fmaf(a, b, c), 0.f);
+#endif
+}
+
+// Child hit mask -> traversal masks by table (shared memory, 3 KB per CTA, filled by the CTA itself):
+//   expand[h]  bit 3*i + k (k = 0..2) set iff bit i of h is set: AND with Node8::triMask = the triangles of the hit leaves;
+//   perm[o][h] bit (i ^ o) set iff bit i of h is set: the hit internal children in front-to-back order for ray octant o
+//              (highest bit = nearest child, as the pop takes the highest bit).
+// Round 1 built both masks child by child from an (offset, count) byte: 2 extracts, a shift and an OR per child on the ALU
+// pipe, which the node test saturates (ncu: ALU pipe 72 % at 78 % issue; SASS: 150 of the 272 node-phase instructions on ALU).
+struct TraceLut { uint32_t expand[256]; uint8_t perm[8][256]; };
+
+__device__ __forceinline__ void traceLutInit(TraceLut& L) {
+    for (uint32_t h = threadIdx.x; h < 256u; h += blockDim.x) {
+        uint32_t e = 0;
+        for (uint32_t i = 0; i < 8u; i++) if ((h >> i) & 1u) e |= 7u << (3u * i);
+        L.expand[h] = e;
+        for (uint32_t o = 0; o < 8u; o++) {
+            uint32_t p = 0;
+            for (uint32_t i = 0; i < 8u; i++) if ((h >> i) & 1u) p |= 1u << (i ^ o);
+            L.perm[o][h] = (uint8_t)p;
+        }
+    }
+    __syncthreads();
+}
+
 template <int MODE, bool COUNT, bool NEED_KEY, class Source, class Sink>
 __device__ __forceinline__ void traceQueue(const DevScene& S, uint32_t n, uint32_t* workCounter, Source& src, Sink& sink, TraceCounters& tc) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t FULL = 0xffffffffu;
     const uint32_t ltMask = (1u << lane) - 1u;
     const uint32_t magic = S.byteMagic;
+    __shared__ TraceLut lut;
+    traceLutInit(lut);
+    // Per-ray time scale 2^-k with 2^k beyond the far end of the scene (root box) as seen from the ray origin: all slab
+    // distances of the node test live in [0, 1] then, and FFMA.SAT clamps the near planes at 0 for free.  A power of two,
+    // folded into 1/dir: every product and sum is the unscaled one times 2^-k exactly, so the test decides as before (the
+    // clamp at 1 can only ADD children, and only beyond the scene).
+    float4 root0 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (EL_SAT && S.nodeCount) root0 = __ldg(S.nodes);
 
     bool active = false, exhausted = (S.nodeCount == 0 && false);
     LaneRay lr; lr.tag = 0; lr.tmaxAny = INFINITY; lr.ray.o = f3(0.f); lr.ray.d = f3(0.f, 0.f, 1.f);
-    float idx = 0.f, idy = 0.f, idz = 0.f, dx = 1.f, dy = 1.f, dz = 1.f;
-    uint32_t octinv4 = 0;
+    float idx = 0.f, idy = 0.f, idz = 0.f, dx = 1.f, dy = 1.f, dz = 1.f, tscale = 1.f;
+    uint32_t octinv = 0, tvalid = 0, tpostValid = 0;
     float slack = 0.f, epsRay = 0.f, tcull = INFINITY, bestLo = INFINITY, bestHi = INFINITY;   // [bestLo, bestHi] brackets the best key
     bool bestExact = false;
     HitRec best; best.tri = -1; best.t = best.u = best.v = best.key = 0.f;
@@ -85,16 +127,23 @@ __device__ __forceinline__ void traceQueue(const DevScene& S, uint32_t n, uint32
                     dx = fabsf(d.x) > 1e-20f ? d.x : copysignf(1e-20f, d.x);
                     dy = fabsf(d.y) > 1e-20f ? d.y : copysignf(1e-20f, d.y);
                     dz = fabsf(d.z) > 1e-20f ? d.z : copysignf(1e-20f, d.z);
-                    idx = 1.0f / dx; idy = 1.0f / dy; idz = 1.0f / dz;
-                    octinv4 = ((dx >= 0.f ? 4u : 0u) | (dy >= 0.f ? 2u : 0u) | (dz >= 0.f ? 1u : 0u)) * 0x01010101u;
                     const F3 o = lr.ray.o;
+                    if (EL_SAT) {
+                        const uint32_t re = __float_as_uint(root0.w);      // root box: [p, p + 255 * 2^e] per axis
+                        const float far1 = (fabsf(o.x - root0.x) + fabsf(o.y - root0.y) + fabsf(o.z - root0.z)) +
+                                           256.f * (__uint_as_float((re & 0xffu) << 23) + __uint_as_float(((re >> 8) & 0xffu) << 23) + __uint_as_float(((re >> 16) & 0xffu) << 23));
+                        const uint32_t fe = min(max(__float_as_uint(far1) >> 23, 64u), 190u);   // biased exponent of the bound, kept far from under/overflow
+                        tscale = __uint_as_float((253u - fe) << 23);                              // 2^-(e+1) < 1 / far1
+                    }
+                    idx = (1.0f / dx) * tscale; idy = (1.0f / dy) * tscale; idz = (1.0f / dz) * tscale;
+                    octinv = (dx >= 0.f ? 4u : 0u) | (dy >= 0.f ? 2u : 0u) | (dz >= 0.f ? 1u : 0u);
                     epsRay = 4e-6f * (fabsf(o.x) + fabsf(o.y) + fabsf(o.z));
                     slack = (MODE == TRACE_CLOSEST_KEY) ? S.keySlack + epsRay : 0.f;
                     tcull = (MODE == TRACE_ANY) ? lr.tmaxAny : INFINITY;
                     bestLo = bestHi = INFINITY; bestExact = false;
                     best.tri = -1; best.t = best.u = best.v = best.key = 0.f;
                     ngroup = make_uint2(0u, S.nodeCount ? 0x80000000u : 0u);
-                    tgroup = make_uint2(0u, 0u); tpost = make_uint2(0u, 0u);
+                    tgroup = make_uint2(0u, 0u); tpost = make_uint2(0u, 0u); tvalid = tpostValid = 0u;
                     sp = 0;
                     active = true;
                 }
@@ -107,7 +156,7 @@ __device__ __forceinline__ void traceQueue(const DevScene& S, uint32_t n, uint32
 
         // ---- bookkeeping: promote the postponed triangle group, pop a node group, or finish -------------------------------
         if (active) {
-            if (tgroup.y == 0u && tpost.y != 0u) { tgroup = tpost; tpost.y = 0u; }
+            if (tgroup.y == 0u && tpost.y != 0u) { tgroup = tpost; tvalid = tpostValid; tpost.y = 0u; }
             if (ngroup.y <= 0x00ffffffu && sp > 0) ngroup = stack[--sp];
             if (ngroup.y <= 0x00ffffffu && tgroup.y == 0u) {
                 if (MODE == TRACE_CLOSEST_KEY && NEED_KEY && best.tri >= 0 && !bestExact) {
@@ -125,7 +174,6 @@ __device__ __forceinline__ void traceQueue(const DevScene& S, uint32_t n, uint32
         const bool doNode = active && ngroup.y > 0x00ffffffu && tpost.y == 0u;
         if (__any_sync(FULL, doNode)) {
             if (doNode) {
-                const uint32_t octinv = octinv4 & 7u;
                 const uint32_t imask = ngroup.y;
                 const uint32_t bit = 31u - __clz(ngroup.y);
                 ngroup.y &= ~(1u << bit);
@@ -134,10 +182,10 @@ __device__ __forceinline__ void traceQueue(const DevScene& S, uint32_t n, uint32
                 const uint32_t rank = __popc(imask & ~(0xffffffffu << slot));
                 const uint32_t nodeIndex = ngroup.x + rank;
                 const float4* np = S.nodes + (size_t)nodeIndex * 5;
-                // KEY mode: a triangle below this node can only win if t - shift - e <= bestHi, and its shift is bounded
-                // by this node's subtree maximum: cull the children with that LOCAL slack instead of the scene maximum
-                const float tcullNode = (MODE == TRACE_CLOSEST_KEY) ? (bestHi + __ldg(S.nodeSlack + nodeIndex) + epsRay) * 1.00001f : tcull;
                 const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+                // KEY mode: a triangle below this node can only win if t - shift - e <= bestHi, and its shift is bounded
+                // by this node's subtree maximum (Node8::slack): cull the children with that LOCAL slack instead of the scene maximum
+                const float tcullNode = ((MODE == TRACE_CLOSEST_KEY) ? (bestHi + n1.w + epsRay) * 1.00001f : tcull) * tscale;
                 if (COUNT) tc.nodes++;
                 const F3 o = lr.ray.o;
                 const uint32_t eim = __float_as_uint(n0.w);
@@ -148,14 +196,9 @@ __device__ __forceinline__ void traceQueue(const DevScene& S, uint32_t n, uint32
                 // addends of the near planes: o - 2^15 a, nudged towards the ray origin by its own rounding bound (see byteMagic15)
                 const float oxN0 = fmaf(-32768.f, ax, ox), oyN0 = fmaf(-32768.f, ay, oy), ozN0 = fmaf(-32768.f, az, oz);
                 const float oxN = fmaf(-fabsf(oxN0), 1.1920929e-7f, oxN0), oyN = fmaf(-fabsf(oyN0), 1.1920929e-7f, oyN0), ozN = fmaf(-fabsf(ozN0), 1.1920929e-7f, ozN0);
-                uint32_t hitmask = 0;
+                uint32_t h8 = 0;                                              // bit i: child box i (= octant slot i) is hit
 #pragma unroll
                 for (int half = 0; half < 2; half++) {
-                    const uint32_t meta4 = __float_as_uint(half ? n1.w : n1.z);
-                    const uint32_t isInner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
-                    const uint32_t innerMask4 = (isInner4 >> 4) * 0xffu;
-                    const uint32_t bitIndex4 = (meta4 ^ (octinv4 & innerMask4)) & 0x1f1f1f1fu;
-                    const uint32_t childBits4 = (meta4 >> 5) & 0x07070707u;
                     const uint32_t qlox = __float_as_uint(half ? n2.y : n2.x), qloy = __float_as_uint(half ? n2.w : n2.z);
                     const uint32_t qloz = __float_as_uint(half ? n3.y : n3.x), qhix = __float_as_uint(half ? n3.w : n3.z);
                     const uint32_t qhiy = __float_as_uint(half ? n4.y : n4.x), qhiz = __float_as_uint(half ? n4.w : n4.z);
@@ -167,23 +210,22 @@ __device__ __forceinline__ void traceQueue(const DevScene& S, uint32_t n, uint32
                         const uint32_t sel = 0x7504u + ((uint32_t)j << 4);       // bytes: 0x00, q_j, 0x00, 0x47
                         // pipe balancing (ncu: ALU pipe 65 % busy, XU 6 %): the near planes are decoded with PRMT (ALU pipe, the
                         // offset folded into the FMA), the far planes with I2F (conversion unit), so neither pipe carries all 48
-                        const float tminx = fmaf(byteMagic15(xmin, magic, sel), ax, oxN), tmaxx = fmaf(byteI2F(xmax, j), ax, ox);
-                        const float tminy = fmaf(byteMagic15(ymin, magic, sel), ay, oyN), tmaxy = fmaf(byteI2F(ymax, j), ay, oy);
-                        const float tminz = fmaf(byteMagic15(zmin, magic, sel), az, ozN), tmaxz = fmaf(byteI2F(zmax, j), az, oz);
-                        const float cmin = fmaxf(fmaxf(tminx, tminy), fmaxf(tminz, 0.f));
+                        const float tminx = fmaSat(byteMagic15(xmin, magic, sel), ax, oxN), tmaxx = fmaf(byteI2F(xmax, j), ax, ox);
+                        const float tminy = fmaSat(byteMagic15(ymin, magic, sel), ay, oyN), tmaxy = fmaf(byteI2F(ymax, j), ay, oy);
+                        const float tminz = fmaSat(byteMagic15(zmin, magic, sel), az, ozN), tmaxz = fmaf(byteI2F(zmax, j), az, oz);
+                        const float cmin = fmaxf(fmaxf(tminx, tminy), tminz);     // >= 0 already (FFMA.SAT)
                         const float cmax = fminf(fminf(tmaxx, tmaxy), fminf(tmaxz, tcullNode));
-                        if (cmin <= cmax * 1.000001f) {          // relative slack for the rounding of the fused distances
-                            const uint32_t cb = (childBits4 >> (8 * j)) & 0xffu, bi = (bitIndex4 >> (8 * j)) & 0xffu;
-                            hitmask |= cb << bi;
-                        }
+                        if (cmin <= cmax * 1.000001f) h8 |= 1u << (4 * half + j);  // relative slack for the rounding of the fused distances
                     }
                 }
+                // empty slots hold a zero box: whatever the test says about them, imask and triMask drop them
+                const uint32_t im8 = eim >> 24, triMask = __float_as_uint(n1.z);
                 ngroup.x = __float_as_uint(n1.x);
-                ngroup.y = (hitmask & 0xff000000u) | (eim >> 24);
-                const uint32_t newTris = hitmask & 0x00ffffffu;
+                ngroup.y = __byte_perm(im8, (uint32_t)lut.perm[octinv][h8 & im8], 0x4210);   // (hit internal children, front to back) << 24 | imask
+                const uint32_t newTris = lut.expand[h8] & triMask;
                 if (newTris) {
-                    if (tgroup.y != 0u) tpost = make_uint2(__float_as_uint(n1.y), newTris);
-                    else tgroup = make_uint2(__float_as_uint(n1.y), newTris);
+                    if (tgroup.y != 0u) { tpost = make_uint2(__float_as_uint(n1.y), newTris); tpostValid = triMask; }
+                    else { tgroup = make_uint2(__float_as_uint(n1.y), newTris); tvalid = triMask; }
                 }
             }
         }
@@ -192,14 +234,14 @@ __device__ __forceinline__ void traceQueue(const DevScene& S, uint32_t n, uint32
         //      test costs about a third of a node test: this keeps the two phases balanced at the leaf level) ---------------
 #pragma unroll 1
         for (int round = 0; round < (MODE == TRACE_ANY ? 1 : EL_TRIS_PER_ITER); round++) {   // measured: 2 rounds -10 % on closest hit, +3 % on any hit
-        if (active && tgroup.y == 0u && tpost.y != 0u) { tgroup = tpost; tpost.y = 0u; }
+        if (active && tgroup.y == 0u && tpost.y != 0u) { tgroup = tpost; tvalid = tpostValid; tpost.y = 0u; }
         const bool doTri = active && tgroup.y != 0u;
         if (!__any_sync(FULL, doTri)) break;
         {
             if (doTri) {
-                const uint32_t ti = 31u - __clz(tgroup.y);
-                tgroup.y &= ~(1u << ti);
-                const float4* tp = S.slots + (size_t)(tgroup.x + ti) * 3;
+                const uint32_t tb = 1u << (31u - __clz(tgroup.y));
+                tgroup.y &= ~tb;
+                const float4* tp = S.slots + (size_t)(tgroup.x + __popc(tvalid & (tb - 1u))) * 3;   // Node8::triMask: slots are packed in bit order
                 const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
                 if (COUNT) tc.tris++;
                 float t, u, v;
