@@ -19,8 +19,14 @@ try:
 except Exception as e: print("$n failed", e)
 PY
 done
+if [ -z "$SKIP_REF" ]; then
 timeout 600 python bench.py --impl reference > $out/bench_reference.json 2> $out/bench_reference.err; echo "ref rc=$?"
 cat $out/bench_reference.json
+fi
+if [ -n "$SANITIZE" ]; then
+timeout 900 compute-sanitizer --tool racecheck python tools/sanitize_run.py > $out/racecheck.log 2>&1; echo "racecheck rc=$?"; tail -3 $out/racecheck.log
+timeout 900 compute-sanitizer --tool memcheck python tools/sanitize_run.py > $out/memcheck.log 2>&1; echo "memcheck rc=$?"; tail -3 $out/memcheck.log
+fi
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/launches.csv python tools/profile_run.py --spp 16 > $out/launches.log 2>&1; echo "ncu list rc=$?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_extend|k_shadowEnv|k_shade" -c 15 -o $out/wave16 -f python tools/profile_run.py --spp 16 > $out/ncu_full.log 2>&1; echo "ncu full rc=$?"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_extend|k_shadowEnv" -c 6 -o $out/wave16 -f python tools/profile_run.py --spp 16 > $out/ncu_full.log 2>&1; echo "ncu full rc=$?"
 ls -la $out
