@@ -16,6 +16,15 @@
 #include <vector>
 #include "../../include/eleven_b200.h"
 
+/* Leaf policy of both builders (binary binned-SAH stage): a node of <= EL_MAX_LEAF (<= 3) triangles stays a leaf unless
+ * splitting it is cheaper by SAH, with a triangle test costing 1 and the split EL_LEAF_COST_NODE. */
+#ifndef EL_MAX_LEAF
+#define EL_MAX_LEAF 3
+#endif
+#ifndef EL_LEAF_COST_NODE
+#define EL_LEAF_COST_NODE 1.0f
+#endif
+
 namespace eleven {
 
 /* 80 bytes = 5 x 16-byte loads.

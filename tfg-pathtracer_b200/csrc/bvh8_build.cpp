@@ -34,14 +34,8 @@ struct Node2 { Box box; int left, right, first, count, span; };   // leaf iff co
 
 static const int   MAXBINS = 64;
 static int BINS = 16;            // ELEVEN_BVH_BINS (experiments); 16 is what the device builder uses
-#ifndef EL_MAX_LEAF
-#define EL_MAX_LEAF 3
-#endif
-#ifndef EL_COST_NODE
-#define EL_COST_NODE 1.0f
-#endif
-static const int   MAX_LEAF = EL_MAX_LEAF;
-static const float COST_TRI = 1.0f, COST_NODE = EL_COST_NODE;
+static const int   MAX_LEAF = EL_MAX_LEAF;                 // bvh8.h
+static const float COST_TRI = 1.0f, COST_NODE = EL_LEAF_COST_NODE;
 
 struct Builder {
     const ElevenTri* tris; uint32_t n;

@@ -38,7 +38,7 @@
 namespace eleven {
 namespace gpubvh {
 
-enum { BINS = 16, MAX_LEAF = 3, BIN_WORDS = 8, NODE_BIN_WORDS = 3 * BINS * BIN_WORDS };   // bin: lo xyz, hi xyz, count, max shift
+enum { BINS = 16, MAX_LEAF = EL_MAX_LEAF, BIN_WORDS = 8, NODE_BIN_WORDS = 3 * BINS * BIN_WORDS };   // bin: lo xyz, hi xyz, count, max shift
 enum { C_NODES = 0, C_NEXT_ACTIVE = 1, C_COUNT = 8 };
 enum { SCENE_LO = 0, SCENE_HI = 3, SCENE_SHIFT = 6, SCENE_WORDS = 8 };
 
@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(128) k_split(Node2G* __restrict__ nodes, const
     // SAH leaf termination, as the host builder: a node of <= MAX_LEAF triangles stays a leaf unless splitting it is cheaper
     if (N.count <= (uint32_t)MAX_LEAF) {
         const float area = boxArea(N.lo, N.hi);
-        if (bestAxis < 0 || area * (float)N.count <= area + bestCost) return;      // cost of a triangle test = cost of a node = 1
+        if (bestAxis < 0 || area * (float)N.count <= area * EL_LEAF_COST_NODE + bestCost) return;      // cost of a triangle test = 1, of the split = EL_LEAF_COST_NODE (bvh8.h)
     }
     const int left = (int)atomicAdd(&counters[C_NODES], 2u);
     Node2G L, R;

@@ -69,10 +69,13 @@ __device__ __forceinline__ float fmaSat(float a, float b, float c) {
 // Round 1 built both masks child by child from an (offset, count) byte: 2 extracts, a shift and an OR per child on the ALU
 // pipe, which the node test saturates (ncu: ALU pipe 72 % at 78 % issue; SASS: 150 of the 272 node-phase instructions on ALU).
 #ifndef EL_COOP_TRIS
-#define EL_COOP_TRIS 1         /* closest-hit triangle tests packed densely over the warp (see traceQueue) */
+#define EL_COOP_TRIS 0         /* closest-hit triangle tests packed densely over the warp (see traceQueue) */
 #endif
 // Per-warp exchange area of the cooperative triangle phase: the rays of the 32 lanes, up to 64 offered (lane, triangle slot)
 // tasks and their results.  2.5 KB per warp with 2 offers per lane.
+#ifndef EL_COOP_ANY
+#define EL_COOP_ANY 0          /* the same for any-hit (shadow) rays */
+#endif
 #ifndef EL_COOP_OFFER
 #define EL_COOP_OFFER 2        /* triangles a lane may offer per iteration (1..3) */
 #endif
@@ -100,9 +103,10 @@ __device__ __forceinline__ void traceQueue(const DevScene& S, uint32_t n, uint32
     const uint32_t FULL = 0xffffffffu;
     const uint32_t ltMask = (1u << lane) - 1u;
     const uint32_t magic = S.byteMagic;
+    constexpr bool COOP = EL_COOP_TRIS && (MODE != TRACE_ANY || EL_COOP_ANY);
     __shared__ TraceLut lut;
-    __shared__ CoopWarp coopAll[(MODE != TRACE_ANY && EL_COOP_TRIS) ? 4 : 1];      // one per warp of the 128-thread CTA
-    CoopWarp& cw = coopAll[(MODE != TRACE_ANY && EL_COOP_TRIS) ? (threadIdx.x >> 5) : 0];
+    __shared__ CoopWarp coopAll[COOP ? 4 : 1];      // one per warp of the 128-thread CTA
+    CoopWarp& cw = coopAll[COOP ? (threadIdx.x >> 5) : 0];
     traceLutInit(lut);
     // Per-ray time scale 2^-k with 2^k beyond the far end of the scene (root box) as seen from the ray origin: all slab
     // distances of the node test live in [0, 1] then, and FFMA.SAT clamps the near planes at 0 for free.  A power of two,
@@ -135,7 +139,7 @@ __device__ __forceinline__ void traceQueue(const DevScene& S, uint32_t n, uint32
                 const uint32_t qi = base + __popc(idle & ltMask);
                 if (qi < n) {
                     src.load(qi, lr);
-                    if (MODE != TRACE_ANY && EL_COOP_TRIS) {       // the ray as other lanes will need it for the cooperative triangle tests
+                    if (COOP) {       // the ray as other lanes will need it for the cooperative triangle tests
                         cw.rayO[lane] = make_float4(lr.ray.o.x, lr.ray.o.y, lr.ray.o.z, 0.f);
                         cw.rayD[lane] = make_float4(lr.ray.d.x, lr.ray.d.y, lr.ray.d.z, 0.f);
                     }
@@ -281,7 +285,7 @@ __device__ __forceinline__ void traceQueue(const DevScene& S, uint32_t n, uint32
             }
         };
 
-        if (MODE != TRACE_ANY && EL_COOP_TRIS) {
+        if (COOP) {
         // ---- triangle phase, closest hit: WARP-COOPERATIVE.  ncu/SASS arithmetic on the per-lane version: a ray needs 10.3
         //      node tests but only 7.4 triangle tests, so two per-lane triangle rounds per iteration ran at ~1/3 SIMT
         //      utilisation (0.64 pending triangles per lane and iteration against 2 offered slots) and cost 200 of the ~480 warp
@@ -329,7 +333,12 @@ __device__ __forceinline__ void traceQueue(const DevScene& S, uint32_t n, uint32
                         const uint32_t sk = k == 0 ? slotOf[0] : (k == 1 ? slotOf[EL_COOP_OFFER > 1 ? 1 : 0] : slotOf[EL_COOP_OFFER > 2 ? 2 : 0]);
                         const float4 rr = cw.res[sk];
                         const int tri = __float_as_int(rr.w);
-                        if (tri >= 0) consider(rr.x, rr.y, rr.z, tri, cw.resS[sk]);
+                        if (MODE == TRACE_ANY) {
+                            if (tri >= 0 && rr.x < lr.tmaxAny && active) {
+                                best.tri = tri; best.t = rr.x; best.u = rr.y; best.v = rr.z; best.key = rr.x;
+                                sink.done(lr, best); active = false;
+                            }
+                        } else if (tri >= 0) consider(rr.x, rr.y, rr.z, tri, cw.resS[sk]);
                     }
                 }
             }

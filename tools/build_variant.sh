@@ -5,6 +5,6 @@ set -e
 cd "$(dirname "$0")/../tfg-pathtracer_b200/csrc"
 sfx=$1; shift
 nvcc -O3 -std=c++17 -lineinfo --fmad=false -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC,-O3 "$@" -c eleven_api.cu -o /tmp/eleven_api_$sfx.o
-[ -f bvh8_build.o ] || make bvh8_build.o
-nvcc -gencode arch=compute_100a,code=sm_100a -shared -o libeleven_b200_$sfx.so /tmp/eleven_api_$sfx.o bvh8_build.o -lpthread
+g++ -O3 -std=c++17 -fPIC -pthread "$@" -c bvh8_build.cpp -o /tmp/bvh8_build_$sfx.o
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o libeleven_b200_$sfx.so /tmp/eleven_api_$sfx.o /tmp/bvh8_build_$sfx.o -lpthread
 echo built libeleven_b200_$sfx.so
