@@ -19,7 +19,7 @@
 /* Leaf policy of both builders (binary binned-SAH stage): a node of <= EL_MAX_LEAF (<= 3) triangles stays a leaf unless
  * splitting it is cheaper by SAH, with a triangle test costing 1 and the split EL_LEAF_COST_NODE. */
 #ifndef EL_MAX_LEAF
-#define EL_MAX_LEAF 3
+#define EL_MAX_LEAF 2
 #endif
 #ifndef EL_LEAF_COST_NODE
 #define EL_LEAF_COST_NODE 1.0f

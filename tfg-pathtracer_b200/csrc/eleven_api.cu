@@ -244,7 +244,6 @@ extern "C" int eleven_scene_upload(ElevenCtx* c, const ElevenSceneDesc* d) {
     if (!c || !d) return fail(ELEVEN_ERR_ARG, "eleven_scene_upload: null argument");
     if (d->camera.xRes == 0 || d->camera.yRes == 0) return fail(ELEVEN_ERR_ARG, "camera resolution is zero");
     if (d->triCount && !d->tris) return fail(ELEVEN_ERR_ARG, "tris is null");
-    if (d->triCount >= (1u << 27)) return fail(ELEVEN_ERR_UNSUPPORTED, "more than 2^27 - 1 triangles (the cooperative triangle phase packs lane + slot into 32 bits)");
     if (d->materialCount == 0 || !d->materials) return fail(ELEVEN_ERR_ARG, "at least one material is required");
     if (d->objectCount == 0 || !d->objectMaterial) return fail(ELEVEN_ERR_ARG, "objectMaterial is required");
     CK(cudaSetDevice(c->cfg.device));

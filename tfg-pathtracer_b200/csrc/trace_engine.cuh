@@ -68,19 +68,6 @@ __device__ __forceinline__ float fmaSat(float a, float b, float c) {
 //              (highest bit = nearest child, as the pop takes the highest bit).
 // Round 1 built both masks child by child from an (offset, count) byte: 2 extracts, a shift and an OR per child on the ALU
 // pipe, which the node test saturates (ncu: ALU pipe 72 % at 78 % issue; SASS: 150 of the 272 node-phase instructions on ALU).
-#ifndef EL_COOP_TRIS
-#define EL_COOP_TRIS 0         /* closest-hit triangle tests packed densely over the warp (see traceQueue) */
-#endif
-// Per-warp exchange area of the cooperative triangle phase: the rays of the 32 lanes, up to 64 offered (lane, triangle slot)
-// tasks and their results.  2.5 KB per warp with 2 offers per lane.
-#ifndef EL_COOP_ANY
-#define EL_COOP_ANY 0          /* the same for any-hit (shadow) rays */
-#endif
-#ifndef EL_COOP_OFFER
-#define EL_COOP_OFFER 2        /* triangles a lane may offer per iteration (1..3) */
-#endif
-struct CoopWarp { float4 rayO[32], rayD[32], res[32 * EL_COOP_OFFER]; uint32_t task[32 * EL_COOP_OFFER]; float resS[32 * EL_COOP_OFFER]; };
-
 struct TraceLut { uint32_t expand[256]; uint8_t perm[8][256]; };
 
 __device__ __forceinline__ void traceLutInit(TraceLut& L) {
@@ -103,10 +90,7 @@ __device__ __forceinline__ void traceQueue(const DevScene& S, uint32_t n, uint32
     const uint32_t FULL = 0xffffffffu;
     const uint32_t ltMask = (1u << lane) - 1u;
     const uint32_t magic = S.byteMagic;
-    constexpr bool COOP = EL_COOP_TRIS && (MODE != TRACE_ANY || EL_COOP_ANY);
     __shared__ TraceLut lut;
-    __shared__ CoopWarp coopAll[COOP ? 4 : 1];      // one per warp of the 128-thread CTA
-    CoopWarp& cw = coopAll[COOP ? (threadIdx.x >> 5) : 0];
     traceLutInit(lut);
     // Per-ray time scale 2^-k with 2^k beyond the far end of the scene (root box) as seen from the ray origin: all slab
     // distances of the node test live in [0, 1] then, and FFMA.SAT clamps the near planes at 0 for free.  A power of two,
@@ -139,10 +123,6 @@ __device__ __forceinline__ void traceQueue(const DevScene& S, uint32_t n, uint32
                 const uint32_t qi = base + __popc(idle & ltMask);
                 if (qi < n) {
                     src.load(qi, lr);
-                    if (COOP) {       // the ray as other lanes will need it for the cooperative triangle tests
-                        cw.rayO[lane] = make_float4(lr.ray.o.x, lr.ray.o.y, lr.ray.o.z, 0.f);
-                        cw.rayD[lane] = make_float4(lr.ray.d.x, lr.ray.d.y, lr.ray.d.z, 0.f);
-                    }
                     const F3 d = lr.ray.d;
                     dx = fabsf(d.x) > 1e-20f ? d.x : copysignf(1e-20f, d.x);
                     dy = fabsf(d.y) > 1e-20f ? d.y : copysignf(1e-20f, d.y);
@@ -285,64 +265,6 @@ __device__ __forceinline__ void traceQueue(const DevScene& S, uint32_t n, uint32
             }
         };
 
-        if (COOP) {
-        // ---- triangle phase, closest hit: WARP-COOPERATIVE.  ncu/SASS arithmetic on the per-lane version: a ray needs 10.3
-        //      node tests but only 7.4 triangle tests, so two per-lane triangle rounds per iteration ran at ~1/3 SIMT
-        //      utilisation (0.64 pending triangles per lane and iteration against 2 offered slots) and cost 200 of the ~480 warp
-        //      instructions of an iteration.  Here every lane OFFERS up to EL_COOP_OFFER (2) pending triangles; the offers are packed densely
-        //      over the 32 lanes (ballot prefix), any lane - also one that is idle waiting for the next queue fetch - runs the
-        //      Moeller-Trumbore test for the ray of the offering lane (ray and result travel through shared memory), and the
-        //      offering lane then judges its candidates in its own order.  Same arithmetic on the same operands: same bits.
-            if (active && tgroup.y == 0u && tpost.y != 0u) { tgroup = tpost; tvalid = tpostValid; tpost.y = 0u; }
-            const uint32_t pend = active ? (uint32_t)__popc(tgroup.y) : 0u;
-            uint32_t slotOf[EL_COOP_OFFER], total = 0;
-#pragma unroll
-            for (int k = 0; k < EL_COOP_OFFER; k++) {             // offers in "all first triangles, then all second ones" order
-                const uint32_t bk = __ballot_sync(FULL, pend > (uint32_t)k);
-                slotOf[k] = total + __popc(bk & ltMask);
-                total += __popc(bk);
-            }
-            if (total != 0u) {
-                __syncwarp();                                     // the previous iteration's results have been consumed
-#pragma unroll
-                for (int k = 0; k < EL_COOP_OFFER; k++) {
-                    if (pend > (uint32_t)k) {
-                        const uint32_t tb = 1u << (31u - __clz(tgroup.y));
-                        tgroup.y &= ~tb;
-                        cw.task[slotOf[k]] = (lane << 27) | (tgroup.x + __popc(tvalid & (tb - 1u)));   // Node8::triMask: slots are packed in bit order
-                        if (COUNT) tc.tris++;
-                    }
-                }
-                __syncwarp();
-#pragma unroll 1
-                for (uint32_t r = lane; r < total; r += 32u) {
-                    const uint32_t task = cw.task[r];
-                    const float4 ro = cw.rayO[task >> 27], rd = cw.rayD[task >> 27];
-                    Ray ry; ry.o = f3(ro.x, ro.y, ro.z); ry.d = f3(rd.x, rd.y, rd.z);
-                    const float4* tp = S.slots + (size_t)(task & 0x07ffffffu) * 3;
-                    const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
-                    float t = 0.f, u = 0.f, v = 0.f;
-                    const bool hit = mollerTrumbore(ry, f3(a.x, a.y, a.z), f3(a.w, b.x, b.y), f3(b.z, b.w, c.x), t, u, v);
-                    cw.res[r] = make_float4(t, u, v, hit ? c.y : __int_as_float(-1));      // .w: triangle id, -1 = rejected
-                    cw.resS[r] = c.w;
-                }
-                __syncwarp();
-#pragma unroll 1
-                for (int k = 0; k < EL_COOP_OFFER; k++) {
-                    if (pend > (uint32_t)k) {
-                        const uint32_t sk = k == 0 ? slotOf[0] : (k == 1 ? slotOf[EL_COOP_OFFER > 1 ? 1 : 0] : slotOf[EL_COOP_OFFER > 2 ? 2 : 0]);
-                        const float4 rr = cw.res[sk];
-                        const int tri = __float_as_int(rr.w);
-                        if (MODE == TRACE_ANY) {
-                            if (tri >= 0 && rr.x < lr.tmaxAny && active) {
-                                best.tri = tri; best.t = rr.x; best.u = rr.y; best.v = rr.z; best.key = rr.x;
-                                sink.done(lr, best); active = false;
-                            }
-                        } else if (tri >= 0) consider(rr.x, rr.y, rr.z, tri, cw.resS[sk]);
-                    }
-                }
-            }
-        } else {
         // ---- triangle phase, per lane: up to EL_TRIS_PER_ITER triangles (leaf nodes yield ~2.5 triangles per node visit, a
         //      triangle test costs about a third of a node test: this keeps the two phases balanced at the leaf level) ---------
 #pragma unroll 1
@@ -370,7 +292,6 @@ __device__ __forceinline__ void traceQueue(const DevScene& S, uint32_t n, uint32
             }
         }
         }   // triangle rounds
-        }
     }
 }
 
