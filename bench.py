@@ -348,11 +348,21 @@ def main():
         ext_rays = stage["rays_extension"]
         ext_s = stage["extend_ms"] * 1e-3
         achieved = bytes_per_ray * ext_rays / ext_s / 1e9 if ext_s > 0 else 0.0
-        traffic = None
+        traffic, issue = None, None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get("k_extend_dram_bytes_per_launch")
+                tj = json.load(open(tp))
+                traffic = tj.get("k_extend_dram_bytes_per_launch")
+                # the roof this kernel actually runs against ("secondary roof = SM issue slots"): warp instructions per
+                # launch from the committed ncu capture of this same workload / the launch time measured live / (SMs x 4 schedulers x clock)
+                wi = tj.get("k_extend_warp_instructions_per_launch")
+                if wi and ext_s > 0 and stage["extend_launches"]:
+                    sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
+                    n_sm = torch.cuda.get_device_properties(local).multi_processor_count
+                    ach = wi * stage["extend_launches"] / ext_s
+                    issue = {"achieved": ach, "peak": n_sm * 4 * sm_hz, "unit": "warp-inst/s", "frac": ach / (n_sm * 4 * sm_hz),
+                             "warp_instructions_per_launch": wi, "source": "profiles/traffic.json (ncu smsp__inst_executed.sum) / live CUDA-event launch time; peak = %d SMs x 4 schedulers x %.0f MHz" % (n_sm, sm_hz / 1e6)}
             except Exception:
                 traffic = None
         out = {
@@ -370,12 +380,12 @@ def main():
             "e2e": {"value": total / dt_e2e, "unit": "pixel-samples/s", "h2d_bytes_per_step": 56, "d2h_bytes_per_step": W * H * 16},
             "gpu_launches": int(st["kernel_launches"] - launches0),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "kernel": "k_extend (closest hit over BVH8)", "peak_source": peak_src,
+                         "kernel": "k_extend (closest hit over BVH8)", "peak_source": peak_src, "issue": issue,
                          "bytes_per_ray": bytes_per_ray, "nodes_per_ray": nodes_per_ray, "tris_per_ray": tris_per_ray, "exact_key_evals_per_ray": keys_per_ray,
                          "launch_ms": stage["extend_ms"] / max(1, stage["extend_launches"]), "launches": int(stage["extend_launches"]),
                          "share_of_step": stage["extend_ms"] / stage["render_ms"] if stage["render_ms"] else None,
                          "stage_ms": {k: stage[k] for k in ("extend_ms", "shade_ms", "connect_ms", "other_ms", "render_ms")},
-                         "note": "BVH8 + triangles of this scene (~8 MB) are L2-resident: the HBM roof is a loose upper bound for this kernel; issue-slot and latency numbers are in profiles/"},
+                         "note": "BVH8 + triangles of this scene (~8 MB) are L2-resident: the HBM roof is a loose upper bound for this kernel, which is bound by instruction issue (see 'issue'); per-phase instruction shares and stall numbers are in profiles/"},
             "setup": {"scene_upload_s": setup_s, "bvh_build_ms": st["bvh_build_ms"], "bvh_nodes": st["bvh_nodes"], "key_slack": st["key_slack"]},
             "clocks": clocks,
         }

@@ -61,7 +61,11 @@ __device__ __forceinline__ void misCombine(const WaveState& W, uint32_t pid, boo
         if (!lightOccluded) CP = f3(lc.x, lc.y, lc.z);
     }
     const float sum = pE + pP + pB;
-    const float w1 = pE / sum, w2 = pP / sum, w3 = pB / sum;
+    // 0 / sum is +0 for any sum > 0: spelled out because the IEEE division takes its out-of-line slow path for a zero
+    // numerator (ncu source page, k_shadowEnv: 8-9 % of the warp instructions in that subroutine at 2 active threads: p_p is 0
+    // in every scene without point lights, p_e whenever the shadow ray is occluded).  Same bits as the division.
+    const bool pos = sum > 0.f;
+    const float w1 = (pos && pE == 0.f) ? 0.f : pE / sum, w2 = (pos && pP == 0.f) ? 0.f : pP / sum, w3 = (pos && pB == 0.f) ? 0.f : pB / sum;
     const float4 thr4 = W.tr[2 * (size_t)pid];
     const F3 thr = f3(thr4.x, thr4.y, thr4.z);
     const F3 mix = f3(w1 * CE.x + w2 * CP.x + w3 * bc.x, w1 * CE.y + w2 * CP.y + w3 * bc.y, w1 * CE.z + w2 * CP.z + w3 * bc.z);
