@@ -5,7 +5,7 @@
  * (524 287 x 44-byte nodes whatever the scene, 57 % empty leaves at ClockCC0 scale) built by a
  * recursive single-threaded CPU builder (S/BVH.hpp:187-330, divideSAH :373-460; S/ = reference
  * src/tfg-pathtracer).  Here: top-down binned-SAH binary build (16 bins, in-place partition, task-parallel),
- * greedy surface-area collapse to 8-wide nodes, octant-ordered child slots, quantised child boxes
+ * SAH-optimal collapse to 8-wide nodes, octant-ordered child slots, quantised child boxes
  * (layout after Ylitie, Karras, Laine: "Efficient Incoherent Ray Traversal on GPUs Through Compressed Wide
  * BVHs", HPG 2017).  Triangles are re-laid out in leaf order as 48-byte records for 128-bit loads.
  */
@@ -16,7 +16,7 @@
 #include <vector>
 #include "../../include/eleven_b200.h"
 
-/* Leaf policy of both builders (binary binned-SAH stage): a node of <= EL_MAX_LEAF (<= 3) triangles stays a leaf unless
+/* Leaf policy of both builders (binary binned-SAH stage): a node of <= EL_MAX_LEAF (2; the node layout allows up to 3) triangles stays a leaf unless
  * splitting it is cheaper by SAH, with a triangle test costing 1 and the split EL_LEAF_COST_NODE. */
 #ifndef EL_MAX_LEAF
 #define EL_MAX_LEAF 2

@@ -2,7 +2,7 @@
  * bvh8_build.cpp — host builder for the compressed 8-wide BVH (see bvh8.h).
  *
  * Replaces S/BVH.hpp:187-330 + divideSAH :373-460 (recursive, single-threaded, fixed depth 18, std::vector copies
- * of 156-byte structs at every level).  Differences by design: adaptive depth, SAH leaf termination (<= 3
+ * of 156-byte structs at every level).  Differences by design: adaptive depth, SAH leaf termination (<= EL_MAX_LEAF = 2
  * triangles), in-place index partition, O(bins) sweep, task-parallel subtrees, wide collapse, quantisation.
  */
 #include "bvh8.h"
@@ -277,7 +277,7 @@ void buildBvh8(const ElevenTri* tris, uint32_t n, const int32_t* triMaterial, Bv
                 qlo[a][s] = (uint8_t)lo; qhi[a][s] = (uint8_t)hi;
             }
             if (isLeaf2(c)) {
-                uint32_t cnt = (uint32_t)c.count;               // <= 3
+                uint32_t cnt = (uint32_t)c.count;               // <= EL_MAX_LEAF (the layout allows 3)
                 N.triMask |= ((1u << cnt) - 1u) << (3 * s);
                 for (uint32_t k = 0; k < cnt; k++) {
                     int t = B.idx[c.first + k];

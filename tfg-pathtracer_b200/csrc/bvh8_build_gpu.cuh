@@ -3,7 +3,7 @@
  *
  * Replaces S/BVH.hpp:187-330 + divideSAH :373-460 (recursive, single-threaded host build: 1.4 s for ClockCC0, >60 s
  * estimated for 10 M triangles) and complements our own host builder (bvh8_build.cpp).  Same algorithm family as the
- * host builder — top-down binned SAH (16 bins x 3 axes), SAH-terminated leaves of <= 3 triangles, collapse to
+ * host builder — top-down binned SAH (16 bins x 3 axes), SAH-terminated leaves of <= EL_MAX_LEAF (2) triangles, collapse to
  * 8-wide nodes (SAH-optimal cut by dynamic programming), octant-ordered slots, outward-rounded 8-bit quantisation — restructured
  * for the device:
  *

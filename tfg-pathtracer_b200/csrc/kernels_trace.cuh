@@ -46,6 +46,17 @@ __global__ void __launch_bounds__(128, EL_EXTEND_MIN_CTAS) k_extend(const __grid
     if (COUNT) { atomicAdd(&W.stats[ST_NODES], (unsigned long long)tc.nodes); atomicAdd(&W.stats[ST_TRIS], (unsigned long long)tc.tris); atomicAdd(&W.stats[ST_KEYS], (unsigned long long)tc.keys); }
 }
 
+// p / sum with the bits of the IEEE division.  0 / sum is +0 for any sum > 0, and that case is branched around: the division
+// takes its out-of-line slow path for a zero numerator (ncu source page of k_shadowEnv: 8-9 % of the kernel's warp instructions
+// in that subroutine at 2 active threads - p_p is 0 in every scene without point lights, p_e whenever the shadow ray is
+// occluded).  `asm volatile` because the compiler otherwise computes the quotient speculatively and selects afterwards.
+__device__ __forceinline__ float misWeight(float p, float sum) {
+    float r;
+    if (p == 0.f && sum > 0.f) r = 0.f;
+    else asm volatile("div.rn.f32 %0, %1, %2;" : "=f"(r) : "f"(p), "f"(sum));
+    return r;
+}
+
 // ---- MIS combination (shade, S/kernel.cu:351-357) --------------------------------------------------------------------------
 // hdriPdf is DEFINED as 0 when the environment shadow ray is occluded (the reference leaves it uninitialised).
 __device__ __forceinline__ void misCombine(const WaveState& W, uint32_t pid, bool lights, bool envOccluded, bool lightOccluded) {
@@ -61,11 +72,7 @@ __device__ __forceinline__ void misCombine(const WaveState& W, uint32_t pid, boo
         if (!lightOccluded) CP = f3(lc.x, lc.y, lc.z);
     }
     const float sum = pE + pP + pB;
-    // 0 / sum is +0 for any sum > 0: spelled out because the IEEE division takes its out-of-line slow path for a zero
-    // numerator (ncu source page, k_shadowEnv: 8-9 % of the warp instructions in that subroutine at 2 active threads: p_p is 0
-    // in every scene without point lights, p_e whenever the shadow ray is occluded).  Same bits as the division.
-    const bool pos = sum > 0.f;
-    const float w1 = (pos && pE == 0.f) ? 0.f : pE / sum, w2 = (pos && pP == 0.f) ? 0.f : pP / sum, w3 = (pos && pB == 0.f) ? 0.f : pB / sum;
+    const float w1 = misWeight(pE, sum), w2 = misWeight(pP, sum), w3 = misWeight(pB, sum);
     const float4 thr4 = W.tr[2 * (size_t)pid];
     const F3 thr = f3(thr4.x, thr4.y, thr4.z);
     const F3 mix = f3(w1 * CE.x + w2 * CP.x + w3 * bc.x, w1 * CE.y + w2 * CP.y + w3 * bc.y, w1 * CE.z + w2 * CP.z + w3 * bc.z);

@@ -51,7 +51,9 @@ __device__ __forceinline__ float byteMagic15(uint32_t q4, uint32_t magic, uint32
 __device__ __forceinline__ float byteI2F(uint32_t q4, int j) { return (float)((q4 >> (8 * j)) & 0xffu); }   // I2F.U8 on the conversion pipe
 
 #ifndef EL_SAT
-#define EL_SAT 0               /* near planes through FFMA.SAT on a per-ray power-of-two time scale (see traceQueue) */
+#define EL_SAT 0               /* 1: near planes through FFMA.SAT on a per-ray power-of-two time scale (see traceQueue).  Exact, 8 FMNMX fewer per
+                                * node, but measured SLOWER (k_extend 18.04 vs 17.84 ms, shadow kernels 72 instead of 64 registers: 7.30 vs 6.88 ms,
+                                * profiles/r1_variants_session3.json): the ray set-up and the scale register cost more than the clamps save */
 #endif
 // a * b + c clamped to [0, 1] in the FMA pipe (FFMA.SAT): the `max(tmin, 0)` of the slab test for free
 __device__ __forceinline__ float fmaSat(float a, float b, float c) {

@@ -29,5 +29,5 @@ timeout 900 compute-sanitizer --tool memcheck python tools/sanitize_run.py > $ou
 fi
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/launches.csv python tools/profile_run.py --spp 16 > $out/launches.log 2>&1; echo "ncu list rc=$?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_extend|k_shadowEnv" -c 6 -o $out/wave16 -f python tools/profile_run.py --spp 16 > $out/ncu_full.log 2>&1; echo "ncu full rc=$?"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_shade<" -c 2 -o $out/shade2 -f python tools/profile_run.py --spp 16 > $out/ncu_shade.log 2>&1; echo "ncu shade rc=$?"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"^k_shade$" -c 2 -o $out/shade2 -f python tools/profile_run.py --spp 16 > $out/ncu_shade.log 2>&1; echo "ncu shade rc=$?"
 ls -la $out
