@@ -76,6 +76,11 @@ def test_bvh8_of_both_builders_is_valid_and_device_build_is_hit_exact(scenes, na
     for a, b in zip(dev.bvh(), dev2.bvh()):
         assert a.tobytes() == b.tobytes(), "device build must be deterministic"
     assert abs(dev.stats()["key_slack"] - host.stats()["key_slack"]) <= 1e-6 * host.stats()["key_slack"]
+    # the tree the CPU suite checks (eleven_bvh_build_host + tests/bvh8_walk.py) IS the tree the kernels walk
+    from tfg_pathtracer_b200 import _capi
+    hn, hs, hk, _ = _capi.bvh_build_host(sc.tris, np.asarray(sc.object_material, np.int32)[sc.tris["objectID"]])
+    for a, b in zip(host.bvh(), (hn, hs, hk)):
+        assert a.tobytes() == b.tobytes(), "host-only builder hook and the uploaded host-built tree differ"
     orc = O.Oracle(sc)
     rays = np.concatenate([MG.ray_batch(sc, 4096, 4096, 2048, seed=5), MG.ray_batch(sc)])
     ref, brute = orc.trace(rays, mode=0), orc.trace(rays, mode=1)
