@@ -27,21 +27,23 @@ def test_mask_tables():
     assert EXPAND[0] == 0 and EXPAND[255] == 0xffffff and EXPAND[0b101] == 0b111000111
 
 
-@pytest.mark.parametrize("scene", ["cornell", "cornell_axis", "grid"])
+@pytest.mark.parametrize("scene", ["cornell", "cornell_axis", "grid", "clock"])
 def test_host_tree_valid_and_walk_matches_brute_force(scene):
     if scene == "cornell":
         sc = S.cornell_box(64, env_size=(66, 33), tilt=(3.0, 7.0, 2.0), box_gap=0.002)
     elif scene == "cornell_axis":
         sc = S.cornell_box(64, env_size=(66, 33))                      # axis-aligned: flat boxes, rays inside box faces
-    else:
+    elif scene == "grid":
         sc = S.displaced_grid(n=48, xres=64, yres=36, env_size=(64, 32))
+    else:
+        sc = S.clock_standin(tex_res=16, xres=64, yres=36, env_size=(64, 32))   # the bench geometry: 125 281 triangles, 13 929 wide nodes
     nodes, slots, slack, key_slack = _capi.bvh_build_host(sc.tris)
     cost, depth, n8 = validate_bvh8(nodes, slots, slack, sc.tris)
     assert n8 == len(nodes) and depth >= 1 and key_slack >= 0
     # same tree from a second build with another thread count (deterministic emission)
     n2, s2, _, _ = _capi.bvh_build_host(sc.tris, threads=1)
     assert n2.tobytes() == nodes.tobytes() and s2.tobytes() == slots.tobytes()
-    rays = MG.ray_batch(sc, 96, 96, 64, seed=5)
+    rays = MG.ray_batch(sc, 96, 96, 64, seed=5) if scene != "clock" else MG.ray_batch(sc, 64, 64, 32, seed=5)
     o, d = _norm_rays(rays)
     visited = [0]
     hits = 0
