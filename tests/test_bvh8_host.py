@@ -58,3 +58,20 @@ def test_host_tree_valid_and_walk_matches_brute_force(scene):
             assert (np.array(w[1:], np.float32).view(np.uint32) == np.array(b[1:], np.float32).view(np.uint32)).all()
     assert hits > len(rays) // 4
     assert visited[0] / len(rays) < 60        # the walk culls (a full sweep would visit every node for every ray)
+
+
+def test_host_builder_hook_edge_cases_and_errors():
+    sc = S.cornell_box(64, env_size=(66, 33))
+    nodes, slots, slack, ks = _capi.bvh_build_host(sc.tris[:0])                 # empty scene: one empty root, no slots
+    assert len(nodes) == 1 and len(slots) == 0 and nodes["imask"][0] == 0 and nodes["triMask"][0] == 0
+    nodes, slots, slack, ks = _capi.bvh_build_host(sc.tris[:1])                 # one triangle: a root with one leaf child
+    assert len(nodes) == 1 and len(slots) == 1 and nodes["triMask"][0] == 1 and nodes["imask"][0] == 0
+    validate_bvh8(nodes, slots, slack, sc.tris[:1])
+    L = _capi.load_library()
+    counts = np.zeros(2, np.uint32)
+    small = np.zeros(1, _capi.NODE8_DT)
+    t = np.ascontiguousarray(sc.tris)
+    rc = L.eleven_bvh_build_host(t.ctypes.data, len(t), None, 1, small.ctypes.data, 1, None, 0, None, counts.ctypes.data, None)
+    assert rc == -1 and b"too small" in L.eleven_last_error() and counts[0] > 1 and counts[1] == len(t)   # sizes come back with the error
+    assert L.eleven_bvh_build_host(None, 5, None, 1, None, 0, None, 0, None, counts.ctypes.data, None) == -1
+    assert b"null" in L.eleven_last_error()
