@@ -1,6 +1,6 @@
 """Image-level pin against the UNMODIFIED reference renderer run on a B200.
 
-tests/golden/ref_cuda_<scene>.npz were produced on the GPU box by tools/ref_compare.py --save, which runs
+tests/golden/ref_cuda_<scene>.npz were produced on the GPU box by tests/ref_compare.py --save, which runs
 oracle/_ref/eleven_ref_headless_precise (the reference's own loader + BVH builder + kernel.cu, nvcc --fmad=false) on a
 scene directory written by scenes.write_reference_scene_dir, and stores (a) the raw float BEAUTY film it rendered and (b)
 the scene exactly as the reference's loader produced it (flat dump: MikkTSpace tangents, stb texel decode).
