@@ -57,7 +57,8 @@ def test_cli_renders_bmp_like_the_library(tmp_path):
     flat = str(tmp_path / "c.flat")
     S.save_flat(c, flat)
     bmp, raw = str(tmp_path / "o.bmp"), str(tmp_path / "o.f32")
-    r = subprocess.run([EXE, flat, "6", bmp, "--mode", "parity", "--raw", raw], capture_output=True, text=True)
+    prev, aov = str(tmp_path / "preview.bmp"), str(tmp_path / "aov")
+    r = subprocess.run([EXE, flat, "6", bmp, "--mode", "parity", "--raw", raw, "--slice", "2", "--preview", prev, "--aov", aov], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr + r.stdout
     assert "Saved!" in r.stdout and "kPaths/s" in r.stdout
     lib = R.Renderer(**R.PARITY).render_setup(c)
@@ -66,6 +67,11 @@ def test_cli_renders_bmp_like_the_library(tmp_path):
     assert (film.view(np.uint32) == lib.film().view(np.uint32)).all()
     img = S.read_bmp(bmp)[::-1]                      # read_bmp returns bottom-up rows; film row 0 is the top row
     assert (img == lib.resolve_rgba8()[..., :3]).all()
+    # the last progressive snapshot (after the last 2-sample slice) is the final picture; the AOV files are the first-hit passes
+    assert (S.read_bmp(prev) == S.read_bmp(bmp)).all()
+    for name, p in (("normal", R.PASS_NORMAL), ("tangent", R.PASS_TANGENT), ("bitangent", R.PASS_BITANGENT)):
+        a = np.fromfile("%s_%s.f32" % (aov, name), np.float32).reshape(96, 96, 4)
+        assert (a.view(np.uint32) == lib.film(p).view(np.uint32)).all(), name
     # two "GPUs" worth of sample split on one device id is not possible from the CLI; check the fast mode runs
     r = subprocess.run([EXE, flat, "8", bmp], capture_output=True, text=True)
     assert r.returncode == 0 and "pixel-samples/s" in r.stdout

@@ -4,7 +4,10 @@
  * SURVEY §2).  Output is a 24-bit BMP written with the reference's save curve fastPow(clamp01(x), 1/2.2)*255
  * (S/main.cpp:156-158; the reference actually writes PNG bytes whatever the extension).
  *
- *   eleven <scene_dir | scene.flat> <#samples> <output.bmp> [--mode fast|parity] [--gpus N] [--slice K] [--raw file.f32]
+ *   eleven <scene_dir | scene.flat> <#samples> <output.bmp> [--mode fast|parity] [--gpus N] [--slice K] [--bvh device|host]
+ *          [--raw file.f32]        linear float RGBA film
+ *          [--preview file.bmp]    8-bit snapshot after every slice (what the reference shows in its preview window)
+ *          [--aov prefix]          prefix_{normal,tangent,bitangent}.f32: first-hit passes, RGBA float (the denoiser hand-off of S/main.cpp:72-74)
  *   eleven --dump-flat <scene_dir> <out.flat>          (loader only, needs no GPU)
  */
 #include <chrono>
@@ -30,6 +33,9 @@ static double fastPowHost(double a, double b) {           // S/stb_image.h:127-1
 
 struct DeviceJob {
     int device = 0, spp = 0; ElevenConfig cfg; ElevenSceneDesc* desc = nullptr;
+    const char* previewPath = nullptr;        // device 0 only: 8-bit snapshot of the film after every slice (the reference's preview window, S/main.cpp:132-184 + Window.hpp)
+    std::vector<float> aov[3];                // NORMAL, TANGENT, BITANGENT first-hit means, RGBA float = OIDN's float3 with a 16-byte stride (S/main.cpp:72-74)
+    bool wantAov = false;
     std::vector<float> film; std::vector<uint32_t> counts; ElevenStats stats; std::string err; int rc = 0;
     ElevenCtx* ctx = nullptr;
 };
@@ -42,6 +48,14 @@ static void runDevice(DeviceJob* j, int slice, bool report) {
         const int k = std::min(slice, j->spp - done);
         if ((j->rc = eleven_render(j->ctx, k))) { j->err = eleven_last_error(); return; }
         done += k;
+        if (j->previewPath) {                                 // progressive preview: resolve on the device, 8-bit BMP on disk (atomic rename)
+            const size_t np_ = (size_t)j->desc->camera.xRes * j->desc->camera.yRes;
+            std::vector<unsigned char> px(np_ * 4);
+            std::string perr, tmp = std::string(j->previewPath) + ".tmp";
+            if (!eleven_resolve_rgba8(j->ctx, ELEVEN_PASS_BEAUTY, px.data(), np_) &&
+                writeBmp24(tmp, (int)j->desc->camera.xRes, (int)j->desc->camera.yRes, px.data(), perr))
+                rename(tmp.c_str(), j->previewPath);
+        }
         if (report) {                                         // the reference's status line (S/main.cpp:172-179)
             ElevenStats st; eleven_get_stats(j->ctx, &st);
             const double ms = (nowS() - t0) * 1e3;
@@ -54,6 +68,13 @@ static void runDevice(DeviceJob* j, int slice, bool report) {
     j->film.resize(n * 4); j->counts.resize(n);
     if ((j->rc = eleven_get_film(j->ctx, ELEVEN_PASS_BEAUTY, j->film.data(), n))) { j->err = eleven_last_error(); return; }
     if ((j->rc = eleven_get_sample_counts(j->ctx, j->counts.data(), n))) { j->err = eleven_last_error(); return; }
+    if (j->wantAov) {
+        const int passes[3] = {ELEVEN_PASS_NORMAL, ELEVEN_PASS_TANGENT, ELEVEN_PASS_BITANGENT};
+        for (int k = 0; k < 3; k++) {
+            j->aov[k].resize(n * 4);
+            if ((j->rc = eleven_get_film(j->ctx, passes[k], j->aov[k].data(), n))) { j->err = eleven_last_error(); return; }
+        }
+    }
     eleven_get_stats(j->ctx, &j->stats);
 }
 
@@ -66,16 +87,18 @@ int main(int argc, char** argv) {
                s.materials.size(), s.textures.size(), s.lights.size(), argv[3]);
         return 0;
     }
-    if (argc < 4) { fprintf(stderr, "usage: eleven <scene_path> <#samples> <output.bmp> [--mode fast|parity] [--gpus N] [--slice K] [--bvh device|host] [--raw file.f32]\n"); return 2; }
+    if (argc < 4) { fprintf(stderr, "usage: eleven <scene_path> <#samples> <output.bmp> [--mode fast|parity] [--gpus N] [--slice K] [--bvh device|host] [--raw file.f32] [--preview file.bmp] [--aov prefix]\n"); return 2; }
     const std::string scenePath = argv[1], outPath = argv[3];
     const int spp = atoi(argv[2]);
-    bool fast = true, deviceBvh = true; int gpus = 1, slice = 16; const char* rawPath = nullptr;
+    bool fast = true, deviceBvh = true; int gpus = 1, slice = 16; const char* rawPath = nullptr; const char* previewPath = nullptr; const char* aovPrefix = nullptr;
     for (int i = 4; i < argc; i++) {
         if (!strcmp(argv[i], "--mode") && i + 1 < argc) fast = strcmp(argv[++i], "parity") != 0;
         else if (!strcmp(argv[i], "--gpus") && i + 1 < argc) gpus = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--slice") && i + 1 < argc) slice = std::max(1, atoi(argv[++i]));
         else if (!strcmp(argv[i], "--raw") && i + 1 < argc) rawPath = argv[++i];
         else if (!strcmp(argv[i], "--bvh") && i + 1 < argc) deviceBvh = strcmp(argv[++i], "host") != 0;
+        else if (!strcmp(argv[i], "--preview") && i + 1 < argc) previewPath = argv[++i];
+        else if (!strcmp(argv[i], "--aov") && i + 1 < argc) aovPrefix = argv[++i];
         else { fprintf(stderr, "eleven: unknown option %s\n", argv[i]); return 2; }
     }
     if (spp <= 0 || gpus < 1) { fprintf(stderr, "eleven: bad sample or GPU count\n"); return 2; }
@@ -99,6 +122,7 @@ int main(int argc, char** argv) {
         j.cfg.sample_offset = (uint32_t)g; j.cfg.sample_stride = (uint32_t)gpus;
         j.cfg.bvh_builder = deviceBvh ? ELEVEN_BVH_DEVICE : ELEVEN_BVH_HOST;
         j.spp = spp / gpus + (g < spp % gpus ? 1 : 0);          // global sample s goes to device s % gpus
+        if (g == 0) { j.previewPath = previewPath; j.wantAov = aovPrefix != nullptr; }   // device 0's share of the samples is an unbiased picture of its own
     }
     t0 = nowS();
     std::vector<std::thread> th;
@@ -128,6 +152,15 @@ int main(int argc, char** argv) {
     printf("Saving file %s...\n", outPath.c_str());
     if (!writeBmp24(outPath, (int)desc.camera.xRes, (int)desc.camera.yRes, rgba.data(), err)) { fprintf(stderr, "eleven: %s\n", err.c_str()); return 1; }
     if (rawPath) { FILE* f = fopen(rawPath, "wb"); if (f) { fwrite(mean.data(), 4, mean.size(), f); fclose(f); } }
+    if (aovPrefix) {                                             // denoiser hand-off: first-hit NORMAL / TANGENT / BITANGENT means of device 0
+        const char* names[3] = {"normal", "tangent", "bitangent"};
+        for (int k = 0; k < 3; k++) {
+            const std::string path = std::string(aovPrefix) + "_" + names[k] + ".f32";
+            FILE* f = fopen(path.c_str(), "wb");
+            if (!f) { fprintf(stderr, "eleven: cannot write %s\n", path.c_str()); return 1; }
+            fwrite(jobs[0].aov[k].data(), 4, jobs[0].aov[k].size(), f); fclose(f);
+        }
+    }
     printf("Saved!\n");
     double renderMs = 0; uint64_t rays = 0, samples = 0;
     for (auto& j : jobs) { renderMs = std::max(renderMs, j.stats.render_ms); rays += j.stats.rays_extension + j.stats.rays_shadow_env + j.stats.rays_shadow_light; samples += j.stats.pixel_samples; }
