@@ -96,7 +96,8 @@ class ClockSampler:
 def get_scene(args, need_dir):
     """ClockCC0 stand-in, generated once per box and cached (flat container for us/oracle, scene dir for the reference)."""
     from tfg_pathtracer_b200 import scenes as S
-    tag = "clock_t%d_%dx%d" % (args.tex, args.width, args.height)
+    workload = getattr(args, "workload", "clock")
+    tag = "clock_t%d_%dx%d" % (args.tex, args.width, args.height) if workload == "clock" else "grid_n%d_%dx%d" % (args.grid, args.width, args.height)
     flat = os.path.join(CACHE, tag + ".flat")
     sdir = os.path.join(CACHE, tag + "_dir")
     os.makedirs(CACHE, exist_ok=True)
@@ -114,7 +115,8 @@ def get_scene(args, need_dir):
     try:
         sc = None
         if not os.path.exists(flat + ".done"):
-            sc = S.clock_standin(tex_res=args.tex, xres=args.width, yres=args.height)
+            sc = S.clock_standin(tex_res=args.tex, xres=args.width, yres=args.height) if workload == "clock" else \
+                S.displaced_grid(args.grid, xres=args.width, yres=args.height)
             S.save_flat(sc, flat)
             open(flat + ".done", "w").close()
         if need_dir and not os.path.exists(sdir + ".done"):
@@ -164,6 +166,78 @@ def run_reference(args, rank, out):
 
 
 # ------------------------------------------------------------------------------------------------------
+NCU_METRICS = ("smsp__inst_executed.sum", "smsp__thread_inst_executed.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+               "lts__t_sectors_op_read.sum", "lts__t_sectors_op_write.sum")
+
+
+def ncu_counters(args, git_sha):
+    """Hardware counters of ONE wave of this very workload, taken in THIS run (untimed, before the timed region): an ncu
+    subprocess replays the traversal/shade kernels of one `--spp-per-step` wave (tools/profile_run.py loads the same cached
+    scene, same mode, same seed: the counter-based RNG makes it the same rays as a bench step).  Returns per-kernel sums
+    {kernel: {launches, warp_inst, thread_inst, dram_bytes, l2_bytes}} or None (+ reason) when ncu is unavailable."""
+    import csv
+    import shutil
+    import tempfile
+    ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
+    if not os.path.exists(ncu):
+        return None, "ncu not found"
+    log = tempfile.mktemp(prefix="eleven_ncu_", suffix=".csv")
+    cmd = [ncu, "--metrics", ",".join(NCU_METRICS), "--clock-control", "none", "--csv", "--log-file", log,
+           "-k", "regex:k_extend|k_shade|k_shadowEnv|k_shadowLight|k_classify",
+           sys.executable, os.path.join(ROOT, "tools", "profile_run.py"), "--spp", str(args.spp_per_step), "--tex", str(args.tex),
+           "--width", str(args.width), "--height", str(args.height), "--mode", args.mode, "--hit-mode", args.hit_mode,
+           "--workload", args.workload, "--grid", str(args.grid), "--wave-spp", str(args.wave_spp)]
+    try:
+        p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    except Exception as e:       # noqa: BLE001
+        return None, "ncu failed to run: %r" % (e,)
+    if p.returncode != 0 or not os.path.exists(log):
+        return None, "ncu rc=%d: %s" % (p.returncode, (p.stderr or p.stdout)[-300:].replace("\n", " "))
+    agg = {}
+    try:
+        rows = list(csv.reader(open(log)))
+        hdr = next(r for r in rows if "Kernel Name" in r and "Metric Name" in r)
+        ik, im, iv, ii = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("ID")
+        seen = {}
+        for r in rows[rows.index(hdr) + 1:]:
+            if len(r) <= max(ik, im, iv):
+                continue
+            name = r[ik].split("(")[0].replace("eleven::", "").replace("void ", "").split("<")[0].strip()
+            a = agg.setdefault(name, {"launches": 0, "warp_inst": 0.0, "thread_inst": 0.0, "dram_bytes": 0.0, "l2_bytes": 0.0})
+            if (name, r[ii]) not in seen:
+                seen[(name, r[ii])] = 1
+                a["launches"] += 1
+            v = float(r[iv].replace(",", ""))
+            m = r[im]
+            if m == "smsp__inst_executed.sum":
+                a["warp_inst"] += v
+            elif m == "smsp__thread_inst_executed.sum":
+                a["thread_inst"] += v
+            elif m.startswith("dram__bytes"):
+                a["dram_bytes"] += v
+            elif m.startswith("lts__t_sectors"):
+                a["l2_bytes"] += 32.0 * v
+    except Exception as e:       # noqa: BLE001
+        return None, "cannot parse the ncu log: %r" % (e,)
+    finally:
+        try:
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+            shutil.copy(log, os.path.join(ROOT, "gpurun_out", "bench_ncu_counters_%s.csv" % args.workload))
+            os.remove(log)
+        except Exception:        # noqa: BLE001
+            pass
+    if "k_extend" not in agg:
+        return None, "no k_extend launch in the ncu log"
+    return agg, "ncu subprocess of this run (git %s): %s over one %d-spp wave" % (git_sha, ", ".join(NCU_METRICS[:2]), args.spp_per_step)
+
+
+def git_head():
+    try:
+        return subprocess.run(["git", "-C", ROOT, "rev-parse", "--short=12", "HEAD"], capture_output=True, text=True, timeout=10).stdout.strip() or "unknown"
+    except Exception:            # noqa: BLE001
+        return "unknown"
+
+
 def cpu_baseline(args, flat):
     import oracle_lib as O
     from tfg_pathtracer_b200 import scenes as S
@@ -204,6 +278,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mode", default="fast", choices=["fast", "parity"])
     ap.add_argument("--hit-mode", default="key", choices=["key", "min_t"], help="closest-hit ordering: the reference key (default) or classic min t")
+    ap.add_argument("--workload", default="clock", choices=["clock", "grid"],
+                    help="clock: ClockCC0 stand-in (BASELINE configs[2], the metric's configuration); grid: configs[3], the ~10 M-triangle displaced grid "
+                         "(BVH8 + triangles ~560 MB >> L2: the workload whose traversal roof is HBM)")
+    ap.add_argument("--grid", type=int, default=2237, help="grid workload: n x n vertices -> 2(n-1)^2 triangles (2237 -> 9 999 392)")
+    ap.add_argument("--no-ncu", action="store_true", help="skip the live ncu counter pass (roofline.issue / traffic fall back to profiles/traffic.json, flagged)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -242,26 +321,20 @@ def main():
         mode["bvh_builder"] = R.BVH_DEVICE if args.bvh == "device" else R.BVH_HOST
     r = R.Renderer(device=local, sample_offset=off, sample_stride=stride, **mode).render_setup(sc)
     setup_s = time.time() - t0
-    film, counts = D.film_tensors(r, "cuda:%d" % local)
+    if world > 1:
+        D.init_comm(r, rank, world)             # native NCCL communicator of the context; torch.distributed only carries the 128-byte id
     S_ = args.spp_per_step
-
-    red_events = []
 
     def step():
         r.render_cuda(S_)                       # blocking; its device time is measured by CUDA events on the context's stream (ElevenStats.render_ms)
-        if world > 1:                           # the one exchange step, timed by CUDA events on torch's stream (where NCCL is enqueued)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            D.reduce_film(film, counts, 0)
-            e1.record()
-            red_events.append((e0, e1))
+        if world > 1:                           # the one exchange step: ONE ncclReduce of the film records (sum.xyz, count) to rank 0, enqueued by the
+            r.reduce_film(0)                    # library on the same stream, into a buffer separate from the local film; timed by its own CUDA events
 
-    def device_ms(render_ms0):
-        """Device time of the steps since `render_ms0`: render (context-stream events) + reduce (torch-stream events)."""
+    def device_ms(st0):
+        """Device time of the steps since the stats snapshot `st0`: render + reduce, CUDA events on the context's stream."""
         torch.cuda.synchronize()
-        ms = r.stats()["render_ms"] - render_ms0 + sum(a.elapsed_time(b) for a, b in red_events)
-        red_events.clear()
-        return ms
+        st = r.stats()
+        return st["render_ms"] - st0["render_ms"] + st["reduce_ms"] - st0["reduce_ms"]
 
     def barrier():
         torch.cuda.synchronize()
@@ -269,20 +342,23 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- per-ray algorithmic bytes from a counters build of the same kernels (untimed) ----
+    # ---- per-ray algorithmic bytes from a counters build of the same kernels on the same rays (untimed) ----
     rc_cfg = dict(mode)
     rc_cfg["flags"] = rc_cfg["flags"] | R.FLAG_COUNTERS
+    sha = git_head()
+    ncu, ncu_src = None, "skipped (--no-ncu)"
     if rank == 0:
         rc = R.Renderer(device=local, **rc_cfg).render_setup(sc)
-        rc.render_cuda(1)
-        st = rc.stats()
-        rays_all = st["rays_extension"] + st["rays_shadow_env"] + st["rays_shadow_light"]
-        nodes_per_ray = st["nodes_visited"] / max(1, rays_all)
-        tris_per_ray = st["tris_tested"] / max(1, rays_all)
-        keys_per_ray = st["key_evals"] / max(1, rays_all)
+        rc.render_cuda(S_)
+        cst = rc.stats()
         rc.close()
+        # ---- hardware counters of one wave of this workload, measured in this run (ncu subprocess; untimed) ----
+        if not args.no_ncu:
+            ncu, ncu_src = ncu_counters(args, sha)
+            if ncu is None:
+                print("bench.py: live ncu counters unavailable: %s" % ncu_src, file=sys.stderr)
     else:
-        nodes_per_ray = tris_per_ray = keys_per_ray = 0.0
+        cst = None
 
     for _ in range(args.warmup):
         r.reset()
@@ -295,14 +371,13 @@ def main():
     r.reset()
     st0 = r.stats()
     launches0 = st0["kernel_launches"]
-    red_events.clear()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step()
     barrier()
     dt_host = time.perf_counter() - t0
-    dt = device_ms(st0["render_ms"]) * 1e-3                              # CUDA events; max over ranks below
+    dt = device_ms(st0) * 1e-3                                           # CUDA events; max over ranks below
     st = r.stats()
     # ---- timed: stage breakdown for the roofline (separate pass so that the events do not perturb `value`) ------
     tk_cfg = dict(mode)
@@ -318,14 +393,16 @@ def main():
     # ---- timed: e2e ---------------------------------------------------------------------------------------
     host_film = r.pinned_array((H, W, 4), np.float32)                 # page-locked host buffer for the per-step film read-back
     r.reset()
-    red_events.clear()
     barrier()
     t1 = time.perf_counter()
     for k in range(args.steps):
         r.set_camera(sc.camera)                                     # H2D: 56 bytes
         step()
-        if rank == 0:
-            r._ck(r.L.eleven_get_film(r.h, R.PASS_BEAUTY, host_film.ctypes.data, W * H))   # resolve + D2H of the result
+        if rank == 0:                                               # resolve + D2H of the result: the film of all ranks (reduced) for N > 1
+            if world > 1:
+                r.film_reduced(R.PASS_BEAUTY, out=host_film)
+            else:
+                r._ck(r.L.eleven_get_film(r.h, R.PASS_BEAUTY, host_film.ctypes.data, W * H))
     barrier()
     dt_e2e = time.perf_counter() - t1
     clocks = sampler.stop() if rank == 0 else None
@@ -344,35 +421,72 @@ def main():
         total = float(W) * H * S_ * args.steps * world
         value = total / dt
         peak, peak_src = load_peaks()
+        # algorithmic bytes of the dominant kernel: per extension ray 80 B x nodes + 48 B x triangles + 32 B ray in + 16 B hit out,
+        # nodes / triangles counted for k_extend alone by the counters build on the same wave
+        ext_rays_c = max(1, cst["rays_extension"])
+        nodes_per_ray = cst["nodes_visited_extend"] / ext_rays_c
+        tris_per_ray = cst["tris_tested_extend"] / ext_rays_c
+        keys_per_ray = cst["key_evals"] / max(1, cst["rays_extension"] + cst["rays_shadow_env"] + cst["rays_shadow_light"])
+        sh_rays_c = max(1, cst["rays_shadow_env"] + cst["rays_shadow_light"])
+        shadow_nodes_per_ray = (cst["nodes_visited"] - cst["nodes_visited_extend"]) / sh_rays_c
+        shadow_tris_per_ray = (cst["tris_tested"] - cst["tris_tested_extend"]) / sh_rays_c
         bytes_per_ray = 80.0 * nodes_per_ray + 48.0 * tris_per_ray + 48.0
         ext_rays = stage["rays_extension"]
         ext_s = stage["extend_ms"] * 1e-3
+        n_launch = max(1, int(stage["extend_launches"]))
         achieved = bytes_per_ray * ext_rays / ext_s / 1e9 if ext_s > 0 else 0.0
-        traffic, issue = None, None
-        tp = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tp):
+        sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
+        n_sm = torch.cuda.get_device_properties(local).multi_processor_count
+        issue_peak = n_sm * 4 * sm_hz
+        traffic, issue, memory, kernels = None, None, None, None
+        if ncu is not None:
+            # everything below is per launch of k_extend, like `achieved`: the wave the ncu subprocess replayed is the wave a step renders
+            ke = ncu["k_extend"]
+            traffic = ke["dram_bytes"] / ke["launches"]
+            ach = ke["warp_inst"] / ext_s * (n_launch / ke["launches"])
+            tpi = ke["thread_inst"] / max(1.0, ke["warp_inst"])
+            issue = {"achieved": ach, "peak": issue_peak, "unit": "warp-inst/s", "frac": ach / issue_peak,
+                     "warp_instructions_per_launch": ke["warp_inst"] / ke["launches"], "warp_instructions_per_ray": ke["warp_inst"] / max(1, ext_rays) * (n_launch / ke["launches"]),
+                     "simt_threads_per_inst": tpi, "useful_lane_frac": ach / issue_peak * tpi / 32.0,
+                     "source": ncu_src + " / live CUDA-event launch time; peak = %d SMs x 4 schedulers x %.0f MHz (sampled during the timed region)" % (n_sm, sm_hz / 1e6)}
+            memory = {"dram_gbs": ke["dram_bytes"] / ext_s / 1e9 * (n_launch / ke["launches"]), "l2_gbs": ke["l2_bytes"] / ext_s / 1e9 * (n_launch / ke["launches"]),
+                      "dram_frac_of_peak": ke["dram_bytes"] / ext_s / 1e9 * (n_launch / ke["launches"]) / peak,
+                      "dram_bytes_per_ray": ke["dram_bytes"] / max(1, ext_rays) * (n_launch / ke["launches"]), "l2_bytes_per_ray": ke["l2_bytes"] / max(1, ext_rays) * (n_launch / ke["launches"]),
+                      "note": "ncu dram__bytes_{read,write}.sum and 32 B x lts__t_sectors_op_{read,write}.sum of the k_extend launches of one wave / their live CUDA-event time"}
+            kernels = {k: {"launches": v["launches"], "warp_inst": v["warp_inst"], "threads_per_inst": v["thread_inst"] / max(1.0, v["warp_inst"]),
+                           "dram_bytes": v["dram_bytes"]} for k, v in ncu.items()}
+        else:
+            tp = os.path.join(ROOT, "profiles", "traffic.json")
             try:
                 tj = json.load(open(tp))
+                stale = tj.get("git") != sha or tj.get("workload") != args.workload
                 traffic = tj.get("k_extend_dram_bytes_per_launch")
-                # the roof this kernel actually runs against ("secondary roof = SM issue slots"): warp instructions per
-                # launch from the committed ncu capture of this same workload / the launch time measured live / (SMs x 4 schedulers x clock)
                 wi = tj.get("k_extend_warp_instructions_per_launch")
-                if wi and ext_s > 0 and stage["extend_launches"]:
-                    sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
-                    n_sm = torch.cuda.get_device_properties(local).multi_processor_count
-                    ach = wi * stage["extend_launches"] / ext_s
-                    issue = {"achieved": ach, "peak": n_sm * 4 * sm_hz, "unit": "warp-inst/s", "frac": ach / (n_sm * 4 * sm_hz),
-                             "warp_instructions_per_launch": wi, "source": "profiles/traffic.json (ncu smsp__inst_executed.sum) / live CUDA-event launch time; peak = %d SMs x 4 schedulers x %.0f MHz" % (n_sm, sm_hz / 1e6)}
-            except Exception:
-                traffic = None
+                if wi and ext_s > 0:
+                    ach = wi * n_launch / ext_s
+                    issue = {"achieved": ach, "peak": issue_peak, "unit": "warp-inst/s", "frac": ach / issue_peak, "warp_instructions_per_launch": wi,
+                             "stale": bool(stale),
+                             "source": "FALLBACK (%s): committed profiles/traffic.json (captured at git %s, workload %s; this run is git %s, workload %s%s) / live launch time"
+                                       % (ncu_src, tj.get("git"), tj.get("workload"), sha, args.workload, " - STALE, do not quote" if stale else "")}
+            except Exception as e:       # noqa: BLE001
+                print("bench.py: profiles/traffic.json unusable: %r" % (e,), file=sys.stderr)
+        if args.workload == "clock":
+            wl = "ClockCC0 stand-in (125281 tris, 12x%d^2 8-bit maps, 4096x2048 HDRI, defocus) %dx%d, %d spp/step/GPU, mode=%s" % (args.tex, W, H, S_, args.mode)
+            l2 = "inputs larger than L2 (textures 805 MB + HDRI 134 MB + 12 GB wave state vs 126 MB L2); no flush needed"
+            note = ("BVH8 + triangles of this scene (~8 MB) are L2-resident: the HBM roof is a loose upper bound for this kernel, which is bound by instruction issue "
+                    "(see 'issue': warp instructions and threads/instruction measured by ncu in this run); 'memory' = the bytes it really moves")
+        else:
+            wl = "displaced grid (BASELINE configs[3]: %d triangles, sun+sky 4096x2048 HDRI) %dx%d, %d spp/step/GPU, mode=%s" % (len(sc.tris), W, H, S_, args.mode)
+            l2 = "BVH8 nodes + triangle slots + shading triangles (%.0f MB) and 12 GB of wave state vs 126 MB L2; no flush needed" % ((st["bvh_nodes"] * 80 + st["bvh_tri_slots"] * 48 + len(sc.tris) * 144) / 1e6)
+            note = "node + triangle fetches of this scene miss L2: 'memory' holds the DRAM / L2 bytes per ray and GB/s ncu measured in this run against the HBM peak"
         out = {
             "metric": "samples_per_second", "value": value, "unit": "pixel-samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dt / args.steps * 1e3, "ms_per_step_host": dt_host / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "ClockCC0 stand-in (125281 tris, 12x%d^2 8-bit maps, 4096x2048 HDRI, defocus) %dx%d, %d spp/step/GPU, mode=%s" % (args.tex, W, H, S_, args.mode),
-                       "spp_per_step": S_, "parallelism": "sample-split x%d, scene replicated, 1 NCCL reduce of film sums per step" % world,
-                       "l2": "inputs larger than L2 (textures 805 MB + HDRI 134 MB + 12 GB wave state vs 126 MB L2); no flush needed",
+            "config": {"workload": wl, "git": sha,
+                       "spp_per_step": S_, "parallelism": "sample-split x%d, scene replicated, 1 native ncclReduce of the film records (sum.xyz + count) to rank 0 per step" % world,
+                       "l2": l2,
                        "wave_spp": "auto (16 samples of every pixel in flight per wave)" if (args.wave_spp == 0 and args.mode == "fast") else (args.wave_spp if args.mode == "fast" else 1),
-                       "timing": "value: CUDA events, max over ranks (render: events on the context's stream around every eleven_render; NCCL reduce: events on torch's stream), "
+                       "timing": "value: CUDA events on the context's stream around every eleven_render and every eleven_reduce_film (ncclReduce on the same stream), max over ranks, "
                                  "bracketed by barrier + cudaDeviceSynchronize; ms_per_step_host and e2e: host clock between the same synchronisations"},
             "mrays_per_s": rays_total / dt / 1e6,
             "frame_spp_per_s": S_ * args.steps * world / dt,
@@ -380,12 +494,13 @@ def main():
             "e2e": {"value": total / dt_e2e, "unit": "pixel-samples/s", "h2d_bytes_per_step": 56, "d2h_bytes_per_step": W * H * 16},
             "gpu_launches": int(st["kernel_launches"] - launches0),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "kernel": "k_extend (closest hit over BVH8)", "peak_source": peak_src, "issue": issue,
+                         "kernel": "k_extend (closest hit over BVH8)", "peak_source": peak_src, "issue": issue, "memory": memory, "kernels": kernels,
                          "bytes_per_ray": bytes_per_ray, "nodes_per_ray": nodes_per_ray, "tris_per_ray": tris_per_ray, "exact_key_evals_per_ray": keys_per_ray,
+                         "shadow_nodes_per_ray": shadow_nodes_per_ray, "shadow_tris_per_ray": shadow_tris_per_ray,
                          "launch_ms": stage["extend_ms"] / max(1, stage["extend_launches"]), "launches": int(stage["extend_launches"]),
                          "share_of_step": stage["extend_ms"] / stage["render_ms"] if stage["render_ms"] else None,
                          "stage_ms": {k: stage[k] for k in ("extend_ms", "shade_ms", "connect_ms", "other_ms", "render_ms")},
-                         "note": "BVH8 + triangles of this scene (~8 MB) are L2-resident: the HBM roof is a loose upper bound for this kernel, which is bound by instruction issue (see 'issue'); per-phase instruction shares and stall numbers are in profiles/"},
+                         "reduce_ms_per_step": (st["reduce_ms"] - st0["reduce_ms"]) / args.steps, "note": note},
             "setup": {"scene_upload_s": setup_s, "bvh_build_ms": st["bvh_build_ms"], "bvh_nodes": st["bvh_nodes"], "key_slack": st["key_slack"]},
             "clocks": clocks,
         }

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define ELEVEN_ABI_VERSION 2
+#define ELEVEN_ABI_VERSION 3
 
 /* ---- status codes ------------------------------------------------------- */
 enum {
@@ -173,6 +173,10 @@ typedef struct ElevenStats {
     float    key_slack;          /* per-scene bound on |key - t| used for culling in HIT_KEY */
     uint32_t samples_done;       /* per-pixel sample count of pixel 0 (getSamples)           */
     uint64_t key_evals;          /* exact reference-key evaluations (only with ELEVEN_FLAG_COUNTERS) */
+    double   reduce_ms;          /* device time inside eleven_reduce_film (CUDA events on the render stream)    */
+    uint64_t reduce_calls;       /* eleven_reduce_film calls so far                                              */
+    uint64_t nodes_visited_extend; /* nodes_visited / tris_tested of the closest-hit kernel (k_extend) alone: the per-ray      */
+    uint64_t tris_tested_extend;   /* figures of the roofline's algorithmic bytes (only with ELEVEN_FLAG_COUNTERS)            */
 } ElevenStats;
 
 typedef struct ElevenCtx ElevenCtx;
@@ -195,7 +199,14 @@ int  eleven_scene_upload(ElevenCtx* ctx, const ElevenSceneDesc* scene);
 int  eleven_render(ElevenCtx* ctx, int spp);
 
 /* getBuffers (S/kernel.cu:688-710): RGBA float, index W*(H-1-y)+x, A = 1; BEAUTY is the mean of
- * per-sample radiance clamped to [0,10] (S/kernel.cu:447-463).  n_pixels must be W*H. */
+ * per-sample radiance clamped to [0,10] (S/kernel.cu:447-463).  n_pixels must be W*H.
+ * Threading (S/main.cpp:132-184: the main thread polls getBuffers/getSamples on bufferStream every 100 ms while the
+ * render thread sits in renderCuda): eleven_get_film, eleven_resolve_rgba8, eleven_get_pathcount, eleven_get_samples,
+ * eleven_get_sample_counts and eleven_get_stats run on the context's SNAPSHOT stream and may be called from another
+ * thread while eleven_render is running; they return the film as of the waves accumulated so far, without waiting for
+ * the render to end.  Every pixel is seen either before or after a wave's update (sum and sample count share one
+ * 16-byte record); different pixels may be one wave apart, as in the reference.  After eleven_render has returned the
+ * film is exact. */
 int  eleven_get_film(ElevenCtx* ctx, int pass, float* rgba, size_t n_pixels);
 int  eleven_get_pathcount(ElevenCtx* ctx, int32_t* out, size_t n_pixels);   /* dev_pathcount */
 int  eleven_get_samples(ElevenCtx* ctx);                                    /* getSamples, S/kernel.cu:712 */
@@ -232,10 +243,31 @@ int  eleven_bvh_build_host(const ElevenTri* tris, uint32_t n, const int32_t* tri
                            void* nodes, size_t node_cap, void* slots, size_t slot_cap, float* node_slack,
                            uint32_t* counts, float* key_slack);
 
-/* Multi-GPU plumbing: the film lives as per-pixel SUMS; these expose it so the
- * caller (one process per GPU) can all-reduce it with NCCL and resolve on the root. */
+/* ---- multi-GPU (the reference has none: cudaSetDevice(0), S/kernel.cu:604) -------------------------------
+ * The scene is replicated, the samples are split (ElevenConfig.sample_offset/stride), every context accumulates per-pixel
+ * SUMS whose .w carries the accepted-sample count (exact below 2^24 samples per pixel), and the one exchange step of a job is
+ * ONE ncclReduce(sum, float32) of those records to the root over NVLink, followed by the fused resolve on the root.
+ * NCCL (libnccl.so.2) is loaded on first use; without it these calls return ELEVEN_ERR_UNSUPPORTED. */
+#define ELEVEN_COMM_ID_BYTES 128
+/* ncclGetUniqueId: call on one rank, hand the 128 bytes to every rank (any transport: torch.distributed, MPI, a file). */
+int  eleven_comm_unique_id(void* id_out);
+/* One process (or thread) per GPU: ncclCommInitRank on the context's device.  Collective: every rank must call it. */
+int  eleven_comm_init_rank(ElevenCtx* ctx, const void* id, int nranks, int rank);
+/* One process driving n contexts on n different devices (the `eleven --gpus N` CLI): ncclCommInitAll; rank i = ctxs[i]. */
+int  eleven_comm_init_all(ElevenCtx** ctxs, int n);
+/* Sums the film records of all ranks into the ROOT context's reduced film (a separate buffer: local films are left as
+ * they are, so the call can be repeated as the render progresses).  all_passes = 0: BEAUTY only (W*H float4);
+ * 1: BEAUTY + NORMAL + TANGENT + BITANGENT (4*W*H float4) — either way ONE ncclReduce, enqueued on the render stream
+ * behind the waves rendered so far; blocks until it has completed.  Collective; must not overlap eleven_render on the
+ * same context.  Without a communicator (single GPU) it copies the local film into the reduced film. */
+int  eleven_reduce_film(ElevenCtx* ctx, int root, int all_passes);
+/* eleven_get_film / eleven_resolve_rgba8 / eleven_get_sample_counts on the REDUCED film (root only, after eleven_reduce_film). */
+int  eleven_get_film_reduced(ElevenCtx* ctx, int pass, float* rgba, size_t n_pixels);
+int  eleven_resolve_rgba8_reduced(ElevenCtx* ctx, int pass, uint8_t* rgba8, size_t n_pixels);
+int  eleven_get_sample_counts_reduced(ElevenCtx* ctx, uint32_t* out, size_t n_pixels);
+/* Device pointer to the local film sums of a pass (W*H float4, .w = sample count), for callers that bring their own
+ * collective.  The four passes are contiguous in pass order BEAUTY, NORMAL, TANGENT, BITANGENT. */
 int  eleven_film_sums_device(ElevenCtx* ctx, int pass, void** d_ptr, size_t* n_floats);
-int  eleven_film_counts_device(ElevenCtx* ctx, void** d_ptr, size_t* n_uints);
 /* Page-locked host memory for film read-backs / ray batches: copies to and from it run at PCIe/C2C rate instead of going
  * through the driver's staging buffer (the reference's host film buffers are pageable `new float[]`, S/main.cpp:44-49). */
 int  eleven_host_alloc(ElevenCtx* ctx, size_t bytes, void** h_ptr);
@@ -248,6 +280,23 @@ int  eleven_device_download(ElevenCtx* ctx, void* h_dst, const void* d_src, size
 /* Fused resolve: mean, alpha, optional 8-bit pack with the reference's output curve
  * fastPow(clamp01(x), 1/2.2)*255 (S/main.cpp:156-158).  rgba8 is a HOST buffer of W*H*4 bytes. */
 int  eleven_resolve_rgba8(ElevenCtx* ctx, int pass, uint8_t* rgba8, size_t n_pixels);
+
+/* ---- known-answer test hooks for the shading functions (SURVEY §8c iii-iv; the reference's own debugging pattern:
+ * printBRDFMaterial / printHDRISampling, S/kernel.cu:726-794).  Host pointers; the device functions exercised are the ones
+ * k_shade calls.  fast_math selects the arithmetic flavour (ELEVEN_FLAG_FAST_MATH). ------------------------------------- */
+/* records: n x 30 floats = HitData scalars in S/kernel.h:46-69 order (metallic, roughness, clearcoatGloss, clearcoat,
+ * anisotropic, eta, transmission, specular, specularTint, sheenTint, subsurface, sheen), emission[3], albedo[3], normal[3],
+ * ray direction[3] (normalised like Ray's ctor), L[3], r1 r2 r3.  Out: DisneyEval rgb + DisneyPdf (n x 4), DisneySample (n x 3)
+ * (S/Disney.hpp:108-253).  Needs no scene. */
+int  eleven_test_disney(ElevenCtx* ctx, const float* records, size_t n, int fast_math, float* eval_pdf, float* sample);
+/* HDRI::sample(r) -> texel (x, y), the NEE direction and HDRI::pdf (S/HDRI.hpp:130-162, S/kernel.cu:236-243) through the
+ * reference CDF search (env_mode 0) or the alias table (env_mode 1: r = the table uniform, r2 = the second uniform). */
+int  eleven_test_hdri(ElevenCtx* ctx, const float* r, const float* r2, size_t n, int env_mode, int fast_math, int32_t* xy, float* dir, float* pdf);
+/* radiance seen by an escaped ray of direction dirs[i] (S/kernel.cu:415-417). */
+int  eleven_test_env_lookup(ElevenCtx* ctx, const float* dirs, size_t n, float* rgb);
+/* generateHitData (S/kernel.cu:54-119) for given interpolated attributes: in n x 14 floats (position[3] unused, normal[3],
+ * tangent[3], bitangent[3], tu, tv) + object ids; out n x 21 floats (HitData scalars, emission, albedo, shading normal). */
+int  eleven_test_hitdata(ElevenCtx* ctx, const float* attrs, const int32_t* object_ids, size_t n, int fast_math, float* out);
 
 #ifdef __cplusplus
 }

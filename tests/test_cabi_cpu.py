@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, s), "missing export %s" % s
     assert sorted(_capi.EXPORTED_SYMBOLS) == syms
     lib.eleven_abi_version.restype = C.c_int
-    assert lib.eleven_abi_version() == 2
+    assert lib.eleven_abi_version() == 3
 
 
 def test_struct_layouts_match_header():

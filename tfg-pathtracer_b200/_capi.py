@@ -22,6 +22,7 @@ ENV_CDF, ENV_ALIAS = 0, 1
 HIT_KEY, HIT_MIN_T = 0, 1
 BVH_HOST, BVH_DEVICE = 0, 1
 FLAG_TERMINATE_DEAD_PATHS, FLAG_COUNTERS, FLAG_TIME_KERNELS, FLAG_SKIP_NULL_NEE, FLAG_FAST_MATH, FLAG_ANYHIT_LIGHT_SHADOWS = 1, 2, 4, 8, 16, 32
+COMM_ID_BYTES = 128
 
 
 class ElevenConfig(C.Structure):
@@ -71,7 +72,8 @@ class ElevenStats(C.Structure):
                 ("tris_tested", C.c_uint64), ("kernel_launches", C.c_uint64), ("render_ms", C.c_double),
                 ("trace_ms", C.c_double), ("extend_ms", C.c_double), ("shade_ms", C.c_double), ("connect_ms", C.c_double),
                 ("other_ms", C.c_double), ("extend_launches", C.c_uint64), ("bvh_build_ms", C.c_double), ("bvh_nodes", C.c_uint32),
-                ("bvh_tri_slots", C.c_uint32), ("key_slack", C.c_float), ("samples_done", C.c_uint32), ("key_evals", C.c_uint64)]
+                ("bvh_tri_slots", C.c_uint32), ("key_slack", C.c_float), ("samples_done", C.c_uint32), ("key_evals", C.c_uint64),
+                ("reduce_ms", C.c_double), ("reduce_calls", C.c_uint64), ("nodes_visited_extend", C.c_uint64), ("tris_tested_extend", C.c_uint64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -141,7 +143,17 @@ def load_library(path: str = LIB_PATH):
     L.eleven_trace_closest.argtypes = [vp, vp, sz, vp]
     L.eleven_trace_device.argtypes = [vp, vp, sz, vp, C.c_int, C.POINTER(C.c_float)]
     L.eleven_film_sums_device.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(sz)]
-    L.eleven_film_counts_device.argtypes = [vp, C.POINTER(vp), C.POINTER(sz)]
+    L.eleven_comm_unique_id.argtypes = [vp]
+    L.eleven_comm_init_rank.argtypes = [vp, vp, C.c_int, C.c_int]
+    L.eleven_comm_init_all.argtypes = [C.POINTER(vp), C.c_int]
+    L.eleven_reduce_film.argtypes = [vp, C.c_int, C.c_int]
+    L.eleven_get_film_reduced.argtypes = [vp, C.c_int, vp, sz]
+    L.eleven_resolve_rgba8_reduced.argtypes = [vp, C.c_int, vp, sz]
+    L.eleven_get_sample_counts_reduced.argtypes = [vp, vp, sz]
+    L.eleven_test_disney.argtypes = [vp, vp, sz, C.c_int, vp, vp]
+    L.eleven_test_hdri.argtypes = [vp, vp, vp, sz, C.c_int, C.c_int, vp, vp, vp]
+    L.eleven_test_env_lookup.argtypes = [vp, vp, sz, vp]
+    L.eleven_test_hitdata.argtypes = [vp, vp, vp, sz, C.c_int, vp]
     L.eleven_device_alloc.argtypes = [vp, sz, C.POINTER(vp)]
     L.eleven_device_free.argtypes = [vp, vp]
     L.eleven_device_upload.argtypes = [vp, vp, vp, sz]
@@ -151,7 +163,7 @@ def load_library(path: str = LIB_PATH):
     L.eleven_host_alloc.argtypes = [vp, sz, C.POINTER(vp)]
     L.eleven_host_free.argtypes = [vp, vp]
     L.eleven_bvh_build_host.argtypes = [vp, C.c_uint32, vp, C.c_int, vp, sz, vp, sz, vp, vp, vp]
-    if L.eleven_abi_version() != 2:
+    if L.eleven_abi_version() != 3:
         raise RuntimeError("ABI version mismatch")
     _lib = L
     return L
@@ -161,7 +173,9 @@ EXPORTED_SYMBOLS = [
     "eleven_abi_version", "eleven_last_error", "eleven_init", "eleven_destroy", "eleven_scene_upload",
     "eleven_render", "eleven_get_film", "eleven_get_pathcount", "eleven_get_samples", "eleven_get_sample_counts", "eleven_get_stats",
     "eleven_film_reset", "eleven_set_camera", "eleven_trace_closest", "eleven_trace_device", "eleven_film_sums_device",
-    "eleven_film_counts_device", "eleven_device_alloc", "eleven_device_free", "eleven_device_upload",
+    "eleven_comm_unique_id", "eleven_comm_init_rank", "eleven_comm_init_all", "eleven_reduce_film", "eleven_get_film_reduced",
+    "eleven_resolve_rgba8_reduced", "eleven_get_sample_counts_reduced", "eleven_test_disney", "eleven_test_hdri",
+    "eleven_test_env_lookup", "eleven_test_hitdata", "eleven_device_alloc", "eleven_device_free", "eleven_device_upload",
     "eleven_device_download", "eleven_resolve_rgba8", "eleven_bvh_download", "eleven_host_alloc",
     "eleven_host_free", "eleven_bvh_build_host",
 ]

@@ -11,6 +11,7 @@
 #include <atomic>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <future>
@@ -33,7 +34,8 @@ struct Box {
 struct Node2 { Box box; int left, right, first, count, span; };   // leaf iff count > 0; span = triangles in the subtree
 
 static const int   MAXBINS = 64;
-static int BINS = 16;            // ELEVEN_BVH_BINS (experiments); 16 is what the device builder uses
+// ELEVEN_BVH_BINS (experiments; read once when the library is loaded, so concurrent builds never write it); 16 is what the device builder uses
+static const int BINS = [] { const char* e = getenv("ELEVEN_BVH_BINS"); return e ? std::max(2, std::min(MAXBINS, atoi(e))) : 16; }();
 static const int   MAX_LEAF = EL_MAX_LEAF;                 // bvh8.h
 static const float COST_TRI = 1.0f, COST_NODE = EL_LEAF_COST_NODE;
 
@@ -129,7 +131,6 @@ void buildBvh8(const ElevenTri* tris, uint32_t n, const int32_t* triMaterial, Bv
     out.nodes.clear(); out.slots.clear(); out.keySlack = 0; out.maxDepth = 0;
     for (int a = 0; a < 3; a++) { out.boundsLo[a] = 0; out.boundsHi[a] = 0; }
     if (threads < 1) threads = 1;
-    if (const char* e = getenv("ELEVEN_BVH_BINS")) BINS = std::max(2, std::min(MAXBINS, atoi(e)));
 
     Builder B; B.tris = tris; B.n = n; B.threads = threads; B.liveTasks = 0;
     B.tbox.resize(n); B.cen.resize(3 * (size_t)n); B.idx.resize(n);

@@ -10,17 +10,21 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
 
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>          /* types only: the library is dlopen'ed on first use (eleven_comm_*), so libeleven_b200.so has no link-time NCCL dependency */
 
 #include "../../include/eleven_b200.h"
 #include "bvh8.h"
 #include "kernels.cuh"
 #include "kernels_trace.cuh"
 #include "bvh8_build_gpu.cuh"
+#include "test_hooks.cuh"
 
 using namespace eleven;
 
@@ -37,8 +41,16 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
 
 struct ElevenCtx {
     ElevenConfig cfg;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t stream = nullptr;               // render stream: every kernel of eleven_render / eleven_trace_* / uploads
+    cudaStream_t snapStream = nullptr;           // snapshot stream: film / counter read-backs, concurrent with a running eleven_render
+                                                 // (the reference polls getBuffers on its bufferStream while the kernel runs, S/kernel.cu:688-710)
+    std::mutex snapMutex;                        // serialises the users of the snapshot stream and of d_resolve
+    std::mutex statsMutex;                       // host-side ElevenStats fields written at the end of eleven_render
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evR0 = nullptr, evR1 = nullptr;
+    ncclComm_t comm = nullptr;                   // film-reduce communicator (eleven_comm_init_rank / eleven_comm_init_all)
+    int commRank = -1, commSize = 0;
+    float4* d_reduced = nullptr;                 // root only: sum over ranks of the film passes (eleven_reduce_film)
+    int reducedPasses = 0;
     std::vector<void*> sceneAllocs, waveAllocs;
     DevScene scene;
     WaveState W;
@@ -76,6 +88,8 @@ static int devUpload(std::vector<void*>& list, const T** p, const T* host, size_
 }
 static void freeAll(std::vector<void*>& list) { for (void* p : list) cudaFree(p); list.clear(); }
 
+static void commDestroy(ElevenCtx* c);
+
 extern "C" int eleven_init(const ElevenConfig* cfg, ElevenCtx** out) {
     if (!cfg || !out) return fail(ELEVEN_ERR_ARG, "eleven_init: null argument");
     if (cfg->rng_mode > 1 || cfg->env_mode > 1 || cfg->hit_mode > 1 || cfg->bvh_builder > 1) return fail(ELEVEN_ERR_ARG, "eleven_init: bad mode");
@@ -93,11 +107,20 @@ extern "C" int eleven_init(const ElevenConfig* cfg, ElevenCtx** out) {
     if (c->cfg.max_bounces == 0) c->cfg.max_bounces = 5;
     if (c->cfg.sample_stride == 0) c->cfg.sample_stride = 1;
     memset(&c->scene, 0, sizeof c->scene); memset(&c->W, 0, sizeof c->W); memset(&c->stats, 0, sizeof c->stats);
-    cudaDeviceProp prop;
-    CK(cudaGetDeviceProperties(&prop, cfg->device));
-    c->numSMs = prop.multiProcessorCount;
-    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    CK(cudaEventCreate(&c->ev0)); CK(cudaEventCreate(&c->ev1));
+    cudaError_t e = cudaDeviceGetAttribute(&c->numSMs, cudaDevAttrMultiProcessorCount, cfg->device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    int prLo = 0, prHi = 0;
+    if (e == cudaSuccess) e = cudaDeviceGetStreamPriorityRange(&prLo, &prHi);
+    // highest priority: the persistent render kernels fill every SM, so a snapshot's blocks are placed when the running kernel retires
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&c->snapStream, cudaStreamNonBlocking, prHi);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->evR0);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->evR1);
+    if (e != cudaSuccess) {                      // nothing half-built survives a failed init
+        eleven_destroy(c);
+        return fail(ELEVEN_ERR_CUDA, std::string("eleven_init: ") + cudaGetErrorString(e));
+    }
     *out = c;
     return ELEVEN_OK;
 }
@@ -106,12 +129,15 @@ extern "C" void eleven_destroy(ElevenCtx* c) {
     if (!c) return;
     cudaSetDevice(c->cfg.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->snapStream) cudaStreamSynchronize(c->snapStream);
+    commDestroy(c);
     freeAll(c->sceneAllocs); freeAll(c->waveAllocs);
+    if (c->d_reduced) cudaFree(c->d_reduced);
     if (c->bvhArena.base) cudaFree(c->bvhArena.base);
-    if (c->ev0) cudaEventDestroy(c->ev0);
-    if (c->ev1) cudaEventDestroy(c->ev1);
+    for (cudaEvent_t e : {c->ev0, c->ev1, c->evR0, c->evR1}) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : c->evPool) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->snapStream) cudaStreamDestroy(c->snapStream);
     delete c;
 }
 
@@ -211,7 +237,9 @@ static int allocWaveK(ElevenCtx* c) {
     APX(rng, Xorwow) A(hitBucket, uint8_t)
     A(qCur, uint32_t) A(qNext, uint32_t) A(qNee, uint32_t)
     if ((rc = devAlloc(c->waveAllocs, &W.qBucket, n * EL_BUCKETS))) return rc;
-    APX(filmBeauty, float4) APX(filmNormal, float4) APX(filmTangent, float4) APX(filmBitangent, float4) APX(filmCount, uint32_t) APX(pathCount, uint32_t)
+    if ((rc = devAlloc(c->waveAllocs, &W.filmBeauty, npx * 4))) return rc;        // the four passes back to back (WaveState)
+    W.filmNormal = W.filmBeauty + npx; W.filmTangent = W.filmBeauty + 2 * npx; W.filmBitangent = W.filmBeauty + 3 * npx;
+    APX(pathCount, uint32_t)
 #undef A
 #undef APX
     const size_t npxResolve = npx;
@@ -233,7 +261,8 @@ static int resetFilm(ElevenCtx* c) {
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(c->stream));
     c->samplesRendered = 0;
-    c->stats.render_ms = 0; c->stats.trace_ms = 0; c->stats.kernel_launches = 0; c->stats.pixel_samples = 0;
+    std::lock_guard<std::mutex> lk(c->statsMutex);
+    c->stats.render_ms = 0; c->stats.trace_ms = 0; c->stats.kernel_launches = 0; c->stats.pixel_samples = 0; c->stats.reduce_ms = 0; c->stats.reduce_calls = 0;
     c->stats.extend_ms = c->stats.shade_ms = c->stats.connect_ms = c->stats.other_ms = 0; c->stats.extend_launches = 0;
     return ELEVEN_OK;
 }
@@ -442,18 +471,34 @@ extern "C" int eleven_film_reset(ElevenCtx* c) {
     return resetFilm(c);
 }
 
+// Persistent grids are sized to what is RESIDENT: SMs x the CTAs per SM the kernel's registers / shared memory admit (occupancy
+// query, cached per kernel).  A larger grid only adds CTAs that wait for a slot, fill their mask tables and find the queue empty.
+// ELEVEN_GRID_EXTEND / ELEVEN_GRID_SHADOW override the CTAs per SM (tuning knobs).
+template <typename K>
+static int persistentGrid(ElevenCtx* c, K kernel, const char* envOverride) {
+    static std::mutex m; static std::vector<std::pair<const void*, int>> cache;
+    if (envOverride) if (const char* e = getenv(envOverride)) return c->numSMs * std::max(1, atoi(e));
+    std::lock_guard<std::mutex> lk(m);
+    for (auto& kv : cache) if (kv.first == (const void*)kernel) return c->numSMs * kv.second;
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, 128, 0) != cudaSuccess || n < 1) { cudaGetLastError(); n = 8; }
+    cache.push_back({(const void*)kernel, n});
+    return c->numSMs * n;
+}
+#define LAUNCH_PERSISTENT(kernel, env, ...) kernel<<<persistentGrid(c, kernel, env), 128, 0, c->stream>>>(__VA_ARGS__)
+
 template <bool COUNT>
-static void launchExtend(ElevenCtx* c, int grid) {
-    if (c->cfg.hit_mode == ELEVEN_HIT_KEY) k_extend<TRACE_CLOSEST_KEY, COUNT><<<grid, 128, 0, c->stream>>>(c->W, c->scene);
-    else k_extend<TRACE_CLOSEST_T, COUNT><<<grid, 128, 0, c->stream>>>(c->W, c->scene);
+static void launchExtend(ElevenCtx* c) {
+    if (c->cfg.hit_mode == ELEVEN_HIT_KEY) LAUNCH_PERSISTENT((k_extend<TRACE_CLOSEST_KEY, COUNT>), "ELEVEN_GRID_EXTEND", c->W, c->scene);
+    else LAUNCH_PERSISTENT((k_extend<TRACE_CLOSEST_T, COUNT>), "ELEVEN_GRID_EXTEND", c->W, c->scene);
 }
 // shadow stages of one bounce; the last one also performs the MIS combination (kernels_trace.cuh).  Returns launches.
 template <bool COUNT>
-static int launchConnect(ElevenCtx* c, int grid) {
-    if (c->scene.lightCount == 0) { k_shadowEnv<false, COUNT><<<grid, 128, 0, c->stream>>>(c->W, c->scene); return 1; }
-    k_shadowEnv<true, COUNT><<<grid, 128, 0, c->stream>>>(c->W, c->scene);
-    if (c->cfg.hit_mode == ELEVEN_HIT_KEY && !(c->cfg.flags & ELEVEN_FLAG_ANYHIT_LIGHT_SHADOWS)) k_shadowLight<ELEVEN_HIT_KEY, COUNT><<<grid, 128, 0, c->stream>>>(c->W, c->scene);
-    else k_shadowLight<ELEVEN_HIT_MIN_T, COUNT><<<grid, 128, 0, c->stream>>>(c->W, c->scene);
+static int launchConnect(ElevenCtx* c) {
+    if (c->scene.lightCount == 0) { LAUNCH_PERSISTENT((k_shadowEnv<false, COUNT>), "ELEVEN_GRID_SHADOW", c->W, c->scene); return 1; }
+    LAUNCH_PERSISTENT((k_shadowEnv<true, COUNT>), "ELEVEN_GRID_SHADOW", c->W, c->scene);
+    if (c->cfg.hit_mode == ELEVEN_HIT_KEY && !(c->cfg.flags & ELEVEN_FLAG_ANYHIT_LIGHT_SHADOWS)) LAUNCH_PERSISTENT((k_shadowLight<ELEVEN_HIT_KEY, COUNT>), "ELEVEN_GRID_SHADOW", c->W, c->scene);
+    else LAUNCH_PERSISTENT((k_shadowLight<ELEVEN_HIT_MIN_T, COUNT>), "ELEVEN_GRID_SHADOW", c->W, c->scene);
     return 2;
 }
 
@@ -465,12 +510,6 @@ extern "C" int eleven_render(ElevenCtx* c, int spp) {
     const uint32_t n = c->nPixels;
     const int gridPix = (int)((n + 255) / 256);
     c->P.sampleStride = c->cfg.sample_stride;
-    const int gridPersist = c->numSMs * 8;             // 148 SMs x 8 CTAs of 128 threads: a multiple of the SM count
-    // traversal kernels: as many CTAs per SM as their register count admits (k_extend 64 registers -> 8, shadow 56 -> 9);
-    // ELEVEN_GRID_EXTEND / ELEVEN_GRID_SHADOW override the CTAs per SM (tuning knobs)
-    static const int ctasExtend = getenv("ELEVEN_GRID_EXTEND") ? std::max(1, atoi(getenv("ELEVEN_GRID_EXTEND"))) : 8;
-    static const int ctasShadow = getenv("ELEVEN_GRID_SHADOW") ? std::max(1, atoi(getenv("ELEVEN_GRID_SHADOW"))) : 8;
-    const int gridExtend = c->numSMs * ctasExtend, gridShadow = c->numSMs * ctasShadow;
     const bool count = (c->cfg.flags & ELEVEN_FLAG_COUNTERS) != 0;
     const bool timeK = (c->cfg.flags & ELEVEN_FLAG_TIME_KERNELS) != 0;
     const bool fastMath = (c->cfg.flags & ELEVEN_FLAG_FAST_MATH) != 0;
@@ -495,15 +534,15 @@ extern "C" int eleven_render(ElevenCtx* c, int spp) {
         else k_raygen<false><<<gridPaths, 256, 0, c->stream>>>(c->W, c->scene, c->P);
         mark(3);
         for (uint32_t b = 0; b < c->cfg.max_bounces; b++) {
-            if (count) launchExtend<true>(c, gridExtend); else launchExtend<false>(c, gridExtend);
+            if (count) launchExtend<true>(c); else launchExtend<false>(c);
             mark(0);
-            k_classify<<<gridPersist, 128, 0, c->stream>>>(c->W, c->scene);
-            if (fastMath) k_shade<true><<<gridPersist, 128, 0, c->stream>>>(c->W, c->scene, c->P);
-            else k_shade<false><<<gridPersist, 128, 0, c->stream>>>(c->W, c->scene, c->P);
+            LAUNCH_PERSISTENT(k_classify, nullptr, c->W, c->scene);
+            if (fastMath) LAUNCH_PERSISTENT(k_shade<true>, nullptr, c->W, c->scene, c->P);
+            else LAUNCH_PERSISTENT(k_shade<false>, nullptr, c->W, c->scene, c->P);
             mark(1);
             k_advance<<<1, 32, 0, c->stream>>>(c->W, c->scene.lightCount, 0);
             mark(3);
-            c->stats.kernel_launches += count ? launchConnect<true>(c, gridShadow) : launchConnect<false>(c, gridShadow);
+            c->stats.kernel_launches += count ? launchConnect<true>(c) : launchConnect<false>(c);
             mark(2);
             k_advance<<<1, 32, 0, c->stream>>>(c->W, c->scene.lightCount, 1);
             mark(3);
@@ -521,6 +560,7 @@ extern "C" int eleven_render(ElevenCtx* c, int spp) {
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(c->stream));
     float ms = 0; CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    std::lock_guard<std::mutex> lk(c->statsMutex);
     c->stats.render_ms += ms;
     for (size_t i = 1; i < evUsed; i++) {
         float t = 0; CK(cudaEventElapsedTime(&t, c->evPool[i - 1], c->evPool[i]));
@@ -531,71 +571,96 @@ extern "C" int eleven_render(ElevenCtx* c, int spp) {
     return ELEVEN_OK;
 }
 
-static float4* filmPass(ElevenCtx* c, int pass) {
+static int passIndex(int pass) {               // position of a pass in the contiguous film block
     switch (pass) {
-        case ELEVEN_PASS_BEAUTY: return c->W.filmBeauty;
-        case ELEVEN_PASS_NORMAL: return c->W.filmNormal;
-        case ELEVEN_PASS_TANGENT: return c->W.filmTangent;
-        case ELEVEN_PASS_BITANGENT: return c->W.filmBitangent;
-        default: return nullptr;
+        case ELEVEN_PASS_BEAUTY: return 0;
+        case ELEVEN_PASS_NORMAL: return 1;
+        case ELEVEN_PASS_TANGENT: return 2;
+        case ELEVEN_PASS_BITANGENT: return 3;
+        default: return -1;
     }
 }
-
-extern "C" int eleven_get_film(ElevenCtx* c, int pass, float* rgba, size_t nPixels) {
-    if (!c || !rgba) return fail(ELEVEN_ERR_ARG, "eleven_get_film: null argument");
-    if (!c->haveScene) return fail(ELEVEN_ERR_STATE, "eleven_get_film: no scene uploaded");
-    if (nPixels != c->nPixels) return fail(ELEVEN_ERR_ARG, "eleven_get_film: n_pixels must be W*H");
-    float4* src = filmPass(c, pass);
-    if (!src) return fail(ELEVEN_ERR_UNSUPPORTED, "eleven_get_film: pass not produced on the device (DENOISE is a host-side OIDN pass in the reference)");
-    CK(cudaSetDevice(c->cfg.device));
-    k_resolve<<<(c->nPixels + 255) / 256, 256, 0, c->stream>>>(src, c->W.filmCount, c->d_resolve, c->nPixels);
-    CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(rgba, c->d_resolve, (size_t)c->nPixels * 16, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    return ELEVEN_OK;
+static float4* filmPass(ElevenCtx* c, int pass) {
+    const int k = passIndex(pass);
+    return k < 0 ? nullptr : c->W.filmBeauty + (size_t)k * c->nPixels;
 }
 
-extern "C" int eleven_resolve_rgba8(ElevenCtx* c, int pass, uint8_t* rgba8, size_t nPixels) {
-    if (!c || !rgba8) return fail(ELEVEN_ERR_ARG, "eleven_resolve_rgba8: null argument");
-    if (!c->haveScene) return fail(ELEVEN_ERR_STATE, "eleven_resolve_rgba8: no scene uploaded");
-    if (nPixels != c->nPixels) return fail(ELEVEN_ERR_ARG, "eleven_resolve_rgba8: n_pixels must be W*H");
-    float4* src = filmPass(c, pass);
-    if (!src) return fail(ELEVEN_ERR_UNSUPPORTED, "eleven_resolve_rgba8: pass not available");
+// ---- film read-back: on the SNAPSHOT stream, concurrent with a running eleven_render (see the header) --------------------
+enum { SRC_LOCAL = 0, SRC_REDUCED = 1 };
+static int filmSource(ElevenCtx* c, int pass, int source, const char* who, float4** src) {
+    if (!c->haveScene) return fail(ELEVEN_ERR_STATE, std::string(who) + ": no scene uploaded");
+    const int k = passIndex(pass);
+    if (k < 0) return fail(ELEVEN_ERR_UNSUPPORTED, std::string(who) + ": pass not produced on the device (DENOISE is a host-side OIDN pass in the reference)");
+    if (source == SRC_LOCAL) { *src = c->W.filmBeauty + (size_t)k * c->nPixels; return ELEVEN_OK; }
+    if (!c->d_reduced) return fail(ELEVEN_ERR_STATE, std::string(who) + ": no reduced film (call eleven_reduce_film; only the root holds one)");
+    if (k >= c->reducedPasses) return fail(ELEVEN_ERR_STATE, std::string(who) + ": this pass was not part of the last eleven_reduce_film (all_passes = 0)");
+    *src = c->d_reduced + (size_t)k * c->nPixels; return ELEVEN_OK;
+}
+static int getFilm(ElevenCtx* c, int pass, float* rgba, size_t nPixels, int source, const char* who) {
+    if (!c || !rgba) return fail(ELEVEN_ERR_ARG, std::string(who) + ": null argument");
+    float4* src = nullptr;
+    if (int rc = filmSource(c, pass, source, who, &src)) return rc;
+    if (nPixels != c->nPixels) return fail(ELEVEN_ERR_ARG, std::string(who) + ": n_pixels must be W*H");
     CK(cudaSetDevice(c->cfg.device));
-    k_resolve8<<<(c->nPixels + 255) / 256, 256, 0, c->stream>>>(src, c->W.filmCount, (uchar4*)c->d_resolve, c->nPixels);
+    std::lock_guard<std::mutex> lk(c->snapMutex);
+    k_resolve<<<(c->nPixels + 255) / 256, 256, 0, c->snapStream>>>(src, c->d_resolve, c->nPixels);
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(rgba8, c->d_resolve, (size_t)c->nPixels * 4, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpyAsync(rgba, c->d_resolve, (size_t)c->nPixels * 16, cudaMemcpyDeviceToHost, c->snapStream));
+    CK(cudaStreamSynchronize(c->snapStream));
     return ELEVEN_OK;
 }
+static int resolve8(ElevenCtx* c, int pass, uint8_t* rgba8, size_t nPixels, int source, const char* who) {
+    if (!c || !rgba8) return fail(ELEVEN_ERR_ARG, std::string(who) + ": null argument");
+    float4* src = nullptr;
+    if (int rc = filmSource(c, pass, source, who, &src)) return rc;
+    if (nPixels != c->nPixels) return fail(ELEVEN_ERR_ARG, std::string(who) + ": n_pixels must be W*H");
+    CK(cudaSetDevice(c->cfg.device));
+    std::lock_guard<std::mutex> lk(c->snapMutex);
+    k_resolve8<<<(c->nPixels + 255) / 256, 256, 0, c->snapStream>>>(src, (uchar4*)c->d_resolve, c->nPixels);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(rgba8, c->d_resolve, (size_t)c->nPixels * 4, cudaMemcpyDeviceToHost, c->snapStream));
+    CK(cudaStreamSynchronize(c->snapStream));
+    return ELEVEN_OK;
+}
+static int sampleCounts(ElevenCtx* c, uint32_t* out, size_t nPixels, int source, const char* who) {
+    if (!c || !out) return fail(ELEVEN_ERR_ARG, std::string(who) + ": null argument");
+    float4* src = nullptr;
+    if (int rc = filmSource(c, ELEVEN_PASS_BEAUTY, source, who, &src)) return rc;
+    if (nPixels != c->nPixels) return fail(ELEVEN_ERR_ARG, std::string(who) + ": n_pixels must be W*H");
+    CK(cudaSetDevice(c->cfg.device));
+    std::lock_guard<std::mutex> lk(c->snapMutex);
+    k_sampleCounts<<<(c->nPixels + 255) / 256, 256, 0, c->snapStream>>>(src, (uint32_t*)c->d_resolve, c->nPixels);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, c->d_resolve, (size_t)c->nPixels * 4, cudaMemcpyDeviceToHost, c->snapStream));
+    CK(cudaStreamSynchronize(c->snapStream));
+    return ELEVEN_OK;
+}
+extern "C" int eleven_get_film(ElevenCtx* c, int pass, float* rgba, size_t n) { return getFilm(c, pass, rgba, n, SRC_LOCAL, "eleven_get_film"); }
+extern "C" int eleven_get_film_reduced(ElevenCtx* c, int pass, float* rgba, size_t n) { return getFilm(c, pass, rgba, n, SRC_REDUCED, "eleven_get_film_reduced"); }
+extern "C" int eleven_resolve_rgba8(ElevenCtx* c, int pass, uint8_t* o, size_t n) { return resolve8(c, pass, o, n, SRC_LOCAL, "eleven_resolve_rgba8"); }
+extern "C" int eleven_resolve_rgba8_reduced(ElevenCtx* c, int pass, uint8_t* o, size_t n) { return resolve8(c, pass, o, n, SRC_REDUCED, "eleven_resolve_rgba8_reduced"); }
+extern "C" int eleven_get_sample_counts(ElevenCtx* c, uint32_t* o, size_t n) { return sampleCounts(c, o, n, SRC_LOCAL, "eleven_get_sample_counts"); }
+extern "C" int eleven_get_sample_counts_reduced(ElevenCtx* c, uint32_t* o, size_t n) { return sampleCounts(c, o, n, SRC_REDUCED, "eleven_get_sample_counts_reduced"); }
 
 extern "C" int eleven_get_pathcount(ElevenCtx* c, int32_t* out, size_t nPixels) {
     if (!c || !out) return fail(ELEVEN_ERR_ARG, "eleven_get_pathcount: null argument");
     if (!c->haveScene) return fail(ELEVEN_ERR_STATE, "eleven_get_pathcount: no scene uploaded");
     if (nPixels != c->nPixels) return fail(ELEVEN_ERR_ARG, "eleven_get_pathcount: n_pixels must be W*H");
     CK(cudaSetDevice(c->cfg.device));
-    CK(cudaMemcpyAsync(out, c->W.pathCount, (size_t)c->nPixels * 4, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    return ELEVEN_OK;
-}
-
-extern "C" int eleven_get_sample_counts(ElevenCtx* c, uint32_t* out, size_t nPixels) {
-    if (!c || !out) return fail(ELEVEN_ERR_ARG, "eleven_get_sample_counts: null argument");
-    if (!c->haveScene) return fail(ELEVEN_ERR_STATE, "eleven_get_sample_counts: no scene uploaded");
-    if (nPixels != c->nPixels) return fail(ELEVEN_ERR_ARG, "eleven_get_sample_counts: n_pixels must be W*H");
-    CK(cudaSetDevice(c->cfg.device));
-    CK(cudaMemcpyAsync(out, c->W.filmCount, (size_t)c->nPixels * 4, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+    std::lock_guard<std::mutex> lk(c->snapMutex);
+    CK(cudaMemcpyAsync(out, c->W.pathCount, (size_t)c->nPixels * 4, cudaMemcpyDeviceToHost, c->snapStream));
+    CK(cudaStreamSynchronize(c->snapStream));
     return ELEVEN_OK;
 }
 
 extern "C" int eleven_get_samples(ElevenCtx* c) {
     if (!c || !c->haveScene) return fail(ELEVEN_ERR_STATE, "eleven_get_samples: no scene uploaded");
-    uint32_t v = 0;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (cudaSetDevice(c->cfg.device) != cudaSuccess) return fail(ELEVEN_ERR_CUDA, "cudaSetDevice");
-    if (cudaMemcpyAsync(&v, c->W.filmCount, 4, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) return fail(ELEVEN_ERR_CUDA, "cudaMemcpyAsync");
-    if (cudaStreamSynchronize(c->stream) != cudaSuccess) return fail(ELEVEN_ERR_CUDA, "cudaStreamSynchronize");
-    return (int)v;
+    std::lock_guard<std::mutex> lk(c->snapMutex);
+    if (cudaMemcpyAsync(&v, c->W.filmBeauty, 16, cudaMemcpyDeviceToHost, c->snapStream) != cudaSuccess) return fail(ELEVEN_ERR_CUDA, "cudaMemcpyAsync");
+    if (cudaStreamSynchronize(c->snapStream) != cudaSuccess) return fail(ELEVEN_ERR_CUDA, "cudaStreamSynchronize");
+    return (int)v.w;
 }
 
 extern "C" int eleven_get_stats(ElevenCtx* c, ElevenStats* out) {
@@ -603,17 +668,25 @@ extern "C" int eleven_get_stats(ElevenCtx* c, ElevenStats* out) {
     if (c->haveScene) {
         CK(cudaSetDevice(c->cfg.device));
         unsigned long long st[ST_COUNT];
-        CK(cudaMemcpyAsync(st, c->W.stats, sizeof st, cudaMemcpyDeviceToHost, c->stream));
         std::vector<uint32_t> pc(c->nPixels);
-        CK(cudaMemcpyAsync(pc.data(), c->W.pathCount, (size_t)c->nPixels * 4, cudaMemcpyDeviceToHost, c->stream));
-        uint32_t s0 = 0;
-        CK(cudaMemcpyAsync(&s0, c->W.filmCount, 4, cudaMemcpyDeviceToHost, c->stream));
-        CK(cudaStreamSynchronize(c->stream));
+        float4 f0 = make_float4(0.f, 0.f, 0.f, 0.f);
+        {
+            std::lock_guard<std::mutex> lk(c->snapMutex);
+            CK(cudaMemcpyAsync(st, c->W.stats, sizeof st, cudaMemcpyDeviceToHost, c->snapStream));
+            CK(cudaMemcpyAsync(pc.data(), c->W.pathCount, (size_t)c->nPixels * 4, cudaMemcpyDeviceToHost, c->snapStream));
+            CK(cudaMemcpyAsync(&f0, c->W.filmBeauty, 16, cudaMemcpyDeviceToHost, c->snapStream));
+            CK(cudaStreamSynchronize(c->snapStream));
+        }
+        uint64_t hb = 0; for (uint32_t v : pc) hb += v;
+        std::lock_guard<std::mutex> lk(c->statsMutex);
         c->stats.rays_extension = st[ST_RAYS_EXT]; c->stats.rays_shadow_env = st[ST_RAYS_ENV]; c->stats.rays_shadow_light = st[ST_RAYS_LIGHT];
         c->stats.nodes_visited = st[ST_NODES]; c->stats.tris_tested = st[ST_TRIS]; c->stats.key_evals = st[ST_KEYS];
-        uint64_t hb = 0; for (uint32_t v : pc) hb += v;
-        c->stats.hit_bounces = hb; c->stats.samples_done = s0;
+        c->stats.nodes_visited_extend = st[ST_NODES_EXT]; c->stats.tris_tested_extend = st[ST_TRIS_EXT];
+        c->stats.hit_bounces = hb; c->stats.samples_done = (uint32_t)f0.w;
+        *out = c->stats;
+        return ELEVEN_OK;
     }
+    std::lock_guard<std::mutex> lk(c->statsMutex);
     *out = c->stats;
     return ELEVEN_OK;
 }
@@ -707,11 +780,6 @@ extern "C" int eleven_film_sums_device(ElevenCtx* c, int pass, void** p, size_t*
     if (!src) return fail(ELEVEN_ERR_UNSUPPORTED, "eleven_film_sums_device: pass not available");
     *p = src; *nFloats = (size_t)c->nPixels * 4; return ELEVEN_OK;
 }
-extern "C" int eleven_film_counts_device(ElevenCtx* c, void** p, size_t* n) {
-    if (!c || !p || !n) return fail(ELEVEN_ERR_ARG, "eleven_film_counts_device: null argument");
-    if (!c->haveScene) return fail(ELEVEN_ERR_STATE, "eleven_film_counts_device: no scene uploaded");
-    *p = c->W.filmCount; *n = c->nPixels; return ELEVEN_OK;
-}
 extern "C" int eleven_device_alloc(ElevenCtx* c, size_t bytes, void** p) {
     if (!c || !p) return fail(ELEVEN_ERR_ARG, "eleven_device_alloc: null argument");
     CK(cudaSetDevice(c->cfg.device));
@@ -728,6 +796,7 @@ extern "C" int eleven_host_alloc(ElevenCtx* c, size_t bytes, void** p) {
 }
 extern "C" int eleven_host_free(ElevenCtx* c, void* p) {
     if (!c) return fail(ELEVEN_ERR_ARG, "eleven_host_free: null context");
+    CK(cudaSetDevice(c->cfg.device));
     CK(cudaFreeHost(p));
     return ELEVEN_OK;
 }
@@ -744,4 +813,206 @@ extern "C" int eleven_device_download(ElevenCtx* c, void* h, const void* d, size
     if (!c || !d || !h) return fail(ELEVEN_ERR_ARG, "eleven_device_download: null argument");
     CK(cudaSetDevice(c->cfg.device));
     CK(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, c->stream)); CK(cudaStreamSynchronize(c->stream)); return ELEVEN_OK;
+}
+
+// ---- multi-GPU: ONE ncclReduce of the film records to the root ---------------------------------------------------
+// The reference is single-GPU (cudaSetDevice(0), S/kernel.cu:604) and keeps running means, which cannot be combined; here the film
+// is sums + counts (.w), so the whole exchange step of a job is one sum-reduce over NVLink.  libnccl.so.2 is loaded on first use:
+// inside a torch process this resolves to the NCCL torch already loaded, in the CLI to the system library.
+namespace {
+struct NcclApi {
+    void* h = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Reduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    std::string err;
+};
+NcclApi* ncclApi() {
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char* names[] = {getenv("ELEVEN_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) { if (n && (api.h = dlopen(n, RTLD_NOW | RTLD_LOCAL))) break; }
+        if (!api.h) { api.err = std::string("cannot load libnccl.so.2: ") + (dlerror() ? dlerror() : "not found"); return; }
+        bool ok = true;
+        auto sym = [&](const char* n) { void* p = dlsym(api.h, n); if (!p) { ok = false; api.err = std::string("libnccl: missing symbol ") + n; } return p; };
+        api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId");
+        api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
+        api.CommInitAll = (decltype(api.CommInitAll))sym("ncclCommInitAll");
+        api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
+        api.Reduce = (decltype(api.Reduce))sym("ncclReduce");
+        api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
+        if (!ok) { dlclose(api.h); api.h = nullptr; }
+    });
+    return &api;
+}
+int ncclFail(const char* what, ncclResult_t r) { return fail(ELEVEN_ERR_CUDA, std::string(what) + ": " + ncclApi()->GetErrorString(r)); }
+} // namespace
+
+static void commDestroy(ElevenCtx* c) {
+    if (c->comm) { ncclApi()->CommDestroy(c->comm); c->comm = nullptr; c->commRank = -1; c->commSize = 0; }
+}
+
+extern "C" int eleven_comm_unique_id(void* idOut) {
+    static_assert(sizeof(ncclUniqueId) == ELEVEN_COMM_ID_BYTES, "ncclUniqueId size");
+    if (!idOut) return fail(ELEVEN_ERR_ARG, "eleven_comm_unique_id: null argument");
+    NcclApi* N = ncclApi();
+    if (!N->h) return fail(ELEVEN_ERR_UNSUPPORTED, N->err);
+    ncclUniqueId id;
+    ncclResult_t r = N->GetUniqueId(&id);
+    if (r != ncclSuccess) return ncclFail("ncclGetUniqueId", r);
+    memcpy(idOut, &id, sizeof id);
+    return ELEVEN_OK;
+}
+
+extern "C" int eleven_comm_init_rank(ElevenCtx* c, const void* idIn, int nranks, int rank) {
+    if (!c || !idIn) return fail(ELEVEN_ERR_ARG, "eleven_comm_init_rank: null argument");
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(ELEVEN_ERR_ARG, "eleven_comm_init_rank: bad rank / nranks");
+    NcclApi* N = ncclApi();
+    if (!N->h) return fail(ELEVEN_ERR_UNSUPPORTED, N->err);
+    CK(cudaSetDevice(c->cfg.device));
+    commDestroy(c);
+    ncclUniqueId id; memcpy(&id, idIn, sizeof id);
+    ncclResult_t r = N->CommInitRank(&c->comm, nranks, id, rank);
+    if (r != ncclSuccess) { c->comm = nullptr; return ncclFail("ncclCommInitRank", r); }
+    c->commRank = rank; c->commSize = nranks;
+    return ELEVEN_OK;
+}
+
+extern "C" int eleven_comm_init_all(ElevenCtx** ctxs, int n) {
+    if (!ctxs || n < 1) return fail(ELEVEN_ERR_ARG, "eleven_comm_init_all: bad argument");
+    NcclApi* N = ncclApi();
+    if (!N->h) return fail(ELEVEN_ERR_UNSUPPORTED, N->err);
+    std::vector<int> devs(n); std::vector<ncclComm_t> comms(n);
+    for (int i = 0; i < n; i++) {
+        if (!ctxs[i]) return fail(ELEVEN_ERR_ARG, "eleven_comm_init_all: null context");
+        devs[i] = ctxs[i]->cfg.device;
+        for (int j = 0; j < i; j++) if (devs[j] == devs[i]) return fail(ELEVEN_ERR_ARG, "eleven_comm_init_all: two contexts on the same device (NCCL needs one rank per device)");
+        commDestroy(ctxs[i]);
+    }
+    ncclResult_t r = N->CommInitAll(comms.data(), n, devs.data());
+    if (r != ncclSuccess) return ncclFail("ncclCommInitAll", r);
+    for (int i = 0; i < n; i++) { ctxs[i]->comm = comms[i]; ctxs[i]->commRank = i; ctxs[i]->commSize = n; }
+    return ELEVEN_OK;
+}
+
+extern "C" int eleven_reduce_film(ElevenCtx* c, int root, int allPasses) {
+    if (!c) return fail(ELEVEN_ERR_ARG, "eleven_reduce_film: null context");
+    if (!c->haveScene) return fail(ELEVEN_ERR_STATE, "eleven_reduce_film: no scene uploaded");
+    const int size = c->comm ? c->commSize : 1, rank = c->comm ? c->commRank : 0;
+    if (root < 0 || root >= size) return fail(ELEVEN_ERR_ARG, "eleven_reduce_film: root out of range");
+    CK(cudaSetDevice(c->cfg.device));
+    const int passes = allPasses ? 4 : 1;
+    const size_t nFloats = (size_t)c->nPixels * 4 * passes;
+    if (rank == root && !c->d_reduced) {
+        cudaError_t e = cudaMalloc((void**)&c->d_reduced, (size_t)c->nPixels * 4 * sizeof(float4));
+        if (e != cudaSuccess) { c->d_reduced = nullptr; return fail(ELEVEN_ERR_NOMEM, std::string("cudaMalloc(reduced film): ") + cudaGetErrorString(e)); }
+    }
+    CK(cudaEventRecord(c->evR0, c->stream));
+    if (c->comm) {
+        // the render stream orders the reduce behind every wave accumulated so far; the snapshot stream never touches d_reduced
+        // while this runs because its readers take snapMutex and the root takes it here too
+        std::unique_lock<std::mutex> lk(c->snapMutex, std::defer_lock);
+        if (rank == root) lk.lock();
+        ncclResult_t r = ncclApi()->Reduce(c->W.filmBeauty, rank == root ? (void*)c->d_reduced : (void*)c->W.filmBeauty, nFloats, ncclFloat, ncclSum, root, c->comm, c->stream);
+        if (r != ncclSuccess) return ncclFail("ncclReduce", r);
+        CK(cudaEventRecord(c->evR1, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    } else {
+        std::lock_guard<std::mutex> lk(c->snapMutex);
+        CK(cudaMemcpyAsync(c->d_reduced, c->W.filmBeauty, nFloats * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+        CK(cudaEventRecord(c->evR1, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    if (rank == root) c->reducedPasses = passes;
+    float ms = 0; CK(cudaEventElapsedTime(&ms, c->evR0, c->evR1));
+    std::lock_guard<std::mutex> lk(c->statsMutex);
+    c->stats.reduce_ms += ms; c->stats.reduce_calls += 1; c->stats.kernel_launches += 1;
+    return ELEVEN_OK;
+}
+
+// ---- known-answer test hooks (test_hooks.cuh) ------------------------------------------------------------------------------------
+namespace {
+struct Scratch {                                  // device buffers of one hook call, freed on every exit path
+    std::vector<void*> p;
+    ~Scratch() { for (void* q : p) cudaFree(q); }
+    template <typename T> T* up(const T* host, size_t count, cudaStream_t s) {
+        void* q = nullptr;
+        if (cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T)) != cudaSuccess) return nullptr;
+        p.push_back(q);
+        if (host && count && cudaMemcpyAsync(q, host, count * sizeof(T), cudaMemcpyHostToDevice, s) != cudaSuccess) return nullptr;
+        return (T*)q;
+    }
+};
+} // namespace
+#define HOOK_DOWN(dst, src, count) CK(cudaMemcpyAsync(dst, src, (size_t)(count) * sizeof(*(dst)), cudaMemcpyDeviceToHost, c->stream))
+
+extern "C" int eleven_test_disney(ElevenCtx* c, const float* records, size_t n, int fastMath, float* evalPdf, float* sample) {
+    if (!c || (n && (!records || !evalPdf || !sample))) return fail(ELEVEN_ERR_ARG, "eleven_test_disney: null argument");
+    if (n == 0) return ELEVEN_OK;
+    CK(cudaSetDevice(c->cfg.device));
+    Scratch S;
+    float* dr = S.up(records, n * 30, c->stream); float* de = S.up<float>(nullptr, n * 4, c->stream); float* ds = S.up<float>(nullptr, n * 3, c->stream);
+    if (!dr || !de || !ds) return fail(ELEVEN_ERR_NOMEM, "eleven_test_disney: device scratch");
+    const unsigned g = (unsigned)((n + 127) / 128);
+    if (fastMath) k_testDisney<true><<<g, 128, 0, c->stream>>>(dr, (uint32_t)n, de, ds);
+    else k_testDisney<false><<<g, 128, 0, c->stream>>>(dr, (uint32_t)n, de, ds);
+    CK(cudaGetLastError());
+    HOOK_DOWN(evalPdf, de, n * 4); HOOK_DOWN(sample, ds, n * 3);
+    CK(cudaStreamSynchronize(c->stream));
+    return ELEVEN_OK;
+}
+
+extern "C" int eleven_test_hdri(ElevenCtx* c, const float* r, const float* r2, size_t n, int envMode, int fastMath, int32_t* xy, float* dir, float* pdf) {
+    if (!c || (n && (!r || !xy || !dir || !pdf))) return fail(ELEVEN_ERR_ARG, "eleven_test_hdri: null argument");
+    if (envMode == ELEVEN_ENV_ALIAS && n && !r2) return fail(ELEVEN_ERR_ARG, "eleven_test_hdri: the alias table needs a second uniform");
+    if (!c->haveScene) return fail(ELEVEN_ERR_STATE, "eleven_test_hdri: no scene uploaded");
+    if (n == 0) return ELEVEN_OK;
+    CK(cudaSetDevice(c->cfg.device));
+    Scratch S;
+    float* dr = S.up(r, n, c->stream); float* dr2 = S.up(r2 ? r2 : r, n, c->stream);
+    int32_t* dxy = S.up<int32_t>(nullptr, n * 2, c->stream); float* dd = S.up<float>(nullptr, n * 3, c->stream); float* dp = S.up<float>(nullptr, n, c->stream);
+    if (!dr || !dr2 || !dxy || !dd || !dp) return fail(ELEVEN_ERR_NOMEM, "eleven_test_hdri: device scratch");
+    const unsigned g = (unsigned)((n + 127) / 128);
+    if (fastMath) k_testHdri<true><<<g, 128, 0, c->stream>>>(c->scene, dr, dr2, (uint32_t)n, envMode, dxy, dd, dp);
+    else k_testHdri<false><<<g, 128, 0, c->stream>>>(c->scene, dr, dr2, (uint32_t)n, envMode, dxy, dd, dp);
+    CK(cudaGetLastError());
+    HOOK_DOWN(xy, dxy, n * 2); HOOK_DOWN(dir, dd, n * 3); HOOK_DOWN(pdf, dp, n);
+    CK(cudaStreamSynchronize(c->stream));
+    return ELEVEN_OK;
+}
+
+extern "C" int eleven_test_env_lookup(ElevenCtx* c, const float* dirs, size_t n, float* rgb) {
+    if (!c || (n && (!dirs || !rgb))) return fail(ELEVEN_ERR_ARG, "eleven_test_env_lookup: null argument");
+    if (!c->haveScene) return fail(ELEVEN_ERR_STATE, "eleven_test_env_lookup: no scene uploaded");
+    if (n == 0) return ELEVEN_OK;
+    CK(cudaSetDevice(c->cfg.device));
+    Scratch S;
+    float* dd = S.up(dirs, n * 3, c->stream); float* dc = S.up<float>(nullptr, n * 3, c->stream);
+    if (!dd || !dc) return fail(ELEVEN_ERR_NOMEM, "eleven_test_env_lookup: device scratch");
+    k_testEnvLookup<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(c->scene, dd, (uint32_t)n, dc);
+    CK(cudaGetLastError());
+    HOOK_DOWN(rgb, dc, n * 3);
+    CK(cudaStreamSynchronize(c->stream));
+    return ELEVEN_OK;
+}
+
+extern "C" int eleven_test_hitdata(ElevenCtx* c, const float* attrs, const int32_t* objectIds, size_t n, int fastMath, float* out) {
+    if (!c || (n && (!attrs || !objectIds || !out))) return fail(ELEVEN_ERR_ARG, "eleven_test_hitdata: null argument");
+    if (!c->haveScene) return fail(ELEVEN_ERR_STATE, "eleven_test_hitdata: no scene uploaded");
+    if (n == 0) return ELEVEN_OK;
+    CK(cudaSetDevice(c->cfg.device));
+    Scratch S;
+    float* da = S.up(attrs, n * 14, c->stream); int32_t* di = S.up(objectIds, n, c->stream); float* dout = S.up<float>(nullptr, n * 21, c->stream);
+    if (!da || !di || !dout) return fail(ELEVEN_ERR_NOMEM, "eleven_test_hitdata: device scratch");
+    const unsigned g = (unsigned)((n + 127) / 128);
+    if (fastMath) k_testHitData<true><<<g, 128, 0, c->stream>>>(c->scene, da, di, (uint32_t)n, dout);
+    else k_testHitData<false><<<g, 128, 0, c->stream>>>(c->scene, da, di, (uint32_t)n, dout);
+    CK(cudaGetLastError());
+    HOOK_DOWN(out, dout, n * 21);
+    CK(cudaStreamSynchronize(c->stream));
+    return ELEVEN_OK;
 }

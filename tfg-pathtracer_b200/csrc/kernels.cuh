@@ -30,7 +30,7 @@ namespace eleven {
 enum { CNT_CUR = 0, CNT_NEXT = 1, CNT_NEE = 2, CNT_WORK_TRACE = 3, CNT_WORK_SHADE = 4, CNT_WORK_CONNECT = 5, CNT_WORK_LIGHT = 6, CNT_WORK_CLASSIFY = 7,
        CNT_BUCKET0 = 8, CNT_COUNT = 16 };
 enum { EL_BUCKETS = 8, EL_MISS_BUCKET = 7 };   // shading queue buckets: materials 0..5, 6 = all further materials, 7 = escaped rays
-enum { ST_RAYS_EXT = 0, ST_RAYS_ENV = 1, ST_RAYS_LIGHT = 2, ST_NODES = 3, ST_TRIS = 4, ST_KEYS = 5, ST_COUNT = 8 };
+enum { ST_RAYS_EXT = 0, ST_RAYS_ENV = 1, ST_RAYS_LIGHT = 2, ST_NODES = 3, ST_TRIS = 4, ST_KEYS = 5, ST_NODES_EXT = 6, ST_TRIS_EXT = 7, ST_COUNT = 8 };   // 3-5: all traversal kernels; 6-7: k_extend alone
 
 struct WaveState {
     // per path (index = film index * K + k)
@@ -50,9 +50,12 @@ struct WaveState {
     uint32_t* qBucket;                   // EL_BUCKETS x pathCapacity: the shading queue, sorted by material (k_classify)
     uint32_t* cnt;                       // CNT_*
     unsigned long long* stats;           // ST_*
-    // film: per-pixel sums + counts
+    // film: per-pixel sums of the four device passes, ONE allocation (BEAUTY, NORMAL, TANGENT, BITANGENT back to back, so that a
+    // single ncclReduce covers them); .w of every record = number of accepted samples of the pixel as a float (exact below 2^24).
+    // Sum and count of a pixel travel in one 16-byte store, so a snapshot taken on another stream while a wave accumulates sees
+    // every pixel either before or after its update, never a sum without its count (eleven_get_film during eleven_render).
     float4* filmBeauty; float4* filmNormal; float4* filmTangent; float4* filmBitangent;
-    uint32_t* filmCount; uint32_t* pathCount;
+    uint32_t* pathCount;
     uint32_t nPixels;
     uint32_t pathCapacity;               // nPixels * largest K: stride of the qBucket rows
 };
@@ -116,7 +119,7 @@ __global__ void k_filmReset(WaveState W) {
     if (i >= W.nPixels) return;
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
     W.filmBeauty[i] = z; W.filmNormal[i] = z; W.filmTangent[i] = z; W.filmBitangent[i] = z;
-    W.filmCount[i] = 0u; W.pathCount[i] = 0u;
+    W.pathCount[i] = 0u;
 }
 
 // fast-mode uniforms: 4 per call, keyed by (pixel, sample, dimension block)
@@ -433,18 +436,24 @@ __global__ void __launch_bounds__(256) k_accumulate(WaveState W, uint32_t logK) 
             paths += sdepth[q];
             if (sok[q]) { f.x += sv[pass][q][0]; f.y += sv[pass][q][1]; f.z += sv[pass][q][2]; count++; }
         }
+        f.w += (float)count;
         film[pix] = f;
-        if (pass == 0) { W.filmCount[pix] += count; W.pathCount[pix] += paths; }
+        if (pass == 0) W.pathCount[pix] += paths;
     }
 }
 
 // film read-back: mean, alpha = 1 (S/kernel.cu:137,461-463)
-__global__ void k_resolve(const float4* __restrict__ sums, const uint32_t* __restrict__ counts, float4* __restrict__ out, uint32_t n) {
+// (plain loads, not __ldg: the film may be written by a concurrent wave on the render stream)
+__global__ void k_resolve(const float4* sums, float4* __restrict__ out, uint32_t n) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const float4 s = sums[i]; const uint32_t c = counts[i];
-    const float inv = c ? 1.0f / (float)c : 0.f;
+    const float4 s = sums[i];
+    const float inv = s.w > 0.f ? 1.0f / s.w : 0.f;
     out[i] = make_float4(s.x * inv, s.y * inv, s.z * inv, 1.0f);
+}
+__global__ void k_sampleCounts(const float4* sums, uint32_t* __restrict__ out, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (uint32_t)sums[i].w;
 }
 // fused resolve -> 8-bit with the reference's output curve fastPow(clamp01(x), 1/2.2)*255 (S/main.cpp:156-158, S/PostProcessing.cpp:30-33)
 __device__ __forceinline__ double fastPowDev(double a, double b) {
@@ -452,11 +461,11 @@ __device__ __forceinline__ double fastPowDev(double a, double b) {
     hi = (int)(b * (double)(hi - 1072632447) + 1072632447.0);
     return __hiloint2double(hi, 0);
 }
-__global__ void k_resolve8(const float4* __restrict__ sums, const uint32_t* __restrict__ counts, uchar4* __restrict__ out, uint32_t n) {
+__global__ void k_resolve8(const float4* sums, uchar4* __restrict__ out, uint32_t n) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const float4 s = sums[i]; const uint32_t c = counts[i];
-    const float inv = c ? 1.0f / (float)c : 0.f;
+    const float4 s = sums[i];
+    const float inv = s.w > 0.f ? 1.0f / s.w : 0.f;
     const float v[4] = {s.x * inv, s.y * inv, s.z * inv, 1.0f};
     unsigned char o[4];
     for (int k = 0; k < 4; k++) {

@@ -43,7 +43,10 @@ __global__ void __launch_bounds__(128, EL_EXTEND_MIN_CTAS) k_extend(const __grid
     TraceCounters tc; tc.nodes = 0; tc.tris = 0; tc.keys = 0;
     ExtendSource src{W}; ExtendSink sink{W, S};
     traceQueue<MODE, COUNT, false>(S, W.cnt[CNT_CUR], &W.cnt[CNT_WORK_TRACE], src, sink, tc);
-    if (COUNT) { atomicAdd(&W.stats[ST_NODES], (unsigned long long)tc.nodes); atomicAdd(&W.stats[ST_TRIS], (unsigned long long)tc.tris); atomicAdd(&W.stats[ST_KEYS], (unsigned long long)tc.keys); }
+    if (COUNT) {
+        atomicAdd(&W.stats[ST_NODES], (unsigned long long)tc.nodes); atomicAdd(&W.stats[ST_TRIS], (unsigned long long)tc.tris); atomicAdd(&W.stats[ST_KEYS], (unsigned long long)tc.keys);
+        atomicAdd(&W.stats[ST_NODES_EXT], (unsigned long long)tc.nodes); atomicAdd(&W.stats[ST_TRIS_EXT], (unsigned long long)tc.tris);
+    }
 }
 
 // p / sum with the bits of the IEEE division.  0 / sum is +0 for any sum > 0, and that case is branched around: the division

@@ -1,6 +1,11 @@
-"""One-process-per-GPU driver logic: the scene is replicated, samples are split across ranks, and the
-per-GPU film SUMS (+ per-pixel sample counts) are summed with ONE reduce to rank 0 (NCCL over NVLink on the GPU box,
-gloo in the CPU tests).  torch.distributed is plumbing only; there is no data-path collective besides that reduce.
+"""One-process-per-GPU driver logic: the scene is replicated, samples are split across ranks, and the per-GPU
+film records (per-pixel SUMS whose .w carries the accepted-sample count) are summed with ONE reduce to the root.
+
+On the GPU box that reduce is native: `eleven_reduce_film` issues one `ncclReduce` over NVLink on the context's render
+stream, into a buffer separate from the local film (Renderer.reduce_film / film_reduced).  torch.distributed is plumbing
+only — it carries the 128-byte NCCL unique id to the ranks (`init_comm`) and provides the barriers of bench.py.
+`reduce_records` is the same exchange step on host tensors; it is what the world_size-2 gloo tests on CPU exercise and
+what a caller that brings its own collective would do with `eleven_film_sums_device`.
 
 The reference has no multi-GPU path (cudaSetDevice(0), S/kernel.cu:604); its running-mean film (S/kernel.cu:451-477)
 cannot be combined across devices, which is why the film is kept as sums here.
@@ -18,40 +23,38 @@ def sample_plan(total_spp: int, rank: int, world: int):
     return rank, world, local
 
 
-class DeviceArray:
-    """Zero-copy __cuda_array_interface__ view of a buffer owned by the C-ABI context (eleven_film_*_device)."""
-
-    def __init__(self, ptr: int, n: int, typestr: str):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
-
-
-def film_tensors(renderer, device):
-    """torch views (no copy) of the context's BEAUTY sums (float32, W*H*4) and sample counts (int32, W*H)."""
-    import torch
-    from .renderer import PASS_BEAUTY
-    sums = torch.as_tensor(DeviceArray(*renderer.film_sums_ptr(PASS_BEAUTY), "<f4"), device=device)
-    counts = torch.as_tensor(DeviceArray(*renderer.film_counts_ptr(), "<i4"), device=device)
-    return sums, counts
-
-
-def reduce_film(sums, counts, dst: int = 0, group=None):
-    """The one exchange step: sum film sums and counts onto rank `dst` (in place there)."""
+def init_comm(renderer, rank: int, world: int, src: int = 0, group=None):
+    """Creates the film-reduce communicator of `renderer` (eleven_comm_init_rank): rank `src` draws the NCCL unique id,
+    torch.distributed (any backend) hands it to the others.  Collective."""
     import torch.distributed as dist
+    box = [renderer.comm_unique_id() if rank == src else None]
+    if world > 1:
+        dist.broadcast_object_list(box, src=src, group=group)
+    renderer.comm_init_rank(box[0], world, rank)
+
+
+def reduce_records(records, dst: int = 0, group=None):
+    """The exchange step on a host/torch tensor of film records (n x 4 float32: sum.xyz, count): returns the sum over ranks
+    on rank `dst` as a NEW tensor (the local records are left untouched, like eleven_reduce_film: the step can be repeated
+    while rendering goes on without double-counting earlier samples); other ranks get None."""
+    import torch.distributed as dist
+    out = records.clone()
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.reduce(sums, dst, group=group)
-        dist.reduce(counts, dst, group=group)
-    return sums, counts
+        dist.reduce(out, dst, group=group)
+        if dist.get_rank(group) != dst:
+            return None
+    return out
 
 
-def resolve(sums, counts):
-    """mean = sum / count per pixel, alpha = 1 (the getBuffers contract, S/kernel.cu:137,461-463).  numpy or torch."""
-    s = sums.reshape(-1, 4)
-    c = counts.reshape(-1, 1)
+def resolve(records):
+    """mean = sum.xyz / count per pixel, alpha = 1 (the getBuffers contract, S/kernel.cu:137,461-463).  numpy or torch."""
+    s = records.reshape(-1, 4)
+    c = s[:, 3:4]
     if isinstance(s, np.ndarray):
         out = np.where(c > 0, s / np.maximum(c, 1), 0).astype(np.float32)
         out[:, 3] = 1.0
         return out
     import torch
-    out = torch.where(c > 0, s / c.clamp(min=1).to(s.dtype), torch.zeros_like(s))
+    out = torch.where(c > 0, s / c.clamp(min=1), torch.zeros_like(s))
     out[:, 3] = 1.0
     return out

@@ -26,27 +26,25 @@ using namespace eleven_host;
 
 static double nowS() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
-static double fastPowHost(double a, double b) {           // S/stb_image.h:127-136 (Ankerl's approximate pow)
-    union { double d; int32_t x[2]; } u; u.d = a;
-    u.x[1] = (int32_t)(b * (u.x[1] - 1072632447) + 1072632447); u.x[0] = 0; return u.d;
-}
-
 struct DeviceJob {
     int device = 0, spp = 0; ElevenConfig cfg; ElevenSceneDesc* desc = nullptr;
     const char* previewPath = nullptr;        // device 0 only: 8-bit snapshot of the film after every slice (the reference's preview window, S/main.cpp:132-184 + Window.hpp)
-    std::vector<float> aov[3];                // NORMAL, TANGENT, BITANGENT first-hit means, RGBA float = OIDN's float3 with a 16-byte stride (S/main.cpp:72-74)
-    bool wantAov = false;
-    std::vector<float> film; std::vector<uint32_t> counts; ElevenStats stats; std::string err; int rc = 0;
+    bool allPasses = false;                   // reduce the AOV passes too (--aov)
+    ElevenStats stats; std::string err; int rc = 0;
+    double uploadS = 0, renderS = 0, reduceS = 0;
     ElevenCtx* ctx = nullptr;
 };
 
+// One host thread per device: upload the (replicated) scene, render this device's share of the samples, then take part in the ONE
+// ncclReduce that sums the film records of all devices onto device 0 (eleven_reduce_film; a plain copy when there is one device).
 static void runDevice(DeviceJob* j, int slice, bool report) {
-    if ((j->rc = eleven_init(&j->cfg, &j->ctx))) { j->err = eleven_last_error(); return; }
-    if ((j->rc = eleven_scene_upload(j->ctx, j->desc))) { j->err = eleven_last_error(); return; }
-    const double t0 = nowS();
-    for (int done = 0; done < j->spp;) {
+    double t0 = nowS();
+    if ((j->rc = eleven_scene_upload(j->ctx, j->desc))) { j->err = eleven_last_error(); }
+    j->uploadS = nowS() - t0;
+    t0 = nowS();
+    for (int done = 0; !j->rc && done < j->spp;) {
         const int k = std::min(slice, j->spp - done);
-        if ((j->rc = eleven_render(j->ctx, k))) { j->err = eleven_last_error(); return; }
+        if ((j->rc = eleven_render(j->ctx, k))) { j->err = eleven_last_error(); break; }
         done += k;
         if (j->previewPath) {                                 // progressive preview: resolve on the device, 8-bit BMP on disk (atomic rename)
             const size_t np_ = (size_t)j->desc->camera.xRes * j->desc->camera.yRes;
@@ -64,21 +62,17 @@ static void runDevice(DeviceJob* j, int slice, bool report) {
             fflush(stdout);
         }
     }
-    const size_t n = (size_t)j->desc->camera.xRes * j->desc->camera.yRes;
-    j->film.resize(n * 4); j->counts.resize(n);
-    if ((j->rc = eleven_get_film(j->ctx, ELEVEN_PASS_BEAUTY, j->film.data(), n))) { j->err = eleven_last_error(); return; }
-    if ((j->rc = eleven_get_sample_counts(j->ctx, j->counts.data(), n))) { j->err = eleven_last_error(); return; }
-    if (j->wantAov) {
-        const int passes[3] = {ELEVEN_PASS_NORMAL, ELEVEN_PASS_TANGENT, ELEVEN_PASS_BITANGENT};
-        for (int k = 0; k < 3; k++) {
-            j->aov[k].resize(n * 4);
-            if ((j->rc = eleven_get_film(j->ctx, passes[k], j->aov[k].data(), n))) { j->err = eleven_last_error(); return; }
-        }
-    }
+    j->renderS = nowS() - t0;
+    // a device that failed still joins the collective (with whatever film it has) so that the others do not hang in NCCL
+    t0 = nowS();
+    const int rrc = eleven_reduce_film(j->ctx, 0, j->allPasses ? 1 : 0);
+    if (!j->rc && rrc) { j->rc = rrc; j->err = eleven_last_error(); }
+    j->reduceS = nowS() - t0;
     eleven_get_stats(j->ctx, &j->stats);
 }
 
 int main(int argc, char** argv) {
+    const double tProcess = nowS();
     std::string err;
     if (argc >= 4 && !strcmp(argv[1], "--dump-flat")) {
         LoadedScene s;
@@ -109,10 +103,12 @@ int main(int argc, char** argv) {
     LoadedScene scene;
     if (!loadScene(scenePath, scene, err)) { fprintf(stderr, "eleven: %s\n", err.c_str()); return 1; }
     ElevenSceneDesc desc = scene.desc();
+    const double loadS = nowS() - t0;
     printf("%s: %zu triangles, %zu textures, %ux%u, loaded in %.0f ms\n", scenePath.c_str(), scene.tris.size(), scene.textures.size(),
-           desc.camera.xRes, desc.camera.yRes, (nowS() - t0) * 1e3);
+           desc.camera.xRes, desc.camera.yRes, loadS * 1e3);
 
     std::vector<DeviceJob> jobs(gpus);
+    std::vector<ElevenCtx*> ctxs(gpus, nullptr);
     for (int g = 0; g < gpus; g++) {
         DeviceJob& j = jobs[g]; memset(&j.cfg, 0, sizeof j.cfg);
         j.device = g; j.desc = &desc;
@@ -122,8 +118,12 @@ int main(int argc, char** argv) {
         j.cfg.sample_offset = (uint32_t)g; j.cfg.sample_stride = (uint32_t)gpus;
         j.cfg.bvh_builder = deviceBvh ? ELEVEN_BVH_DEVICE : ELEVEN_BVH_HOST;
         j.spp = spp / gpus + (g < spp % gpus ? 1 : 0);          // global sample s goes to device s % gpus
-        if (g == 0) { j.previewPath = previewPath; j.wantAov = aovPrefix != nullptr; }   // device 0's share of the samples is an unbiased picture of its own
+        j.allPasses = aovPrefix != nullptr;
+        if (g == 0) j.previewPath = previewPath;                 // device 0's share of the samples is an unbiased picture of its own
+        if (eleven_init(&j.cfg, &j.ctx)) { fprintf(stderr, "eleven: device %d: %s\n", g, eleven_last_error()); return 1; }
+        ctxs[g] = j.ctx;
     }
+    if (gpus > 1 && eleven_comm_init_all(ctxs.data(), gpus)) { fprintf(stderr, "eleven: %s\n", eleven_last_error()); return 1; }
     t0 = nowS();
     std::vector<std::thread> th;
     for (int g = 1; g < gpus; g++) th.emplace_back(runDevice, &jobs[g], slice, false);
@@ -133,39 +133,41 @@ int main(int argc, char** argv) {
     for (auto& j : jobs) if (j.rc) { fprintf(stderr, "eleven: device %d: %s\n", j.device, j.err.c_str()); return 1; }
     const double wall = nowS() - t0;
 
+    // device 0 holds the film of the whole job (sum over devices of sums and counts): fused resolve -> 8-bit there, one D2H
     const size_t n = (size_t)desc.camera.xRes * desc.camera.yRes;
     std::vector<unsigned char> rgba(n * 4);
-    std::vector<float> mean;
-    if (gpus == 1) {
-        if (eleven_resolve_rgba8(jobs[0].ctx, ELEVEN_PASS_BEAUTY, rgba.data(), n)) { fprintf(stderr, "eleven: %s\n", eleven_last_error()); return 1; }
-        mean = jobs[0].film;
-    } else {                                                     // host-side combine of the per-device means (CLI only; bench uses NCCL)
-        mean.assign(n * 4, 0.f);
-        for (size_t i = 0; i < n; i++) {
-            double s[3] = {0, 0, 0}; uint64_t c = 0;
-            for (auto& j : jobs) { for (int k = 0; k < 3; k++) s[k] += (double)j.film[4 * i + k] * j.counts[i]; c += j.counts[i]; }
-            for (int k = 0; k < 3; k++) mean[4 * i + k] = c ? (float)(s[k] / c) : 0.f;
-            mean[4 * i + 3] = 1.f;
-            for (int k = 0; k < 4; k++) { float x = mean[4 * i + k]; x = x < 0 ? 0 : x > 1 ? 1 : x; rgba[4 * i + k] = (unsigned char)(fastPowHost(x, 1.0 / 2.2) * 255); }
-        }
-    }
+    if (eleven_resolve_rgba8_reduced(jobs[0].ctx, ELEVEN_PASS_BEAUTY, rgba.data(), n)) { fprintf(stderr, "eleven: %s\n", eleven_last_error()); return 1; }
     printf("Saving file %s...\n", outPath.c_str());
     if (!writeBmp24(outPath, (int)desc.camera.xRes, (int)desc.camera.yRes, rgba.data(), err)) { fprintf(stderr, "eleven: %s\n", err.c_str()); return 1; }
-    if (rawPath) { FILE* f = fopen(rawPath, "wb"); if (f) { fwrite(mean.data(), 4, mean.size(), f); fclose(f); } }
-    if (aovPrefix) {                                             // denoiser hand-off: first-hit NORMAL / TANGENT / BITANGENT means of device 0
+    if (rawPath) {
+        std::vector<float> mean(n * 4);
+        if (eleven_get_film_reduced(jobs[0].ctx, ELEVEN_PASS_BEAUTY, mean.data(), n)) { fprintf(stderr, "eleven: %s\n", eleven_last_error()); return 1; }
+        FILE* f = fopen(rawPath, "wb"); if (f) { fwrite(mean.data(), 4, mean.size(), f); fclose(f); }
+    }
+    if (aovPrefix) {                                             // denoiser hand-off: first-hit NORMAL / TANGENT / BITANGENT means over all devices' samples
         const char* names[3] = {"normal", "tangent", "bitangent"};
+        const int passes[3] = {ELEVEN_PASS_NORMAL, ELEVEN_PASS_TANGENT, ELEVEN_PASS_BITANGENT};
+        std::vector<float> aov(n * 4);
         for (int k = 0; k < 3; k++) {
+            if (eleven_get_film_reduced(jobs[0].ctx, passes[k], aov.data(), n)) { fprintf(stderr, "eleven: %s\n", eleven_last_error()); return 1; }
             const std::string path = std::string(aovPrefix) + "_" + names[k] + ".f32";
             FILE* f = fopen(path.c_str(), "wb");
             if (!f) { fprintf(stderr, "eleven: cannot write %s\n", path.c_str()); return 1; }
-            fwrite(jobs[0].aov[k].data(), 4, jobs[0].aov[k].size(), f); fclose(f);
+            fwrite(aov.data(), 4, aov.size(), f); fclose(f);
         }
     }
     printf("Saved!\n");
-    double renderMs = 0; uint64_t rays = 0, samples = 0;
-    for (auto& j : jobs) { renderMs = std::max(renderMs, j.stats.render_ms); rays += j.stats.rays_extension + j.stats.rays_shadow_env + j.stats.rays_shadow_light; samples += j.stats.pixel_samples; }
+    double renderMs = 0, reduceMs = 0, uploadS = 0, renderS = 0; uint64_t rays = 0, samples = 0;
+    for (auto& j : jobs) {
+        renderMs = std::max(renderMs, j.stats.render_ms); reduceMs = std::max(reduceMs, j.stats.reduce_ms);
+        uploadS = std::max(uploadS, j.uploadS); renderS = std::max(renderS, j.renderS);
+        rays += j.stats.rays_extension + j.stats.rays_shadow_env + j.stats.rays_shadow_light; samples += j.stats.pixel_samples;
+    }
     printf("%d spp on %d GPU(s): render %.1f ms (wall incl. upload %.1f ms), %.1f M pixel-samples/s, %.1f Mrays/s, BVH8 %u nodes built in %.1f ms\n",
            spp, gpus, renderMs, wall * 1e3, samples / renderMs / 1e3, rays / renderMs / 1e3, jobs[0].stats.bvh_nodes, jobs[0].stats.bvh_build_ms);
+    // the job as a user times it (process start -> picture on disk), phase by phase: what a strong-scaling number must include
+    printf("job: {\"gpus\": %d, \"spp\": %d, \"load_s\": %.3f, \"upload_s\": %.3f, \"render_s\": %.3f, \"render_device_ms\": %.1f, \"reduce_device_ms\": %.2f, \"total_s\": %.3f}\n",
+           gpus, spp, loadS, uploadS, renderS, renderMs, reduceMs, nowS() - tProcess);
     for (auto& j : jobs) eleven_destroy(j.ctx);
     return 0;
 }

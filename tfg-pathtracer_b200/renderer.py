@@ -168,7 +168,58 @@ class Renderer:
         self._ck(self.L.eleven_film_sums_device(self.h, p, C.byref(ptr), C.byref(n)))
         return ptr.value, n.value
 
-    def film_counts_ptr(self):
-        ptr, n = C.c_void_p(), C.c_size_t()
-        self._ck(self.L.eleven_film_counts_device(self.h, C.byref(ptr), C.byref(n)))
-        return ptr.value, n.value
+    # --- multi-GPU: one native ncclReduce of the film records to the root -------------------
+    def comm_unique_id(self) -> bytes:
+        buf = C.create_string_buffer(_capi.COMM_ID_BYTES)
+        self._ck(self.L.eleven_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init_rank(self, unique_id: bytes, nranks: int, rank: int):
+        assert len(unique_id) == _capi.COMM_ID_BYTES
+        self._ck(self.L.eleven_comm_init_rank(self.h, C.c_char_p(unique_id), int(nranks), int(rank)))
+
+    def reduce_film(self, root=0, all_passes=False):
+        self._ck(self.L.eleven_reduce_film(self.h, int(root), 1 if all_passes else 0))
+
+    def film_reduced(self, p=PASS_BEAUTY, out=None):
+        a = np.empty((self.H, self.W, 4), np.float32) if out is None else out
+        self._ck(self.L.eleven_get_film_reduced(self.h, p, a.ctypes.data, self.W * self.H))
+        return a
+
+    def resolve_rgba8_reduced(self, p=PASS_BEAUTY):
+        a = np.empty((self.H, self.W, 4), np.uint8)
+        self._ck(self.L.eleven_resolve_rgba8_reduced(self.h, p, a.ctypes.data, self.W * self.H))
+        return a
+
+    def get_sample_counts_reduced(self):
+        c = np.empty(self.W * self.H, np.uint32)
+        self._ck(self.L.eleven_get_sample_counts_reduced(self.h, c.ctypes.data, self.W * self.H))
+        return c
+
+    # --- known-answer hooks for the device shading functions (eleven_test_*) ------------------------------
+    def test_disney(self, records, fast_math=False):
+        rec = np.ascontiguousarray(records, np.float32).reshape(-1, 30)
+        ev, sm = np.zeros((len(rec), 4), np.float32), np.zeros((len(rec), 3), np.float32)
+        self._ck(self.L.eleven_test_disney(self.h, rec.ctypes.data, len(rec), int(fast_math), ev.ctypes.data, sm.ctypes.data))
+        return ev, sm
+
+    def test_hdri(self, r, r2=None, env_mode=ENV_CDF, fast_math=False):
+        r = np.ascontiguousarray(r, np.float32)
+        r2 = None if r2 is None else np.ascontiguousarray(r2, np.float32)
+        xy, d, pdf = np.zeros((len(r), 2), np.int32), np.zeros((len(r), 3), np.float32), np.zeros(len(r), np.float32)
+        self._ck(self.L.eleven_test_hdri(self.h, r.ctypes.data, None if r2 is None else r2.ctypes.data, len(r), int(env_mode), int(fast_math),
+                                         xy.ctypes.data, d.ctypes.data, pdf.ctypes.data))
+        return xy, d, pdf
+
+    def test_env_lookup(self, dirs):
+        dirs = np.ascontiguousarray(dirs, np.float32).reshape(-1, 3)
+        rgb = np.zeros((len(dirs), 3), np.float32)
+        self._ck(self.L.eleven_test_env_lookup(self.h, dirs.ctypes.data, len(dirs), rgb.ctypes.data))
+        return rgb
+
+    def test_hitdata(self, attrs, object_ids, fast_math=False):
+        attrs = np.ascontiguousarray(attrs, np.float32).reshape(-1, 14)
+        ids = np.ascontiguousarray(object_ids, np.int32)
+        out = np.zeros((len(attrs), 21), np.float32)
+        self._ck(self.L.eleven_test_hitdata(self.h, attrs.ctypes.data, ids.ctypes.data, len(attrs), int(fast_math), out.ctypes.data))
+        return out

@@ -17,12 +17,17 @@ ap.add_argument("--width", type=int, default=1920)
 ap.add_argument("--height", type=int, default=1080)
 ap.add_argument("--mode", default="fast")
 ap.add_argument("--hit-mode", default="key")
+ap.add_argument("--workload", default="clock")
+ap.add_argument("--grid", type=int, default=2237)
+ap.add_argument("--wave-spp", type=int, default=0)
 a = ap.parse_args()
 flat, _ = bench.get_scene(a, need_dir=False)
 sc = S.load_flat(flat)
 cfg = dict(R.FAST if a.mode == "fast" else R.PARITY)
 if a.hit_mode == "min_t":
     cfg["hit_mode"] = R.HIT_MIN_T
+if a.mode == "fast":
+    cfg["wave_spp"] = a.wave_spp
 r = R.Renderer(**cfg).render_setup(sc)
 r.render_cuda(a.spp)
 st = r.stats()
