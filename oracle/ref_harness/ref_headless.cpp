@@ -8,7 +8,9 @@
  * applied by sed to a temporary copy at build time, see the Makefile — nothing is copied into
  * the repo).  Output: oracle/_ref/eleven_ref_headless_{precise,fast} (git-ignored binaries).
  *
- * usage: eleven_ref_headless <scene_dir> <spp> <out_prefix> [--dump-scene file] [--external-textures] [--warmup spp]
+ * usage: eleven_ref_headless <scene_dir> <spp> <out_prefix> [--dump-scene file] [--external-textures] [--warmup spp] [--snapshots a,b,c]
+ *   --snapshots: also write <out_prefix>.beauty@<n>.f32 when the film holds n samples (n ascending, < spp): renderCuda is called
+ *   in segments, which the reference's running-mean film supports (its own --warmup path does the same)
  *   <out_prefix>.beauty.f32 / .normal.f32 / .tangent.f32 / .bitangent.f32  (W*H*4 floats each)
  *   <out_prefix>.pathcount.i32, <out_prefix>.json (timings, counters)
  */
@@ -88,11 +90,12 @@ static void dumpScene(Scene& s, const char* path, bool externalTextures) {
 int main(int argc, char** argv) {
     if (argc < 4) { fprintf(stderr, "usage: %s <scene_dir> <spp> <out_prefix> [--dump-scene file] [--external-textures]\n", argv[0]); return 1; }
     std::string dir = argv[1]; int spp = atoi(argv[2]); std::string out = argv[3];
-    const char* dump = 0; bool ext = false; int warm = 0;
+    const char* dump = 0; bool ext = false; int warm = 0; std::vector<int> snaps;
     for (int i = 4; i < argc; i++) {
         if (!strcmp(argv[i], "--dump-scene") && i + 1 < argc) dump = argv[++i];
         else if (!strcmp(argv[i], "--warmup") && i + 1 < argc) warm = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--external-textures")) ext = true;
+        else if (!strcmp(argv[i], "--snapshots") && i + 1 < argc) { for (char* t = strtok(argv[++i], ","); t; t = strtok(0, ",")) snaps.push_back(atoi(t)); }
     }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -110,7 +113,18 @@ int main(int argc, char** argv) {
     if (e != cudaSuccess) { fprintf(stderr, "renderSetup: %s\n", cudaGetErrorString(e)); return 5; }
     const double setupMs = t3 - t2;
     if (warm > 0) { renderCuda(&scene, warm); cudaDeviceSynchronize(); t3 = nowMs(); }     // untimed warm-up samples
-    renderCuda(&scene, spp);
+    int done = 0;
+    for (int sn : snaps) {
+        if (sn <= done || sn >= spp) continue;
+        renderCuda(&scene, sn - done); cudaDeviceSynchronize(); done = sn;
+        RenderData sd; sd.pars = RenderParameters(W, H, sn);
+        for (int i = 0; i < PASSES_COUNT; i++) sd.passes[i] = new float[(size_t)W * H * 4];
+        std::vector<int> spc((size_t)W * H);
+        getBuffers(sd, spc.data(), W * H); cudaDeviceSynchronize();
+        writeRaw(out + ".beauty@" + std::to_string(sn) + ".f32", sd.passes[BEAUTY], (size_t)W * H * 16);
+        for (int i = 0; i < PASSES_COUNT; i++) delete[] sd.passes[i];
+    }
+    renderCuda(&scene, spp - done);
     e = cudaDeviceSynchronize();
     double t4 = nowMs();
     if (e != cudaSuccess) { fprintf(stderr, "renderCuda: %s\n", cudaGetErrorString(e)); return 5; }

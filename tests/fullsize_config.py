@@ -8,6 +8,7 @@ size-independent parity properties of SURVEY §8c (what can be checked without a
   P4  KEY and MIN_T modes pick the same triangle except inside the per-scene key slack
   P5  rendering: film finite, sample counts == spp except NaN-dropped pixels, fast-mode mean == parity-mode mean (statistically)
   P6  on a 2 048-ray subsample, the CPU oracle's BRUTE-FORCE closest hit (exact reference arithmetic) equals ours bit for bit
+Driver-run: tests/test_gpu_fullsize.py calls run() for configs 2, 4 and 5 and asserts every property.
 
 configs: 2 = Cornell box 1024^2 256 spp; 3 = ClockCC0 stand-in 1000 spp; 4 = ~10 M-triangle displaced grid 1920x1080 512 spp;
          5 = 3840x2160 4096 spp textured + 4 point lights (spp can be cut with --spp: throughput is per sample)
@@ -52,7 +53,7 @@ def mt64(tri, rays):
     return t, u, v, det
 
 
-def main():
+def parser():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", type=int, required=True)
     ap.add_argument("--spp", type=int, default=0, help="override the config's spp (throughput is per sample)")
@@ -61,7 +62,12 @@ def main():
     ap.add_argument("--rays", type=int, default=1 << 20)
     ap.add_argument("--no-oracle", action="store_true")
     ap.add_argument("--bvh", default="device", choices=["device", "host"], help="builder of the tree the parity-mode properties run on")
-    a = ap.parse_args()
+    ap.add_argument("--oracle-rays", type=int, default=2048, help="size of the subsample traced by the oracle's brute force (P6)")
+    return ap
+
+
+def run(a):
+    """All checks of one config; returns the record (tests/test_gpu_fullsize.py asserts on it, main() prints it)."""
     out = {"config": a.config}
     t0 = time.time()
     sc, spp = build(a.config, a.grid, a.tex)
@@ -135,7 +141,7 @@ def main():
     rt.close()
     if not a.no_oracle:
         import oracle_lib as O
-        sub = rng.choice(len(rays), 2048, replace=False)
+        sub = rng.choice(len(rays), a.oracle_rays, replace=False)
         orc = O.Oracle(sc, build_bvh=False)
         t0 = time.time()
         ob = orc.trace(rays[sub], mode=1, threads=os.cpu_count() or 8)
@@ -169,6 +175,12 @@ def main():
                fast_mrays_per_s=rays_total / (stf["render_ms"] * 1e3), rays_per_sample=rays_total / (sc.width * sc.height * spp),
                P5_fast_finite=bool(np.isfinite(ff).all()), P5_mean_fast=float(ff.mean()), P5_mean_parity_2spp=float(fp.mean()))
     f.close()
+    return out
+
+
+def main():
+    a = parser().parse_args()
+    out = run(a)
     print(json.dumps(out))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(out, open(os.path.join(ROOT, "gpurun_out", "config%d.json" % a.config), "w"), indent=1)

@@ -148,6 +148,15 @@ class Oracle:
         self.L.orc_env_lookup(self.h, _p(dirs), len(dirs), _p(rgb))
         return rgb
 
+    def hitdata(self, attrs, object_ids):
+        """generateHitData (S/kernel.cu:54-119) for interpolated attributes (n x 14: position, normal, tangent, bitangent, tu, tv):
+        n x 21 floats = HitData scalars, emission, albedo, shading normal."""
+        attrs = np.ascontiguousarray(attrs, np.float32).reshape(-1, 14)
+        out = np.zeros((len(attrs), 27), np.float32)
+        for i in range(len(attrs)):
+            self.L.orc_hitdata(self.h, _p(attrs[i]), int(object_ids[i]), _p(out[i]))
+        return out[:, :21]
+
     def camera_ray(self, x, y, r5):
         r5 = np.ascontiguousarray(r5, np.float32)
         out = np.zeros(6, np.float32)

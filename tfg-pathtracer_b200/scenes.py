@@ -626,6 +626,43 @@ def displaced_grid(n=2237, seed=4, xres=1920, yres=1080, env_size=(4096, 2048)):
                      np.zeros(0, LIGHT_DT), "grid%d" % n, ["terrain"], ["ground"])
 
 
+def material_zoo(xres=160, yres=90, seed=23, lights=1, env_size=(128, 64)):
+    """Parity scene for every shading path the default materials never reach (Disney.hpp:108-253, Texture.hpp:114-142,
+    kernel.cu:349,355): the ClockCC0 stand-in geometry with
+      clock  clearcoat + clearcoatGloss + anisotropic + sheen + sheenTint + subsurface + specularTint, a FLOAT (F32_RGB),
+             bilinear-filtered, non-power-of-two albedo map, a tiled + offset non-power-of-two roughness map, constant metallic
+      table  constant emission + an emission-free clearcoat, bilinear 8-bit albedo map of odd size, no normal map
+      plant  four congruent 8-bit maps (the packed-record path) + an 8-bit bilinear EMISSION map + sheen / subsurface / anisotropy
+    plus a point light, so that all three MIS strategies (environment, point light, emission through the BRDF) carry weight."""
+    base = clock_standin(seed=11, tex_res=32, xres=xres, yres=yres, env_size=env_size, lights=lights)
+    rng = np.random.RandomState(seed)
+    tex = []
+    def add(data, fmt, **kw):
+        tex.append(TextureData(np.ascontiguousarray(data), fmt, **kw)); return len(tex) - 1
+    u8 = lambda shape: rng.randint(0, 256, shape + (3,)).astype(np.uint8)
+    smooth = lambda h, w, s_: np.clip(value_noise((h, w), s_, 3, 4)[..., None] * np.array([0.9, 0.7, 0.5]) + 0.1, 0, 1)
+    # clock
+    a0 = add(smooth(24, 40, seed + 1).astype(np.float32), TEX_F32_RGB, filter=1)
+    r0 = add(np.repeat((value_noise((23, 37), seed + 2, 3, 4) * 255).astype(np.uint8)[..., None], 3, -1), TEX_U8_LINEAR, xTile=2.0, yTile=3.0, xOffset=0.25, yOffset=0.4)
+    n0 = add(base.textures[0].data, TEX_U8_LINEAR)
+    m0 = default_material(albedoTextureID=a0, roughnessTextureID=r0, normalTextureID=n0, metallic=0.35, clearcoat=0.8, clearcoatGloss=0.6,
+                          anisotropic=0.5, sheen=0.3, sheenTint=0.4, subsurface=0.3, specularTint=0.5, specular=0.7)
+    # table
+    a1 = add((smooth(27, 45, seed + 3) * 255).astype(np.uint8), TEX_U8_SRGB, filter=1)
+    m1 = default_material(albedoTextureID=a1, roughness=0.45, metallic=0.0, clearcoat=0.3, clearcoatGloss=0.9, emission=(0.8, 0.5, 0.2),
+                          specularTint=1.0, sheen=1.0, sheenTint=1.0)
+    # plant: packed maps + emission map
+    alb, rough, metal, nrm = material_maps(32, seed * 7, (0.25, 0.6, 0.2))
+    n2 = add(nrm, TEX_U8_LINEAR); a2 = add(alb, TEX_U8_SRGB); r2 = add(rough, TEX_U8_LINEAR); t2 = add(metal, TEX_U8_LINEAR)
+    e2 = add((u8((16, 16)) // 3), TEX_U8_SRGB, filter=1)
+    m2 = default_material(normalTextureID=n2, albedoTextureID=a2, roughnessTextureID=r2, metallicTextureID=t2, emissionTextureID=e2,
+                          sheen=0.8, sheenTint=0.2, subsurface=0.7, anisotropic=0.8, clearcoat=1.0, clearcoatGloss=0.1, specular=0.3, specularTint=0.3)
+    base.materials = np.stack([m0, m1, m2])
+    base.textures = tex
+    base.name = "material_zoo"
+    return base
+
+
 def textured_lights(xres=3840, yres=2160, tex_res=4096, seed=11):
     """Config 5: C1-style textured materials + 4 point lights + defocus + env at 3840x2160."""
     s = clock_standin(seed, tex_res, xres, yres, lights=4)
