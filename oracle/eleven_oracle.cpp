@@ -247,7 +247,13 @@ struct Scene {
     std::vector<uint32_t> samples, pathcount;
     std::vector<Xorwow> rng;
     std::atomic<uint64_t> raysExt, raysEnv, raysLight;
-    Scene() : raysExt(0), raysEnv(0), raysLight(0) {}
+    // 0: the reference's binarySearch (S/HDRI.hpp:130-142), which returns the texel AFTER the one whose CDF interval holds r for about
+    //    half of all r (it stops on `to`, one past `from`, without a final comparison) while HDRI::pdf is evaluated for the texel it
+    //    returned: the texel distribution is ~(w_i + w_(i-1))/2 against a pdf of w_i.
+    // 1: exact inversion (the texel i with cdf[i] < r <= cdf[i+1]).  NOT the reference: the yardstick for the product's alias-table
+    //    mode (north_star), which samples the nominal weights w_i exactly and therefore shares THIS estimator's expectation.
+    int envSearchExact;
+    Scene() : raysExt(0), raysEnv(0), raysLight(0), envSearchExact(0) {}
 };
 
 // ----------------------------------------------------------------------------------------------
@@ -480,6 +486,11 @@ static int cdfSearch(const float* arr, float value, int length) {
     }
     return to;
 }
+static int cdfSearchExact(const float* arr, float value, int length) {     // smallest i with arr[i + 1] >= value
+    int lo = 0, hi = length - 1;
+    while (lo < hi) { int m = lo + (hi - lo) / 2; if (arr[m + 1] >= value) hi = m; else lo = m + 1; }
+    return lo;
+}
 static float hdriPdf(const Scene& S, int x, int y) {
     V3 dv = S.hdri.texel(x, y);
     float theta = (((float)y / (float)S.hdri.height)) * PIf;
@@ -658,7 +669,7 @@ static Ray cameraRay(const ElevenCamera& c, int x, int y, float r1, float r2, fl
 // S/kernel.cu:210-258 (HDRIIS branch).  Returns the contribution; pdf = 0 when occluded (defined UB).
 static V3 hdriLight(Scene& S, const Ray& ray, V3 point, const HitData& hd, float r1, float& pdf) {
     const Tex& t = S.hdri;
-    int count = cdfSearch(S.cdf.data(), r1, t.width * t.height);
+    int count = S.envSearchExact ? cdfSearchExact(S.cdf.data(), r1, t.width * t.height) : cdfSearch(S.cdf.data(), r1, t.width * t.height);
     float sx = (float)(count % t.width), sy = (float)(count / t.width);                      // HDRI::sample :154-162
     float nu = sx / (float)t.width, nv = sy / (float)t.height;
     float iu, iv; t.inverseTransformUV(nu, nv, iu, iv);
@@ -929,7 +940,7 @@ void orc_camera_ray(void* h, int x, int y, const float* r5, float* out6) {
 void orc_hdri_sample(void* h, const float* r, int n, int32_t* xy, float* dir3, float* pdf) {
     Scene& S = *(Scene*)h; const Tex& t = S.hdri;
     for (int i = 0; i < n; i++) {
-        int count = cdfSearch(S.cdf.data(), r[i], t.width * t.height);
+        int count = S.envSearchExact ? cdfSearchExact(S.cdf.data(), r[i], t.width * t.height) : cdfSearch(S.cdf.data(), r[i], t.width * t.height);
         int x = count % t.width, y = count / t.width;
         xy[2 * i] = x; xy[2 * i + 1] = y;
         float nu = (float)x / (float)t.width, nv = (float)y / (float)t.height, iu, iv;
@@ -939,6 +950,8 @@ void orc_hdri_sample(void* h, const float* r, int n, int32_t* xy, float* dir3, f
         pdf[i] = hdriPdf(S, (int)(iu * t.width), (int)(iv * t.height));
     }
 }
+// 0 = the reference's binarySearch (default), 1 = exact inversion (yardstick for the alias-table mode; see Scene::envSearchExact)
+void orc_set_env_search(void* h, int exact) { ((Scene*)h)->envSearchExact = exact ? 1 : 0; }
 void orc_hdri_cdf(void* h, float* cdf, float* radianceSum) {
     Scene& S = *(Scene*)h; if (cdf) memcpy(cdf, S.cdf.data(), S.cdf.size() * 4); *radianceSum = S.radianceSum;
 }

@@ -54,6 +54,7 @@ def lib():
         L.orc_camera_ray.argtypes = [vp, C.c_int, C.c_int, vp, vp]
         L.orc_hdri_sample.argtypes = [vp, vp, C.c_int, vp, vp, vp]
         L.orc_hdri_cdf.argtypes = [vp, vp, vp]
+        L.orc_set_env_search.argtypes = [vp, C.c_int]
         L.orc_spherical_mapping.argtypes = [vp, C.c_int, vp]
         L.orc_env_lookup.argtypes = [vp, vp, C.c_int, vp]
         L.orc_hitdata.argtypes = [vp, vp, C.c_int, vp]
@@ -135,6 +136,11 @@ class Oracle:
         pdf = np.zeros(len(r), np.float32)
         self.L.orc_hdri_sample(self.h, _p(r), len(r), _p(xy), _p(d), _p(pdf))
         return xy, d, pdf
+
+    def set_env_search(self, exact):
+        """False: the reference's binarySearch (default).  True: exact CDF inversion — NOT the reference (whose search returns the
+        next texel for half of the uniforms), the yardstick the alias-table mode is compared with."""
+        self.L.orc_set_env_search(self.h, 1 if exact else 0)
 
     def hdri_cdf(self):
         cdf = np.zeros(self.scene.hdri.width * self.scene.hdri.height + 1, np.float32)

@@ -59,22 +59,30 @@ def test_skip_null_nee_is_bit_identical(scenes, name):
 
 @pytest.mark.parametrize("name", ["clock", "zoo", "cornell", "grid"])
 def test_dead_path_termination_is_bit_identical(scenes, name):
-    """A path whose throughput is exactly 0 adds thr * (...) = 0 at every later bounce: stopping it leaves the radiance sum as it is.
-    (The one exception would be 0 * inf = NaN from a later bounce, which the reference would drop as a NaN sample: counted below.)"""
+    """A path whose throughput is exactly 0 adds thr * (...) = 0 at every later bounce: stopping it leaves the radiance sum as it is —
+    with ONE exception, and the test pins it: a later bounce of the dead path can produce 0 * inf = NaN (a zero pdf in a division),
+    which makes the reference DROP the whole sample (S/kernel.cu:449: NaN samples are not accumulated and not counted).  The
+    terminated path never gets there, so that sample is kept with the radiance it had.  Hence: every pixel is bit-identical in
+    all passes unless its accepted-sample count differs, the terminated render never counts FEWER samples, and the samples involved
+    are few (recorded; < 2 % of all samples on the scene that provokes it most, the displaced grid)."""
     sc = scenes[name]
-    a = R.Renderer(**BASE_FAST_RNG).render_setup(sc); a.render_cuda(8)
+    spp = 8
+    a = R.Renderer(**BASE_FAST_RNG).render_setup(sc); a.render_cuda(spp)
     cfg = dict(BASE_FAST_RNG); cfg["flags"] = R.FLAG_TERMINATE_DEAD_PATHS
-    b = R.Renderer(**cfg).render_setup(sc); b.render_cuda(8)
+    b = R.Renderer(**cfg).render_setup(sc); b.render_cuda(spp)
     fa, fb = a.film(), b.film()
     same = (bits(fa) == bits(fb)).all(-1)
-    ca, cb = a.get_sample_counts(), b.get_sample_counts()
+    ca, cb = a.get_sample_counts().reshape(same.shape), b.get_sample_counts().reshape(same.shape)
     m = record("terminate_" + name, identical_fraction=same.mean(), count_diff_pixels=int((ca != cb).sum()),
+               nan_dropped_samples_without=int(spp * ca.size - ca.sum()), nan_dropped_samples_with=int(spp * cb.size - cb.sum()),
+               sample_fraction_kept_instead_of_dropped=float((cb.astype(np.int64) - ca).sum() / (spp * ca.size)),
                ext_rays_without=a.stats()["rays_extension"], ext_rays_with=b.stats()["rays_extension"])
-    assert same.mean() >= 0.9999, m
-    assert (ca != cb).mean() <= 1e-4
+    assert (same | (ca != cb)).all(), m                             # equal counts => identical bits
+    assert (cb >= ca).all(), m                                      # termination only ever KEEPS a sample the other render dropped
+    assert (cb.astype(np.int64) - ca).sum() <= 0.02 * spp * ca.size, m
     for p in (R.PASS_NORMAL, R.PASS_TANGENT, R.PASS_BITANGENT):
-        assert (bits(a.film(p)) == bits(b.film(p))).all(-1).mean() >= 0.9999
-    assert b.stats()["rays_extension"] <= a.stats()["rays_extension"]
+        assert ((bits(a.film(p)) == bits(b.film(p))).all(-1) | (ca != cb)).all()
+    assert b.stats()["rays_extension"] < a.stats()["rays_extension"]
     a.close(); b.close()
 
 
@@ -108,24 +116,36 @@ def test_fast_math_alone_against_the_oracle(scenes, name):
 
 @pytest.mark.parametrize("name", ["clock", "zoo"])
 def test_alias_table_alone_against_the_oracle(scenes, name):
-    """PARITY + ELEVEN_ENV_ALIAS: another map from uniforms to texels with the same texel distribution (test_gpu_shading.py checks the
-    distribution itself): the image is a different realisation of the same estimator — compared with the ORACLE's at equal spp."""
+    """PARITY + ELEVEN_ENV_ALIAS: another map from uniforms to texels.  The alias table draws texel i with probability w_i, the pdf
+    the estimator divides by (test_gpu_shading.py checks that distribution against the oracle's CDF).  The REFERENCE's binarySearch
+    does not: for about half of the uniforms it returns the texel after the one whose CDF interval holds r (S/HDRI.hpp:130-142,
+    measured on the oracle: 50.4 % of the picks), while HDRI::pdf is evaluated for the returned texel — a biased estimator wherever
+    neighbouring texels differ (1.2 % of the image mean on the 128x64 environment of the zoo scene, nothing measurable on smooth ones).
+    So the yardstick for the alias mode is the oracle with EXACT CDF inversion (oracle_lib.Oracle.set_env_search(True): every other
+    line of the estimator is the reference's); the reference-search oracle is rendered too and the gap between the two recorded."""
     sc = scenes[name]
     spp = 64
     orc = O.Oracle(sc); orc.render(spp)
+    ref_search = orc.film(0)[..., :3].copy()
+    orc.reset(); orc.set_env_search(True); orc.render(spp)
     ref = orc.film(0)[..., :3]
     cfg = dict(R.PARITY); cfg["env_mode"] = R.ENV_ALIAS
     r = R.Renderer(**cfg).render_setup(sc); r.render_cuda(spp)
     img = r.film()[..., :3]
-    p = R.Renderer(**R.PARITY).render_setup(sc); p.render_cuda(spp)
-    par = p.film()[..., :3]
     med, p95 = _block_stats(img, ref)
-    # noise yardstick: two independent realisations differ by sqrt(2) sigma; the parity render IS the oracle's realisation, so
-    # RMSE(alias, oracle) is compared with the per-pixel standard error estimated from the oracle image's own block variance
-    m = record("alias_alone_" + name, mean_alias=img.mean(), mean_oracle=ref.mean(), mean_parity=par.mean(), median_block_rel=med, p95_block_rel=p95)
-    assert abs(img.mean() - ref.mean()) / ref.mean() < 0.01, m
+    # noise yardstick: image means of independent realisations of the SAME estimator (counter RNG, four seeds, alias table)
+    means = []
+    for seed in range(4):
+        f = R.Renderer(rng_mode=R.RNG_FAST, env_mode=R.ENV_ALIAS, hit_mode=R.HIT_KEY, flags=0, seed=100 + seed).render_setup(sc)
+        f.render_cuda(spp); means.append(float(f.film()[..., :3].mean())); f.close()
+    sigma = float(np.std(means, ddof=1))
+    m = record("alias_alone_" + name, mean_alias=img.mean(), mean_oracle_exact_inversion=ref.mean(), mean_oracle_reference_search=ref_search.mean(),
+               reference_search_bias=float((ref_search.mean() - ref.mean()) / ref.mean()), sigma_of_image_mean=sigma, seed_means=means,
+               median_block_rel=med, p95_block_rel=p95)
+    assert abs(img.mean() - ref.mean()) < max(5.0 * np.sqrt(2.0) * sigma, 0.002 * ref.mean()), m
+    assert abs(np.mean(means) - ref.mean()) < max(5.0 * sigma, 0.002 * ref.mean()), m
     assert med < 0.05, m
-    r.close(); p.close(); orc.close()
+    r.close(); orc.close()
 
 
 def test_snapshot_stream_serves_the_film_while_a_render_is_running(scenes):

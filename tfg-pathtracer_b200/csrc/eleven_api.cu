@@ -44,6 +44,9 @@ struct ElevenCtx {
     cudaStream_t stream = nullptr;               // render stream: every kernel of eleven_render / eleven_trace_* / uploads
     cudaStream_t snapStream = nullptr;           // snapshot stream: film / counter read-backs, concurrent with a running eleven_render
                                                  // (the reference polls getBuffers on its bufferStream while the kernel runs, S/kernel.cu:688-710)
+    cudaStream_t auxStream = nullptr;            // the shadow stage of bounce b runs here, concurrently with extend + classify of bounce b+1
+    cudaEvent_t evFork = nullptr, evJoin = nullptr;
+    bool overlap = true;                         // ELEVEN_OVERLAP=0 serialises the stages on the render stream (A/B knob)
     std::mutex snapMutex;                        // serialises the users of the snapshot stream and of d_resolve
     std::mutex statsMutex;                       // host-side ElevenStats fields written at the end of eleven_render
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evR0 = nullptr, evR1 = nullptr;
@@ -113,6 +116,10 @@ extern "C" int eleven_init(const ElevenConfig* cfg, ElevenCtx** out) {
     if (e == cudaSuccess) e = cudaDeviceGetStreamPriorityRange(&prLo, &prHi);
     // highest priority: the persistent render kernels fill every SM, so a snapshot's blocks are placed when the running kernel retires
     if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&c->snapStream, cudaStreamNonBlocking, prHi);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->auxStream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->evFork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->evJoin, cudaEventDisableTiming);
+    if (const char* ov = getenv("ELEVEN_OVERLAP")) c->overlap = atoi(ov) != 0;
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
     if (e == cudaSuccess) e = cudaEventCreate(&c->evR0);
@@ -130,11 +137,13 @@ extern "C" void eleven_destroy(ElevenCtx* c) {
     cudaSetDevice(c->cfg.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->snapStream) cudaStreamSynchronize(c->snapStream);
+    if (c->auxStream) cudaStreamSynchronize(c->auxStream);
     commDestroy(c);
     freeAll(c->sceneAllocs); freeAll(c->waveAllocs);
     if (c->d_reduced) cudaFree(c->d_reduced);
     if (c->bvhArena.base) cudaFree(c->bvhArena.base);
-    for (cudaEvent_t e : {c->ev0, c->ev1, c->evR0, c->evR1}) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : {c->ev0, c->ev1, c->evR0, c->evR1, c->evFork, c->evJoin}) if (e) cudaEventDestroy(e);
+    if (c->auxStream) cudaStreamDestroy(c->auxStream);
     for (cudaEvent_t e : c->evPool) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->snapStream) cudaStreamDestroy(c->snapStream);
@@ -485,22 +494,27 @@ static int persistentGrid(ElevenCtx* c, K kernel, const char* envOverride) {
     cache.push_back({(const void*)kernel, n});
     return c->numSMs * n;
 }
-#define LAUNCH_PERSISTENT(kernel, env, ...) kernel<<<persistentGrid(c, kernel, env), 128, 0, c->stream>>>(__VA_ARGS__)
+#define LAUNCH_PERSISTENT_ON(st, kernel, env, ...) kernel<<<persistentGrid(c, kernel, env), 128, 0, st>>>(__VA_ARGS__)
+#define LAUNCH_PERSISTENT(kernel, env, ...) LAUNCH_PERSISTENT_ON(c->stream, kernel, env, __VA_ARGS__)
 
-template <bool COUNT>
+template <bool COUNT, bool FM>
 static void launchExtend(ElevenCtx* c) {
-    if (c->cfg.hit_mode == ELEVEN_HIT_KEY) LAUNCH_PERSISTENT((k_extend<TRACE_CLOSEST_KEY, COUNT>), "ELEVEN_GRID_EXTEND", c->W, c->scene);
-    else LAUNCH_PERSISTENT((k_extend<TRACE_CLOSEST_T, COUNT>), "ELEVEN_GRID_EXTEND", c->W, c->scene);
+    if (c->cfg.hit_mode == ELEVEN_HIT_KEY) LAUNCH_PERSISTENT((k_extend<TRACE_CLOSEST_KEY, COUNT, FM>), "ELEVEN_GRID_EXTEND", c->W, c->scene);
+    else LAUNCH_PERSISTENT((k_extend<TRACE_CLOSEST_T, COUNT, FM>), "ELEVEN_GRID_EXTEND", c->W, c->scene);
 }
 // shadow stages of one bounce; the last one also performs the MIS combination (kernels_trace.cuh).  Returns launches.
-template <bool COUNT>
-static int launchConnect(ElevenCtx* c) {
-    if (c->scene.lightCount == 0) { LAUNCH_PERSISTENT((k_shadowEnv<false, COUNT>), "ELEVEN_GRID_SHADOW", c->W, c->scene); return 1; }
-    LAUNCH_PERSISTENT((k_shadowEnv<true, COUNT>), "ELEVEN_GRID_SHADOW", c->W, c->scene);
-    if (c->cfg.hit_mode == ELEVEN_HIT_KEY && !(c->cfg.flags & ELEVEN_FLAG_ANYHIT_LIGHT_SHADOWS)) LAUNCH_PERSISTENT((k_shadowLight<ELEVEN_HIT_KEY, COUNT>), "ELEVEN_GRID_SHADOW", c->W, c->scene);
-    else LAUNCH_PERSISTENT((k_shadowLight<ELEVEN_HIT_MIN_T, COUNT>), "ELEVEN_GRID_SHADOW", c->W, c->scene);
+template <bool COUNT, bool FM>
+static int launchConnect(ElevenCtx* c, cudaStream_t st) {
+    if (c->scene.lightCount == 0) { LAUNCH_PERSISTENT_ON(st, (k_shadowEnv<false, COUNT, FM>), "ELEVEN_GRID_SHADOW", c->W, c->scene); return 1; }
+    LAUNCH_PERSISTENT_ON(st, (k_shadowEnv<true, COUNT, FM>), "ELEVEN_GRID_SHADOW", c->W, c->scene);
+    if (c->cfg.hit_mode == ELEVEN_HIT_KEY && !(c->cfg.flags & ELEVEN_FLAG_ANYHIT_LIGHT_SHADOWS)) LAUNCH_PERSISTENT_ON(st, (k_shadowLight<ELEVEN_HIT_KEY, COUNT, FM>), "ELEVEN_GRID_SHADOW", c->W, c->scene);
+    else LAUNCH_PERSISTENT_ON(st, (k_shadowLight<ELEVEN_HIT_MIN_T, COUNT, FM>), "ELEVEN_GRID_SHADOW", c->W, c->scene);
     return 2;
 }
+template <bool FM>
+static void launchExtendRt(ElevenCtx* c, bool count) { if (count) launchExtend<true, FM>(c); else launchExtend<false, FM>(c); }
+template <bool FM>
+static int launchConnectRt(ElevenCtx* c, bool count, cudaStream_t st) { return count ? launchConnect<true, FM>(c, st) : launchConnect<false, FM>(c, st); }
 
 extern "C" int eleven_render(ElevenCtx* c, int spp) {
     if (!c) return fail(ELEVEN_ERR_ARG, "eleven_render: null context");
@@ -533,23 +547,42 @@ extern "C" int eleven_render(ElevenCtx* c, int spp) {
         if (fastMath) k_raygen<true><<<gridPaths, 256, 0, c->stream>>>(c->W, c->scene, c->P);
         else k_raygen<false><<<gridPaths, 256, 0, c->stream>>>(c->W, c->scene, c->P);
         mark(3);
+        // Stage overlap: the shadow stage of bounce b (reads the NEE records and queue, writes throughput / radiance) and extend +
+        // classify of bounce b+1 (read the new rays, write hits and the shading queue) touch disjoint data, so the shadow stage runs
+        // on the aux stream while the render stream goes on; they join in front of shade(b+1), which needs the throughput and
+        // re-uses the NEE queue.  Every traversal kernel is a persistent grid whose last rays leave most of the machine idle for
+        // 100-200 us: with two kernels in flight the one kernel's tail is filled by the other's CTAs.  Off with stage timing
+        // (the events would time overlapped stages) and with ELEVEN_OVERLAP=0.
+        const bool overlap = c->overlap && !timeK;
+        bool joinPending = false;
         for (uint32_t b = 0; b < c->cfg.max_bounces; b++) {
-            if (count) launchExtend<true>(c); else launchExtend<false>(c);
+            if (fastMath) launchExtendRt<true>(c, count); else launchExtendRt<false>(c, count);
             mark(0);
             LAUNCH_PERSISTENT(k_classify, nullptr, c->W, c->scene);
+            if (joinPending) { CK(cudaStreamWaitEvent(c->stream, c->evJoin, 0)); k_advance<<<1, 32, 0, c->stream>>>(c->W, c->scene.lightCount, 3); joinPending = false; }
             if (fastMath) LAUNCH_PERSISTENT(k_shade<true>, nullptr, c->W, c->scene, c->P);
             else LAUNCH_PERSISTENT(k_shade<false>, nullptr, c->W, c->scene, c->P);
             mark(1);
             k_advance<<<1, 32, 0, c->stream>>>(c->W, c->scene.lightCount, 0);
             mark(3);
-            c->stats.kernel_launches += count ? launchConnect<true>(c) : launchConnect<false>(c);
-            mark(2);
-            k_advance<<<1, 32, 0, c->stream>>>(c->W, c->scene.lightCount, 1);
-            mark(3);
+            if (overlap) {
+                CK(cudaEventRecord(c->evFork, c->stream));
+                CK(cudaStreamWaitEvent(c->auxStream, c->evFork, 0));
+                c->stats.kernel_launches += fastMath ? launchConnectRt<true>(c, count, c->auxStream) : launchConnectRt<false>(c, count, c->auxStream);
+                CK(cudaEventRecord(c->evJoin, c->auxStream));
+                joinPending = true;
+                k_advance<<<1, 32, 0, c->stream>>>(c->W, c->scene.lightCount, 2);
+            } else {
+                c->stats.kernel_launches += fastMath ? launchConnectRt<true>(c, count, c->stream) : launchConnectRt<false>(c, count, c->stream);
+                mark(2);
+                k_advance<<<1, 32, 0, c->stream>>>(c->W, c->scene.lightCount, 1);
+                mark(3);
+            }
             c->stats.extend_launches += 1;
             std::swap(c->W.qCur, c->W.qNext);      // kernel arguments are captured at launch: the next bounce reads the list just written
             c->stats.kernel_launches += 5;
         }
+        if (joinPending) { CK(cudaStreamWaitEvent(c->stream, c->evJoin, 0)); k_advance<<<1, 32, 0, c->stream>>>(c->W, c->scene.lightCount, 3); }
         k_accumulate<<<gridPaths, 256, 0, c->stream>>>(c->W, logK);
         mark(3);
         c->stats.kernel_launches += 2;

@@ -61,13 +61,14 @@ struct WaveState {
 };
 
 // slots of a path's NEE line
-enum { NEE_ENV_DIR = 0,                  // w_e.xyz, p_e        } sector 0: all the environment shadow ray needs
-       NEE_POS = 1,                      // hit position P      }
+enum { NEE_ENV_DIR = 0,                  // direction of the environment shadow ray (w_e as Ray's ctor re-normalises it), p_e   } sector 0: all the
+       NEE_POS = 1,                      // its origin P + 0.001 w_e                                                               } shadow ray needs
        NEE_ENV_C = 2,                    // C_e.xyz, p_b        } sector 1: the rest of the MIS combination
        NEE_THR_MUL = 3,                  // f*cos/p_b (throughput update factor)
        NEE_BRDF_C = 4,                   // C_b.xyz (only with emission)
        NEE_LIGHT_DIR = 5,                // w_l.xyz, dist (only with point lights)
        NEE_LIGHT_C = 6,                  // C_p.xyz, p_p
+       NEE_HITPOS = 7,                   // hit position P (only with point lights: origin of the light shadow ray)
        NEE_STRIDE = 8 };
 __device__ __forceinline__ float4& neeRec(const WaveState& W, uint32_t pid, int k) { return W.nee[(size_t)pid * NEE_STRIDE + k]; }
 
@@ -220,6 +221,9 @@ __device__ __forceinline__ void appendWarpAggregated(uint32_t* q, uint32_t* coun
     q[base + __popc(mask & ((1u << lane) - 1u))] = value;
 }
 
+#ifndef EL_SHADE_PREFETCH
+#define EL_SHADE_PREFETCH 1
+#endif
 #ifndef EL_SHADE_MIN_CTAS
 #define EL_SHADE_MIN_CTAS 6      /* 80 registers, 24 warps/SM: the kernel waits on texture gathers (ncu: long_scoreboard), measured -11 % vs 91 registers */
 #endif
@@ -233,6 +237,29 @@ __global__ void __launch_bounds__(128, EL_SHADE_MIN_CTAS) k_shade(WaveState W, c
 #pragma unroll
     for (int b = 0; b < EL_BUCKETS; b++) prefix[b + 1] = prefix[b] + W.cnt[CNT_BUCKET0 + b];
     const uint32_t n = prefix[EL_BUCKETS];
+    // queue position -> path id through the bucket prefix sums
+    auto queueEntry = [&](uint32_t qi) -> uint32_t {
+        uint32_t b = 0;
+#pragma unroll
+        for (int k = 1; k < EL_BUCKETS; k++) b += (qi >= prefix[k]) ? 1u : 0u;
+        return W.qBucket[(size_t)b * W.pathCapacity + (qi - prefix[b])];
+    };
+#if EL_SHADE_PREFETCH
+    // Software pipeline over the warp's queue blocks: the chain queue entry -> hit record -> triangle -> texel is four dependent
+    // gathers (ncu: long_scoreboard 4.2 warps per issue cycle, issue 54 %).  The NEXT block's work fetch, queue entry and hit record
+    // are requested while the current block is shaded, so an iteration starts with the triangle index already in registers.
+    uint32_t base = warpFetch(&W.cnt[CNT_WORK_SHADE], lane);
+    uint32_t pid = 0; float4 hv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (base + lane < n) { pid = queueEntry(base + lane); hv = W.hit[pid]; }
+    for (;;) {
+        if (base >= n) break;
+        const uint32_t qi = base + lane;
+        const uint32_t nbase = warpFetch(&W.cnt[CNT_WORK_SHADE], lane);
+        uint32_t npid = 0; float4 nhv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (nbase + lane < n) npid = queueEntry(nbase + lane);
+        bool toNee = false, toNext = false;
+        if (qi < n) {
+#else
     for (;;) {
         const uint32_t base = warpFetch(&W.cnt[CNT_WORK_SHADE], lane);
         if (base >= n) break;
@@ -240,11 +267,9 @@ __global__ void __launch_bounds__(128, EL_SHADE_MIN_CTAS) k_shade(WaveState W, c
         bool toNee = false, toNext = false;
         uint32_t pid = 0;
         if (qi < n) {
-            uint32_t b = 0;
-#pragma unroll
-            for (int k = 1; k < EL_BUCKETS; k++) b += (qi >= prefix[k]) ? 1u : 0u;
-            pid = W.qBucket[(size_t)b * W.pathCapacity + (qi - prefix[b])];
+            pid = queueEntry(qi);
             const float4 hv = W.hit[pid];
+#endif
             const int tri = __float_as_int(hv.x);
             const float4 o4 = W.ray[2 * (size_t)pid], d4 = W.ray[2 * (size_t)pid + 1];
             Ray ray; ray.o = f3(o4.x, o4.y, o4.z); ray.d = f3(d4.x, d4.y, d4.z);
@@ -294,6 +319,9 @@ __global__ void __launch_bounds__(128, EL_SHADE_MIN_CTAS) k_shade(WaveState W, c
                 const float4* tp = S.shadeTris + (size_t)tri * 9;
                 const float4 q4 = __ldg(tp + 4), q5 = __ldg(tp + 5), q6 = __ldg(tp + 6), q7 = __ldg(tp + 7), q8 = __ldg(tp + 8);
                 const TriGeom g = loadTriGeom(S.shadeTris, tri);
+#if EL_SHADE_PREFETCH
+                if (nbase + lane < n) nhv = W.hit[npid];            // the next block's hit record: requested behind this path's own gathers
+#endif
                 F3 N;
                 const F3 Pp = hitPosition(ray, g, t, u, v, N);
                 const F3 t0 = f3(q4.z, q4.w, q5.x), t1 = f3(q5.y, q5.z, q5.w), t2 = f3(q6.x, q6.y, q6.z);
@@ -342,12 +370,17 @@ __global__ void __launch_bounds__(128, EL_SHADE_MIN_CTAS) k_shade(WaveState W, c
                 const F3 mulB = f3(M<FM>::div(fB.x * cB, pB), M<FM>::div(fB.y * cB, pB), M<FM>::div(fB.z * cB, pB));
                 const F3 CB = hd.emission * mulB;
 
-                neeRec(W, pid, NEE_ENV_DIR) = make_float4(wE.x, wE.y, wE.z, pE);
+                // the environment shadow ray, complete: Ray(point + newDir*0.001, newDir) with the constructor's normalisation
+                // (S/kernel.cu:246, S/Ray.hpp:14-18).  Same operations as before, moved here from the shadow kernel's ray set-up, where
+                // they were 7-8 % of an issue-bound kernel's instructions; this kernel waits on gathers and has the slots free.
+                const Ray er = makeRay(ex::madd(Pp, wE, 0.001f), wE);
+                neeRec(W, pid, NEE_ENV_DIR) = make_float4(er.d.x, er.d.y, er.d.z, pE);
                 neeRec(W, pid, NEE_ENV_C) = make_float4(CE.x, CE.y, CE.z, pB);
-                neeRec(W, pid, NEE_POS) = make_float4(Pp.x, Pp.y, Pp.z, 0.f);
+                neeRec(W, pid, NEE_POS) = make_float4(er.o.x, er.o.y, er.o.z, 0.f);
                 neeRec(W, pid, NEE_THR_MUL) = make_float4(mulB.x, mulB.y, mulB.z, 0.f);
                 if (W.sceneHasEmission) neeRec(W, pid, NEE_BRDF_C) = make_float4(CB.x, CB.y, CB.z, 0.f);
                 if (S.lightCount > 0) {
+                    neeRec(W, pid, NEE_HITPOS) = make_float4(Pp.x, Pp.y, Pp.z, 0.f);
                     neeRec(W, pid, NEE_LIGHT_DIR) = make_float4(wL.x, wL.y, wL.z, dist);
                     neeRec(W, pid, NEE_LIGHT_C) = make_float4(CP.x, CP.y, CP.z, pP);
                 }
@@ -378,6 +411,10 @@ __global__ void __launch_bounds__(128, EL_SHADE_MIN_CTAS) k_shade(WaveState W, c
         }
         appendWarpAggregated(W.qNee, &W.cnt[CNT_NEE], toNee, pid);
         appendWarpAggregated(W.qNext, &W.cnt[CNT_NEXT], toNext, pid);
+#if EL_SHADE_PREFETCH
+        if (nbase + lane < n && !(qi < n && __float_as_int(hv.x) >= 0)) nhv = W.hit[npid];   // lanes that shaded no hit this round (escaped ray / ragged end) have not asked yet
+        base = nbase; pid = npid; hv = nhv;
+#endif
     }
 }
 
@@ -390,10 +427,16 @@ __global__ void k_advance(WaveState W, uint32_t lights, int phase) {
         W.stats[ST_RAYS_ENV] += W.cnt[CNT_NEE];
         if (lights) W.stats[ST_RAYS_LIGHT] += W.cnt[CNT_NEE];
         W.cnt[CNT_WORK_CONNECT] = 0u; W.cnt[CNT_WORK_LIGHT] = 0u;
-    } else {                     // after connect: next bounce
+    } else if (phase == 1) {     // after connect: next bounce
         W.cnt[CNT_CUR] = W.cnt[CNT_NEXT]; W.cnt[CNT_NEXT] = 0u; W.cnt[CNT_NEE] = 0u;
         W.cnt[CNT_WORK_TRACE] = 0u; W.cnt[CNT_WORK_SHADE] = 0u; W.cnt[CNT_WORK_CLASSIFY] = 0u;
         for (int b = 0; b < EL_BUCKETS; b++) W.cnt[CNT_BUCKET0 + b] = 0u;
+    } else if (phase == 2) {     // stage overlap: the next bounce's extend + classify start while connect still reads the NEE queue
+        W.cnt[CNT_CUR] = W.cnt[CNT_NEXT]; W.cnt[CNT_NEXT] = 0u;
+        W.cnt[CNT_WORK_TRACE] = 0u; W.cnt[CNT_WORK_SHADE] = 0u; W.cnt[CNT_WORK_CLASSIFY] = 0u;
+        for (int b = 0; b < EL_BUCKETS; b++) W.cnt[CNT_BUCKET0 + b] = 0u;
+    } else {                     // stage overlap: connect has finished, shade may refill the NEE queue
+        W.cnt[CNT_NEE] = 0u;
     }
 }
 

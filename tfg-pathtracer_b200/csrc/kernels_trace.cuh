@@ -14,6 +14,9 @@
 
 namespace eleven {
 
+#ifndef EL_FAST_TRI
+#define EL_FAST_TRI 1            /* fast-math configuration: Moeller-Trumbore with contracted multiply-adds and MUFU reciprocal (mollerTrumboreFast) */
+#endif
 #ifndef EL_EXTEND_MIN_CTAS
 #define EL_EXTEND_MIN_CTAS 7      /* <= 72 registers, 7 CTAs per SM: no spills; 64 registers x 8 CTAs measured equal (but spills in KEY mode), no bound (93 registers x 5 CTAs) is 13 % slower */
 #endif
@@ -38,11 +41,11 @@ struct ExtendSink {
         W.hitBucket[lr.tag] = h.tri < 0 ? (uint8_t)EL_MISS_BUCKET : (uint8_t)min((uint32_t)__ldg(S.triMaterial + h.tri), (uint32_t)(EL_MISS_BUCKET - 1));
     }
 };
-template <int MODE, bool COUNT>
+template <int MODE, bool COUNT, bool FM>
 __global__ void __launch_bounds__(128, EL_EXTEND_MIN_CTAS) k_extend(const __grid_constant__ WaveState W, const __grid_constant__ DevScene S) {
     TraceCounters tc; tc.nodes = 0; tc.tris = 0; tc.keys = 0;
     ExtendSource src{W}; ExtendSink sink{W, S};
-    traceQueue<MODE, COUNT, false>(S, W.cnt[CNT_CUR], &W.cnt[CNT_WORK_TRACE], src, sink, tc);
+    traceQueue<MODE, COUNT, false, FM && EL_FAST_TRI>(S, W.cnt[CNT_CUR], &W.cnt[CNT_WORK_TRACE], src, sink, tc);
     if (COUNT) {
         atomicAdd(&W.stats[ST_NODES], (unsigned long long)tc.nodes); atomicAdd(&W.stats[ST_TRIS], (unsigned long long)tc.tris); atomicAdd(&W.stats[ST_KEYS], (unsigned long long)tc.keys);
         atomicAdd(&W.stats[ST_NODES_EXT], (unsigned long long)tc.nodes); atomicAdd(&W.stats[ST_TRIS_EXT], (unsigned long long)tc.tris);
@@ -92,8 +95,7 @@ struct ShadowEnvSource {
     __device__ __forceinline__ void load(uint32_t qi, LaneRay& lr) const {
         const uint32_t pid = W.qNee[qi];
         const float4 p = neeRec(W, pid, NEE_POS), e = neeRec(W, pid, NEE_ENV_DIR);
-        const F3 w = f3(e.x, e.y, e.z);
-        lr.ray = makeRay(ex::madd(f3(p.x, p.y, p.z), w, 0.001f), w);      // Ray(point + newDir*0.001, newDir), S/kernel.cu:246
+        lr.ray.o = f3(p.x, p.y, p.z); lr.ray.d = f3(e.x, e.y, e.z);       // Ray(point + newDir*0.001, newDir), S/kernel.cu:246: built by k_shade
         lr.tmaxAny = INFINITY; lr.tag = pid;
     }
 };
@@ -106,11 +108,11 @@ struct ShadowEnvSink {
         else misCombine(W, lr.tag, false, occluded, false);
     }
 };
-template <bool LIGHTS, bool COUNT>
+template <bool LIGHTS, bool COUNT, bool FM>
 __global__ void __launch_bounds__(128) k_shadowEnv(const __grid_constant__ WaveState W, const __grid_constant__ DevScene S) {
     TraceCounters tc; tc.nodes = 0; tc.tris = 0; tc.keys = 0;
     ShadowEnvSource src{W}; ShadowEnvSink<LIGHTS> sink{W};
-    traceQueue<TRACE_ANY, COUNT, false>(S, W.cnt[CNT_NEE], &W.cnt[CNT_WORK_CONNECT], src, sink, tc);
+    traceQueue<TRACE_ANY, COUNT, false, FM && EL_FAST_TRI>(S, W.cnt[CNT_NEE], &W.cnt[CNT_WORK_CONNECT], src, sink, tc);
     if (COUNT) { atomicAdd(&W.stats[ST_NODES], (unsigned long long)tc.nodes); atomicAdd(&W.stats[ST_TRIS], (unsigned long long)tc.tris); atomicAdd(&W.stats[ST_KEYS], (unsigned long long)tc.keys); }
 }
 
@@ -120,7 +122,7 @@ struct ShadowLightSource {
     const WaveState& W;
     __device__ __forceinline__ void load(uint32_t qi, LaneRay& lr) const {
         const uint32_t pid = W.qNee[qi];
-        const float4 p = neeRec(W, pid, NEE_POS), l = neeRec(W, pid, NEE_LIGHT_DIR);
+        const float4 p = neeRec(W, pid, NEE_HITPOS), l = neeRec(W, pid, NEE_LIGHT_DIR);
         const F3 w = f3(l.x, l.y, l.z);
         lr.ray = makeRay(ex::madd(f3(p.x, p.y, p.z), w, 0.001f), w);      // S/kernel.cu:192
         lr.tmaxAny = HITMODE == ELEVEN_HIT_KEY ? INFINITY : l.w - 0.001f;
@@ -135,7 +137,7 @@ struct ShadowLightSink {
         bool occluded = h.tri >= 0;
         if (HITMODE == ELEVEN_HIT_KEY && occluded) {
             // the reference takes the CLOSEST hit and compares |hit.position - point| with the light distance (S/kernel.cu:193-197)
-            const float4 p = neeRec(W, pid, NEE_POS);
+            const float4 p = neeRec(W, pid, NEE_HITPOS);
             const TriGeom g = loadTriGeom(S.shadeTris, h.tri);
             F3 sn;
             const F3 hp = hitPosition(lr.ray, g, h.t, h.u, h.v, sn);
@@ -145,11 +147,11 @@ struct ShadowLightSink {
         misCombine(W, pid, true, envOccluded, occluded);
     }
 };
-template <int HITMODE, bool COUNT>
+template <int HITMODE, bool COUNT, bool FM>
 __global__ void __launch_bounds__(128) k_shadowLight(const __grid_constant__ WaveState W, const __grid_constant__ DevScene S) {
     TraceCounters tc; tc.nodes = 0; tc.tris = 0; tc.keys = 0;
     ShadowLightSource<HITMODE> src{W}; ShadowLightSink<HITMODE> sink{W, S};
-    traceQueue<(HITMODE == ELEVEN_HIT_KEY ? TRACE_CLOSEST_KEY : TRACE_ANY), COUNT, false>(S, W.cnt[CNT_NEE], &W.cnt[CNT_WORK_LIGHT], src, sink, tc);
+    traceQueue<(HITMODE == ELEVEN_HIT_KEY ? TRACE_CLOSEST_KEY : TRACE_ANY), COUNT, false, FM && EL_FAST_TRI>(S, W.cnt[CNT_NEE], &W.cnt[CNT_WORK_LIGHT], src, sink, tc);
     if (COUNT) { atomicAdd(&W.stats[ST_NODES], (unsigned long long)tc.nodes); atomicAdd(&W.stats[ST_TRIS], (unsigned long long)tc.tris); atomicAdd(&W.stats[ST_KEYS], (unsigned long long)tc.keys); }
 }
 
@@ -174,7 +176,7 @@ __global__ void __launch_bounds__(128) k_traceBatch(const float* __restrict__ ra
                                                   const __grid_constant__ DevScene S, uint32_t* workCounter, unsigned long long* stats) {
     TraceCounters tc; tc.nodes = 0; tc.tris = 0; tc.keys = 0;
     BatchSource src{rays}; BatchSink sink{hits};
-    traceQueue<MODE, COUNT, true>(S, n, workCounter, src, sink, tc);
+    traceQueue<MODE, COUNT, true, false>(S, n, workCounter, src, sink, tc);      // the closest-hit contract: always the exact test
     if (COUNT && stats) { atomicAdd(&stats[ST_NODES], (unsigned long long)tc.nodes); atomicAdd(&stats[ST_TRIS], (unsigned long long)tc.tris); atomicAdd(&stats[ST_KEYS], (unsigned long long)tc.keys); }
 }
 

@@ -86,7 +86,7 @@ __device__ __forceinline__ void traceLutInit(TraceLut& L) {
     __syncthreads();
 }
 
-template <int MODE, bool COUNT, bool NEED_KEY, class Source, class Sink>
+template <int MODE, bool COUNT, bool NEED_KEY, bool FAST_TRI, class Source, class Sink>
 __device__ __forceinline__ void traceQueue(const DevScene& S, uint32_t n, uint32_t* workCounter, Source& src, Sink& sink, TraceCounters& tc) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t FULL = 0xffffffffu;
@@ -282,7 +282,9 @@ __device__ __forceinline__ void traceQueue(const DevScene& S, uint32_t n, uint32
                 const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
                 if (COUNT) tc.tris++;
                 float t, u, v;
-                if (mollerTrumbore(lr.ray, f3(a.x, a.y, a.z), f3(a.w, b.x, b.y), f3(b.z, b.w, c.x), t, u, v)) {
+                const bool triHit = FAST_TRI ? mollerTrumboreFast(lr.ray, f3(a.x, a.y, a.z), f3(a.w, b.x, b.y), f3(b.z, b.w, c.x), t, u, v)
+                                             : mollerTrumbore(lr.ray, f3(a.x, a.y, a.z), f3(a.w, b.x, b.y), f3(b.z, b.w, c.x), t, u, v);
+                if (triHit) {
                     const int tri = __float_as_int(c.y);
                     if (MODE == TRACE_ANY) {
                         if (t < lr.tmaxAny) {

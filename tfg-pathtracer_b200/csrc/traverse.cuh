@@ -41,6 +41,25 @@ __device__ __forceinline__ bool mollerTrumbore(const Ray& r, F3 v0, F3 e1, F3 e2
     return true;
 }
 
+// The same test in the arithmetic of the reference's SHIPPING build (-use_fast_math: contracted multiply-adds, MUFU reciprocal): the
+// render kernels of the fast-math configuration use it; (t, u, v) differ from the exact ones by rounding only.  The closest-hit
+// contract (eleven_trace_closest, the parity configuration) always runs mollerTrumbore above.
+__device__ __forceinline__ bool mollerTrumboreFast(const Ray& r, F3 v0, F3 e1, F3 e2, float& t, float& u, float& v) {
+    const float EPSILON = 0.0000001f;
+    const float px = fmaf(r.d.y, e2.z, -(r.d.z * e2.y)), py = fmaf(r.d.z, e2.x, -(r.d.x * e2.z)), pz = fmaf(r.d.x, e2.y, -(r.d.y * e2.x));
+    const float det = fmaf(e1.x, px, fmaf(e1.y, py, e1.z * pz));
+    if (fabsf(det) < EPSILON) return false;
+    const float inv_det = __fdividef(1.0f, det);
+    const float tx = r.o.x - v0.x, ty = r.o.y - v0.y, tz = r.o.z - v0.z;
+    u = fmaf(tx, px, fmaf(ty, py, tz * pz)) * inv_det;
+    if (u < 0.0f || u > 1.0f) return false;
+    const float qx = fmaf(ty, e1.z, -(tz * e1.y)), qy = fmaf(tz, e1.x, -(tx * e1.z)), qz = fmaf(tx, e1.y, -(ty * e1.x));
+    v = fmaf(r.d.x, qx, fmaf(r.d.y, qy, r.d.z * qz)) * inv_det;
+    if (v < 0.0f || u + v > 1.0f) return false;
+    t = fmaf(e2.x, qx, fmaf(e2.y, qy, e2.z * qz)) * inv_det;
+    return t >= 0.0f;
+}
+
 // ---- S/Tri.hpp:70-92: hit position with the shadow-terminator shift ---------------------------------
 struct TriGeom { F3 v0, v1, v2, n0, n1, n2; };
 

@@ -212,25 +212,6 @@ static ElevenMaterial defaultMaterial() {          // Material.hpp:12-36
     return m;
 }
 
-static void computeTangents(ElevenTri& T) {
-    const float* P0 = T.vertices[0]; float e1[3], e2[3];
-    for (int a = 0; a < 3; a++) { e1[a] = T.vertices[1][a] - P0[a]; e2[a] = T.vertices[2][a] - P0[a]; }
-    const float du1 = T.uv[1][0] - T.uv[0][0], dv1 = T.uv[1][1] - T.uv[0][1], du2 = T.uv[2][0] - T.uv[0][0], dv2 = T.uv[2][1] - T.uv[0][1];
-    const float det = du1 * dv2 - du2 * dv1;
-    float tg[3], bt[3];
-    if (fabsf(det) > 1e-20f) { const float r = 1.f / det; for (int a = 0; a < 3; a++) { tg[a] = (e1[a] * dv2 - e2[a] * dv1) * r; bt[a] = (e2[a] * du1 - e1[a] * du2) * r; } }
-    else for (int a = 0; a < 3; a++) { tg[a] = e1[a]; bt[a] = e2[a]; }
-    const float gn[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};
-    const float cx[3] = {gn[1] * tg[2] - gn[2] * tg[1], gn[2] * tg[0] - gn[0] * tg[2], gn[0] * tg[1] - gn[1] * tg[0]};
-    T.tangentsSign = (cx[0] * bt[0] + cx[1] * bt[1] + cx[2] * bt[2]) < 0 ? -1.f : 1.f;
-    for (int k = 0; k < 3; k++) {
-        const float* n = T.normals[k]; const float d = n[0] * tg[0] + n[1] * tg[1] + n[2] * tg[2];
-        float t[3] = {tg[0] - n[0] * d, tg[1] - n[1] * d, tg[2] - n[2] * d};
-        const float l = sqrtf(t[0] * t[0] + t[1] * t[1] + t[2] * t[2]);
-        for (int a = 0; a < 3; a++) T.tangents[k][a] = l > 1e-20f ? t[a] / l : 0.f;
-    }
-}
-
 static bool loadDir(std::string dir, LoadedScene& s, std::string& err) {
     if (!dir.empty() && dir.back() != '/') dir += '/';
     std::string text;
@@ -302,9 +283,12 @@ static bool loadDir(std::string dir, LoadedScene& s, std::string& err) {
     // geometry (S/ObjLoader.hpp:71-171)
     std::ifstream obj(dir + "scene.obj");
     if (!obj) { err = "cannot open " + dir + "scene.obj"; return false; }
-    std::vector<float> V, VT, VN; int object = -1; std::string objMtl;
+    std::vector<float> V, VT, VN; int object = -1; std::string objMtl; size_t objectFirstTri = 0;
     auto closeObject = [&]() {
         if (object < 0) return;
+        // tangent frames per object, like CalcTangents::calc(&mo) at the end of parseObj (S/ObjLoader.hpp:167-168)
+        computeTangentSpace(s.tris.data() + objectFirstTri, s.tris.size() - objectFirstTri);
+        objectFirstTri = s.tris.size();
         int mid = 0; for (size_t j = 0; j < s.materialNames.size(); j++) if (s.materialNames[j] == objMtl) mid = (int)j;
         s.objectMaterial.push_back(mid);
     };
@@ -333,7 +317,7 @@ static bool loadDir(std::string dir, LoadedScene& s, std::string& err) {
                 }
                 corner++;
             }
-            if (corner == 3) { computeTangents(T); s.tris.push_back(T); }
+            if (corner == 3) s.tris.push_back(T);
         }
     }
     closeObject();

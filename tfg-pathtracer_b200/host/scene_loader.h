@@ -12,9 +12,8 @@
  *               bottom image row (the reference flips on load, S/Texture.hpp:49); texture ids in the reference's order
  *               (per material: map_Bump, map_Kd, map_Ns, refl — its std::map iteration order), de-duplicated by path
  *   HDRI/<name>.hdr  Radiance RGBE (flat or new-RLE), not flipped; or a 1024x1024 constant colour (S/HDRI.hpp:22-38)
- * Known difference: tangents come from a per-triangle UV-gradient frame orthogonalised against the vertex normals, not
- * from MikkTSpace (vendored third-party code in the reference, S/mikktspace.cpp).  They only enter the image through
- * normal maps and the TANGENT/BITANGENT AOVs; parity runs against the reference use the scene dump of its own loader.
+ *   tangents    Mikkelsen tangent space per `o` object, as the reference computes it through its vendored mikktspace
+ *               (tangent_space.cpp; pinned against the reference loader's own output, tests/test_host_cli.py)
  */
 #ifndef ELEVEN_SCENE_LOADER_H
 #define ELEVEN_SCENE_LOADER_H
@@ -43,6 +42,9 @@ struct LoadedScene {
 /* Loads <dir>/scene.json + scene.mtl + scene.obj (reference layout) or, if `path` is a file, an ELVNSCN1 flat container. */
 bool loadScene(const std::string& path, LoadedScene& out, std::string& err);
 bool saveFlat(const LoadedScene& s, const std::string& path, std::string& err);
+
+/* Per-corner tangents + Tri::tangentsSign of one mesh object (S/ObjLoader.hpp:167-168 -> S/mikktspaceCallback.hpp). */
+void computeTangentSpace(ElevenTri* tris, size_t n);
 
 bool readBmp24(const std::string& path, int& w, int& h, std::vector<unsigned char>& rgbBottomUp, std::string& err);
 bool readHdr(const std::string& path, int& w, int& h, std::vector<float>& rgbTopDown, std::string& err);

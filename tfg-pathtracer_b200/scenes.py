@@ -663,6 +663,72 @@ def material_zoo(xres=160, yres=90, seed=23, lights=1, env_size=(128, 64)):
     return base
 
 
+def tangent_torture(seed=5):
+    """Mesh that exercises every branch of the loader's tangent-space pass (host/tangent_space.cpp; the reference: mikktspace through
+    S/mikktspaceCallback.hpp): a UV sphere whose seam duplicates vertices with different texture coordinates, one hemisphere with a
+    MIRRORED mapping (orientation flips: groups must not cross it), flat-shaded and smooth-shaded parts, triangles with two equal
+    positions (degenerate: borrow a neighbour's frame), triangles whose three texture coordinates coincide or are collinear (no
+    derivative: "group with anything"), two fans glued along one edge used by four triangles (butterfly), an isolated triangle with a
+    degenerate mapping (keeps the default frame), as a second object a plane with rotated / scaled UV islands."""
+    rng = np.random.RandomState(seed)
+    P, UV, N = [], [], []
+    nu, nv = 24, 12
+    def sph(i, j):
+        th, ph = np.pi * j / nv, 2 * np.pi * i / nu
+        p = np.array([np.sin(th) * np.cos(ph), np.cos(th), np.sin(th) * np.sin(ph)])
+        return 0.5 * p * (1 + 0.15 * np.sin(3 * ph) * np.sin(2 * th)), p
+    for j in range(nv):
+        for i in range(nu):
+            q = [(i, j), (i + 1, j), (i + 1, j + 1), (i, j + 1)]
+            pts = [sph(*c) for c in q]
+            uvs = [np.array([c[0] / nu, c[1] / nv]) for c in q]
+            if i >= nu // 2:
+                uvs = [np.array([1.0 - u[0], u[1]]) for u in uvs]                      # mirrored island
+            for tri in ((0, 1, 2), (0, 2, 3)):
+                pp = np.array([pts[k][0] for k in tri]); nn = np.array([pts[k][1] for k in tri])
+                if j in (3, 4):                                                        # a flat-shaded band
+                    fn = np.cross(pp[1] - pp[0], pp[2] - pp[0]); fn = fn / (np.linalg.norm(fn) + 1e-30)
+                    nn = np.repeat(fn[None], 3, 0)
+                P.append(pp); N.append(nn); UV.append(np.array([uvs[k] for k in tri]))
+    P, UV, N = [np.array(x) for x in (P, UV, N)]
+    n0 = len(P)
+    pick = rng.choice(n0, 40, replace=False)
+    P[pick[:10], 1] = P[pick[:10], 0]                                                  # two equal positions
+    UV[pick[10:20]] = UV[pick[10:20], :1]                                              # all three texture coordinates equal
+    UV[pick[20:30], 2] = 0.5 * (UV[pick[20:30], 0] + UV[pick[20:30], 1])               # collinear texture coordinates
+    UV[pick[30:40]] = UV[pick[30:40]][:, ::-1]                                         # locally flipped mapping inside an island
+    # butterfly: four triangles on one edge
+    a, b = np.array([0.0, 1.2, 0.0]), np.array([0.0, 1.6, 0.0])
+    wings = [np.array([0.4, 1.4, 0.0]), np.array([-0.4, 1.4, 0.1]), np.array([0.0, 1.4, 0.4]), np.array([0.1, 1.4, -0.4])]
+    for k, w in enumerate(wings):
+        pp = np.array([a, b, w]) if k % 2 == 0 else np.array([b, a, w])
+        fn = np.cross(pp[1] - pp[0], pp[2] - pp[0]); fn /= np.linalg.norm(fn)
+        P = np.concatenate([P, pp[None]]); N = np.concatenate([N, np.repeat(fn[None], 3, 0)[None]])
+        UV = np.concatenate([UV, np.array([[0.0, 0.0], [0.0, 1.0], [1.0, 0.5]])[None] if k % 2 == 0 else np.array([[0.0, 1.0], [0.0, 0.0], [1.0, 0.5]])[None]])
+    # isolated triangle without a mapping
+    P = np.concatenate([P, np.array([[[2.0, 0, 0], [2.5, 0, 0], [2.0, 0.5, 0]]])]); N = np.concatenate([N, np.array([[[0, 0, 1.0]] * 3])])
+    UV = np.concatenate([UV, np.zeros((1, 3, 2))])
+    t0 = make_tris(P, UV, N, 0)
+    # second object: plane with rotated / scaled UV islands
+    g = 10
+    P2, UV2, N2 = [], [], []
+    for y in range(g):
+        for x in range(g):
+            c = np.array([[x, 0, y], [x + 1, 0, y], [x + 1, 0, y + 1], [x, 0, y + 1]], np.float64) / g - np.array([0.5, 0.8, 0.5])
+            ang = 0.7 * ((x // 3) + 2 * (y // 3)); s_ = 1.0 + 0.5 * ((x // 3) % 2)
+            R = np.array([[np.cos(ang), -np.sin(ang)], [np.sin(ang), np.cos(ang)]]) * s_
+            uv = (np.array([[x, y], [x + 1, y], [x + 1, y + 1], [x, y + 1]], np.float64) / g) @ R.T
+            for tri in ((0, 2, 1), (0, 3, 2)):
+                P2.append(c[list(tri)]); UV2.append(uv[list(tri)]); N2.append(np.array([[0, 1.0, 0]] * 3))
+    t1 = make_tris(np.array(P2), np.array(UV2), np.array(N2), 1)
+    base = cornell_box(32)
+    base.tris = np.concatenate([t0, t1])
+    base.object_material = np.zeros(2, np.int32)
+    base.object_names = ["blob", "plane"]
+    base.name = "tangent_torture"
+    return base
+
+
 def textured_lights(xres=3840, yres=2160, tex_res=4096, seed=11):
     """Config 5: C1-style textured materials + 4 point lights + defocus + env at 3840x2160."""
     s = clock_standin(seed, tex_res, xres, yres, lights=4)
