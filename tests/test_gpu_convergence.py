@@ -82,8 +82,15 @@ def test_config3_1000spp_full_frame_against_the_reference_render():
     from tfg_pathtracer_b200 import scenes as S
     g = np.load(FIX_FULL)
     ref, spp = g["block4"].astype(np.float64), int(g["spp"])
-    flat, _ = bench.get_scene(argparse.Namespace(tex=4096, width=1920, height=1080, workload="clock", grid=0), need_dir=False)
-    sc = S.load_flat(flat)
+    # the scene through the PRODUCT's loader from the scene directory the reference rendered (same OBJ / MTL / BMP / HDR files, same
+    # Mikkelsen tangents: host/tangent_space.cpp), i.e. `eleven <scene dir>` against `eleven_ref <scene dir>`
+    import subprocess
+    import tempfile
+    _, sdir = bench.get_scene(argparse.Namespace(tex=4096, width=1920, height=1080, workload="clock", grid=0), need_dir=True)
+    dump = os.path.join(tempfile.gettempdir(), "eleven_fullframe_product.flat")
+    subprocess.run([os.path.join(ROOT, "tfg-pathtracer_b200", "host", "eleven"), "--dump-flat", sdir, dump], cwd=sdir, check=True, capture_output=True)
+    sc = S.load_flat(dump)
+    os.remove(dump)
     imgs = []
     for seed in (11, 12):
         f = R.Renderer(seed=seed, **R.FAST).render_setup(sc); f.render_cuda(spp)
@@ -92,7 +99,5 @@ def test_config3_1000spp_full_frame_against_the_reference_render():
     ratio = 0.5 * (e_ref + e_ref2) / e_self
     m = record("config3_1000spp_fullframe", rmse_ours_vs_reference=e_ref, rmse_ours2_vs_reference=e_ref2, rmse_ours_vs_ours=e_self, ratio=ratio,
                mean_ours=float(imgs[0].mean()), mean_reference=float(ref.mean()), spp=spp)
-    # NOTE the scene here comes from our generator's flat file, the reference rendered its own loader's version of it (MikkTSpace
-    # tangents): the two differ in the tangent frame of normal-mapped surfaces only
     assert 0.95 <= ratio <= 1.08, m
     assert abs(imgs[0].mean() - ref.mean()) / ref.mean() < 0.002, m

@@ -24,6 +24,7 @@
 #include "kernels.cuh"
 #include "kernels_trace.cuh"
 #include "bvh8_build_gpu.cuh"
+#include "scene_upload.cuh"
 #include "test_hooks.cuh"
 
 using namespace eleven;
@@ -195,19 +196,25 @@ static int uploadTexture(ElevenCtx* c, const ElevenTexture& t, DevTex& out, bool
     const size_t n = (size_t)t.width * t.height;
     out.width = t.width; out.height = t.height; out.xTile = t.xTile; out.yTile = t.yTile; out.xOffset = t.xOffset; out.yOffset = t.yOffset;
     out.format = t.format; out.filter = t.filter;
+    // the caller's texels go up as they are and are expanded on the device (scene_upload.cuh); the staging buffer is stream-ordered
+    const size_t rawBytes = n * (t.format == ELEVEN_TEX_F32_RGB ? 12 : 3);
+    void* raw = nullptr;
+    cudaError_t e = cudaMallocAsync(&raw, rawBytes, c->stream);
+    if (e != cudaSuccess) return fail(ELEVEN_ERR_NOMEM, std::string("cudaMallocAsync(texture staging): ") + cudaGetErrorString(e));
+    CK(cudaMemcpyAsync(raw, t.data, rawBytes, cudaMemcpyHostToDevice, c->stream));
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    int rc;
     if (t.format == ELEVEN_TEX_F32_RGB) {
-        std::vector<float4> tmp(n);
-        const float* s = (const float*)t.data;
-        for (size_t i = 0; i < n; i++) tmp[i] = make_float4(s[3 * i], s[3 * i + 1], s[3 * i + 2], (s[3 * i] + s[3 * i + 1]) + s[3 * i + 2]);
-        const float4* d = nullptr; int rc = devUpload(c->sceneAllocs, &d, tmp.data(), n); if (rc) return rc;
+        float4* d = nullptr; if ((rc = devAlloc(c->sceneAllocs, &d, n))) return rc;
+        k_expandRgbF32<<<grid, 256, 0, c->stream>>>((const float*)raw, d, n);
         out.data = d;
     } else {
-        std::vector<uchar4> tmp(n);
-        const uint8_t* s = (const uint8_t*)t.data;
-        for (size_t i = 0; i < n; i++) tmp[i] = make_uchar4(s[3 * i], s[3 * i + 1], s[3 * i + 2], 255);
-        const uchar4* d = nullptr; int rc = devUpload(c->sceneAllocs, &d, tmp.data(), n); if (rc) return rc;
+        uchar4* d = nullptr; if ((rc = devAlloc(c->sceneAllocs, &d, n))) return rc;
+        k_expandRgb8<<<grid, 256, 0, c->stream>>>((const uint8_t*)raw, d, n);
         out.data = d;
     }
+    CK(cudaGetLastError());
+    CK(cudaFreeAsync(raw, c->stream));
     return ELEVEN_OK;
 }
 
@@ -291,6 +298,48 @@ extern "C" int eleven_scene_upload(ElevenCtx* c, const ElevenSceneDesc* d) {
     DevScene& S = c->scene; memset(&S, 0, sizeof S);
     S.byteMagic = 0x47000000u;
     int rc;
+    // ELEVEN_UPLOAD_TRACE=1: wall-clock split of this call on stderr (host stages are synchronous)
+    const bool trace = getenv("ELEVEN_UPLOAD_TRACE") != nullptr;
+    auto tNow = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double tLast = tNow();
+    auto lap = [&](const char* what) { if (!trace) return; cudaDeviceSynchronize(); const double t = tNow(); fprintf(stderr, "[eleven_scene_upload] %-28s %8.1f ms\n", what, t - tLast); tLast = t; };
+    // The environment's CDF is a sequential float running sum (it must reproduce the reference's bits, S/HDRI.hpp:107-128) and the alias
+    // table a sequential pairing: host work, ~0.2 s for 4096x2048 texels.  It runs on its own thread while this one feeds the GPU
+    // (triangles, BVH8 build, textures).
+    std::vector<float> envCdf; std::vector<AliasEntry> envAlias; float envSum = 0.f; std::string envErr;
+    struct Joiner { std::thread t; void join() { if (t.joinable()) t.join(); } ~Joiner() { join(); } } envJoin;
+    if (!d->hdri.data || d->hdri.width <= 0 || d->hdri.height <= 0 || d->hdri.format != ELEVEN_TEX_F32_RGB) return fail(ELEVEN_ERR_ARG, "hdri must be a non-empty ELEVEN_TEX_F32_RGB texture");
+    envJoin.t = std::thread([&envCdf, &envAlias, &envSum, &envErr, d]() {
+        const int EW = d->hdri.width, EH = d->hdri.height; const size_t n = (size_t)EW * EH;
+        const float* src = (const float*)d->hdri.data;
+        auto texel = [&](int x, int y) -> size_t {          // Texture::getValueFromCoordinates addressing, S/Texture.hpp:95-108
+            x = (int)(d->hdri.xTile * (x + d->hdri.xOffset * EW)) % EW;
+            y = (int)(d->hdri.yTile * (y + d->hdri.yOffset * EH)) % EH;
+            long long idx = (long long)y * EW + x; if (idx < 0) idx = 0; if (idx >= (long long)n) idx = (long long)n - 1;
+            return (size_t)idx;
+        };
+        float sum = 0;
+        for (int j = 0; j < EH; j++) for (int i = 0; i < EW; i++) { const float* p = src + 3 * texel(i, j); sum += p[0] + p[1] + p[2]; }
+        if (!(sum > 0)) { envErr = "environment has zero total radiance (the reference hangs on it, SURVEY F10)"; return; }
+        std::vector<float>& cdf = envCdf; cdf.resize(n + 1); cdf[0] = 0; size_t k = 0;
+        for (int j = 0; j < EH; j++) for (int i = 0; i < EW; i++) { const float* p = src + 3 * texel(i, j); cdf[k + 1] = cdf[k] + (p[0] + p[1] + p[2]) / sum; k++; }
+        envSum = sum;
+        // Walker/Vose alias table over P_i = cdf[i+1]-cdf[i]: the texel weights the reference's pdf assumes
+        std::vector<AliasEntry>& alias = envAlias; alias.resize(n);
+        std::vector<double> p(n); double tot = 0;
+        for (size_t i = 0; i < n; i++) { p[i] = std::max(0.0, (double)cdf[i + 1] - (double)cdf[i]); tot += p[i]; }
+        std::vector<uint32_t> small, large; small.reserve(n); large.reserve(n);
+        for (size_t i = 0; i < n; i++) { p[i] = p[i] * (double)n / tot; (p[i] < 1.0 ? small : large).push_back((uint32_t)i); }
+        while (!small.empty() && !large.empty()) {
+            const uint32_t s = small.back(), l = large.back(); small.pop_back();
+            alias[s].prob = (float)p[s]; alias[s].alias = l;
+            p[l] = (p[l] + p[s]) - 1.0;
+            if (p[l] < 1.0) { large.pop_back(); small.push_back(l); }
+        }
+        for (uint32_t i : large) { alias[i].prob = 1.0f; alias[i].alias = i; }
+        for (uint32_t i : small) { alias[i].prob = 1.0f; alias[i].alias = i; }
+    });
+
 
     // triangles -> per-triangle material, BVH8, shading records
     std::vector<int32_t> triMat(d->triCount);
@@ -346,6 +395,7 @@ extern "C" int eleven_scene_upload(ElevenCtx* c, const ElevenSceneDesc* d) {
         }
         if ((rc = devUpload(c->sceneAllocs, &S.shadeTris, (const float4*)st.data(), (size_t)d->triCount * 9))) return rc;
     }
+    lap("triangles + BVH8");
     if ((rc = devUpload(c->sceneAllocs, &S.objectMaterial, d->objectMaterial, d->objectCount))) return rc;
     static_assert(sizeof(DevMaterial) == sizeof(ElevenMaterial), "material layout");
     for (uint32_t i = 0; i < d->materialCount; i++) {
@@ -357,6 +407,7 @@ extern "C" int eleven_scene_upload(ElevenCtx* c, const ElevenSceneDesc* d) {
     std::vector<DevTex> texs(d->textureCount);
     for (uint32_t i = 0; i < d->textureCount; i++) if ((rc = uploadTexture(c, d->textures[i], texs[i], false))) return rc;
     if ((rc = devUpload(c->sceneAllocs, &S.textures, texs.data(), texs.size()))) return rc;
+    lap("material textures");
     {   // packed map records (DevPackedMaps): materials whose four maps are 8-bit, unfiltered and congruent
         std::vector<DevPackedMaps> packed(d->materialCount);
         memset(packed.data(), 0, packed.size() * sizeof(DevPackedMaps));
@@ -373,57 +424,29 @@ extern "C" int eleven_scene_upload(ElevenCtx* c, const ElevenSceneDesc* d) {
             if (!ok) continue;
             const ElevenTexture& t0 = d->textures[ids[0]];
             const size_t n = (size_t)t0.width * t0.height;
-            const uint8_t* src[4]; for (int k = 0; k < 4; k++) src[k] = (const uint8_t*)d->textures[ids[k]].data;
-            std::vector<uint2> rec(n);
-            for (size_t p = 0; p < n; p++) {
-                rec[p].x = (uint32_t)src[0][3 * p] | ((uint32_t)src[0][3 * p + 1] << 8) | ((uint32_t)src[0][3 * p + 2] << 16) | ((uint32_t)src[1][3 * p] << 24);
-                rec[p].y = (uint32_t)src[3][3 * p] | ((uint32_t)src[3][3 * p + 1] << 8) | ((uint32_t)src[3][3 * p + 2] << 16) | ((uint32_t)src[2][3 * p] << 24);
-            }
-            const uint2* dp = nullptr;
-            if ((rc = devUpload(c->sceneAllocs, &dp, rec.data(), n))) return rc;
+            uint2* dp = nullptr;
+            if ((rc = devAlloc(c->sceneAllocs, &dp, n))) return rc;
+            k_packMaps<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>((const uchar4*)texs[ids[0]].data, (const uchar4*)texs[ids[1]].data,
+                                                                             (const uchar4*)texs[ids[2]].data, (const uchar4*)texs[ids[3]].data, dp, n);
+            CK(cudaGetLastError());
             DevPackedMaps& P = packed[i];
             P.data = dp; P.width = t0.width; P.height = t0.height; P.xTile = t0.xTile; P.yTile = t0.yTile; P.xOffset = t0.xOffset; P.yOffset = t0.yOffset;
             P.albedoFormat = d->textures[ids[0]].format; P.roughFormat = d->textures[ids[1]].format; P.metalFormat = d->textures[ids[2]].format; P.normalFormat = d->textures[ids[3]].format;
         }
         if ((rc = devUpload(c->sceneAllocs, &S.packed, packed.data(), packed.size()))) return rc;
     }
+    lap("packed material maps");
     float lut[512]; buildLut(lut);
     if ((rc = devUpload(c->sceneAllocs, &S.lut, lut, 512))) return rc;
 
-    // environment: float4 texels + the reference's float CDF (S/HDRI.hpp:107-128) + alias table over its increments
+    // environment: float4 texels + the reference's float CDF (S/HDRI.hpp:107-128) + alias table over its increments (built by envWorker)
     if ((rc = uploadTexture(c, d->hdri, S.hdri, true))) return rc;
-    {
-        const int EW = d->hdri.width, EH = d->hdri.height; const size_t n = (size_t)EW * EH;
-        const float* src = (const float*)d->hdri.data;
-        auto texel = [&](int x, int y) -> size_t {          // Texture::getValueFromCoordinates addressing, S/Texture.hpp:95-108
-            x = (int)(d->hdri.xTile * (x + d->hdri.xOffset * EW)) % EW;
-            y = (int)(d->hdri.yTile * (y + d->hdri.yOffset * EH)) % EH;
-            long long idx = (long long)y * EW + x; if (idx < 0) idx = 0; if (idx >= (long long)n) idx = (long long)n - 1;
-            return (size_t)idx;
-        };
-        float sum = 0;
-        for (int j = 0; j < EH; j++) for (int i = 0; i < EW; i++) { const float* p = src + 3 * texel(i, j); sum += p[0] + p[1] + p[2]; }
-        if (!(sum > 0)) return fail(ELEVEN_ERR_ARG, "environment has zero total radiance (the reference hangs on it, SURVEY F10)");
-        std::vector<float> cdf(n + 1); cdf[0] = 0; size_t k = 0;
-        for (int j = 0; j < EH; j++) for (int i = 0; i < EW; i++) { const float* p = src + 3 * texel(i, j); cdf[k + 1] = cdf[k] + (p[0] + p[1] + p[2]) / sum; k++; }
-        S.radianceSum = sum;
-        if ((rc = devUpload(c->sceneAllocs, &S.cdf, cdf.data(), n + 1))) return rc;
-        // Walker/Vose alias table over P_i = cdf[i+1]-cdf[i]: the reference's *effective* texel distribution
-        std::vector<AliasEntry> alias(n);
-        std::vector<double> p(n); double tot = 0;
-        for (size_t i = 0; i < n; i++) { p[i] = std::max(0.0, (double)cdf[i + 1] - (double)cdf[i]); tot += p[i]; }
-        std::vector<uint32_t> small, large; small.reserve(n); large.reserve(n);
-        for (size_t i = 0; i < n; i++) { p[i] = p[i] * (double)n / tot; (p[i] < 1.0 ? small : large).push_back((uint32_t)i); }
-        while (!small.empty() && !large.empty()) {
-            const uint32_t s = small.back(), l = large.back(); small.pop_back();
-            alias[s].prob = (float)p[s]; alias[s].alias = l;
-            p[l] = (p[l] + p[s]) - 1.0;
-            if (p[l] < 1.0) { large.pop_back(); small.push_back(l); }
-        }
-        for (uint32_t i : large) { alias[i].prob = 1.0f; alias[i].alias = i; }
-        for (uint32_t i : small) { alias[i].prob = 1.0f; alias[i].alias = i; }
-        if ((rc = devUpload(c->sceneAllocs, &S.alias, alias.data(), n))) return rc;
-    }
+    envJoin.join();
+    if (!envErr.empty()) return fail(ELEVEN_ERR_ARG, envErr);
+    S.radianceSum = envSum;
+    if ((rc = devUpload(c->sceneAllocs, &S.cdf, envCdf.data(), envCdf.size()))) return rc;
+    if ((rc = devUpload(c->sceneAllocs, &S.alias, envAlias.data(), envAlias.size()))) return rc;
+    lap("environment + CDF + alias");
     S.lightCount = d->pointLightCount;
     if ((rc = devUpload(c->sceneAllocs, &S.lights, (const float*)d->pointLights, (size_t)d->pointLightCount * 6))) return rc;
     static_assert(sizeof(DevCamera) == sizeof(ElevenCamera), "camera layout");
@@ -432,6 +455,7 @@ extern "C" int eleven_scene_upload(ElevenCtx* c, const ElevenSceneDesc* d) {
     c->width = d->camera.xRes; c->height = d->camera.yRes;
     const uint32_t nPix = c->width * c->height;
     if (nPix != c->nPixels || !c->W.ray) { c->nPixels = nPix; if ((rc = allocWave(c))) return rc; }
+    lap("wave state allocation");
     c->W.sceneHasEmission = 0u;
     for (uint32_t i = 0; i < d->materialCount; i++) {
         const ElevenMaterial& m = d->materials[i];

@@ -225,7 +225,9 @@ __device__ __forceinline__ void appendWarpAggregated(uint32_t* q, uint32_t* coun
 #define EL_SHADE_PREFETCH 1
 #endif
 #ifndef EL_SHADE_MIN_CTAS
-#define EL_SHADE_MIN_CTAS 6      /* 80 registers, 24 warps/SM: the kernel waits on texture gathers (ncu: long_scoreboard), measured -11 % vs 91 registers */
+#define EL_SHADE_MIN_CTAS 5      /* <= 102 registers (96 used, no spills), 20 warps/SM.  Without the prefetch 6 CTAs x 80 registers was the best point
+                                  * (round 1); with it the queue -> hit part of the gather chain is hidden and the 200 bytes of spills cost more than the
+                                  * sixth CTA brings: 7.52 -> 6.46 ms per 16-spp step (profiles/r2_variants_session2.json) */
 #endif
 template <bool FM>
 __global__ void __launch_bounds__(128, EL_SHADE_MIN_CTAS) k_shade(WaveState W, const __grid_constant__ DevScene S, const __grid_constant__ RenderParams P) {
@@ -247,7 +249,10 @@ __global__ void __launch_bounds__(128, EL_SHADE_MIN_CTAS) k_shade(WaveState W, c
 #if EL_SHADE_PREFETCH
     // Software pipeline over the warp's queue blocks: the chain queue entry -> hit record -> triangle -> texel is four dependent
     // gathers (ncu: long_scoreboard 4.2 warps per issue cycle, issue 54 %).  The NEXT block's work fetch, queue entry and hit record
-    // are requested while the current block is shaded, so an iteration starts with the triangle index already in registers.
+    // are requested while the current block is shaded, so an iteration starts with the triangle index already in registers:
+    // 8.65 -> 7.52 ms per 16-spp step at 6 CTAs/SM, 6.40 ms at 5 CTAs/SM without spills (profiles/r2_variants_session{2,3}.json).
+    // A two-deep version (hit record of block i+1 at the top, prefetch.global.L2 of its ray / throughput / triangle, queue entry of
+    // block i+2) measured SLOWER: 6.69 ms — the extra L2 prefetches compete with the demand gathers of a kernel at 56 % of the HBM roof.
     uint32_t base = warpFetch(&W.cnt[CNT_WORK_SHADE], lane);
     uint32_t pid = 0; float4 hv = make_float4(0.f, 0.f, 0.f, 0.f);
     if (base + lane < n) { pid = queueEntry(base + lane); hv = W.hit[pid]; }

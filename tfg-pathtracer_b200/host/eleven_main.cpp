@@ -42,6 +42,7 @@ static void runDevice(DeviceJob* j, int slice, bool report) {
     if ((j->rc = eleven_scene_upload(j->ctx, j->desc))) { j->err = eleven_last_error(); }
     j->uploadS = nowS() - t0;
     t0 = nowS();
+    double lastReport = t0;
     for (int done = 0; !j->rc && done < j->spp;) {
         const int k = std::min(slice, j->spp - done);
         if ((j->rc = eleven_render(j->ctx, k))) { j->err = eleven_last_error(); break; }
@@ -54,7 +55,8 @@ static void runDevice(DeviceJob* j, int slice, bool report) {
                 writeBmp24(tmp, (int)j->desc->camera.xRes, (int)j->desc->camera.yRes, px.data(), perr))
                 rename(tmp.c_str(), j->previewPath);
         }
-        if (report) {                                         // the reference's status line (S/main.cpp:172-179)
+        if (report && (done == j->spp || nowS() - lastReport >= 0.1)) {   // the reference's status line, at its 100 ms polling period (S/main.cpp:132,172-179)
+            lastReport = nowS();
             ElevenStats st; eleven_get_stats(j->ctx, &st);
             const double ms = (nowS() - t0) * 1e3;
             printf("\rkPaths/s: %.1f, %d/%d samples, %.2f seconds running, %llu total paths", st.hit_bounces / ms, done, j->spp, ms / 1e3,
@@ -98,20 +100,15 @@ int main(int argc, char** argv) {
     if (spp <= 0 || gpus < 1) { fprintf(stderr, "eleven: bad sample or GPU count\n"); return 2; }
     if (!fast && gpus > 1) { fprintf(stderr, "eleven: the reference RNG stream cannot be split across GPUs; use --mode fast\n"); return 2; }
 
-    printf("Loading scene \n");
-    double t0 = nowS();
-    LoadedScene scene;
-    if (!loadScene(scenePath, scene, err)) { fprintf(stderr, "eleven: %s\n", err.c_str()); return 1; }
-    ElevenSceneDesc desc = scene.desc();
-    const double loadS = nowS() - t0;
-    printf("%s: %zu triangles, %zu textures, %ux%u, loaded in %.0f ms\n", scenePath.c_str(), scene.tris.size(), scene.textures.size(),
-           desc.camera.xRes, desc.camera.yRes, loadS * 1e3);
-
+    // CUDA context creation (~1 s per process on a B200 box) does not depend on the scene: one thread per device creates the
+    // contexts while this thread reads and parses the scene files
     std::vector<DeviceJob> jobs(gpus);
     std::vector<ElevenCtx*> ctxs(gpus, nullptr);
+    std::vector<std::thread> initTh;
+    const double tInit = nowS();
     for (int g = 0; g < gpus; g++) {
         DeviceJob& j = jobs[g]; memset(&j.cfg, 0, sizeof j.cfg);
-        j.device = g; j.desc = &desc;
+        j.device = g;
         j.cfg.device = g; j.cfg.max_bounces = 5;
         j.cfg.rng_mode = fast ? ELEVEN_RNG_FAST : ELEVEN_RNG_REFERENCE; j.cfg.env_mode = fast ? ELEVEN_ENV_ALIAS : ELEVEN_ENV_CDF;
         j.cfg.hit_mode = ELEVEN_HIT_KEY; j.cfg.flags = fast ? (ELEVEN_FLAG_TERMINATE_DEAD_PATHS | ELEVEN_FLAG_SKIP_NULL_NEE | ELEVEN_FLAG_FAST_MATH | ELEVEN_FLAG_ANYHIT_LIGHT_SHADOWS) : 0u;
@@ -120,9 +117,22 @@ int main(int argc, char** argv) {
         j.spp = spp / gpus + (g < spp % gpus ? 1 : 0);          // global sample s goes to device s % gpus
         j.allPasses = aovPrefix != nullptr;
         if (g == 0) j.previewPath = previewPath;                 // device 0's share of the samples is an unbiased picture of its own
-        if (eleven_init(&j.cfg, &j.ctx)) { fprintf(stderr, "eleven: device %d: %s\n", g, eleven_last_error()); return 1; }
-        ctxs[g] = j.ctx;
+        initTh.emplace_back([&j]() { if ((j.rc = eleven_init(&j.cfg, &j.ctx))) j.err = eleven_last_error(); });
     }
+
+    printf("Loading scene \n");
+    double t0 = nowS();
+    LoadedScene scene;
+    const bool loaded = loadScene(scenePath, scene, err);
+    const double loadS = nowS() - t0;
+    for (auto& t : initTh) t.join();
+    const double initS = nowS() - tInit;
+    for (auto& j : jobs) if (j.rc) { fprintf(stderr, "eleven: device %d: %s\n", j.device, j.err.c_str()); return 1; }
+    if (!loaded) { fprintf(stderr, "eleven: %s\n", err.c_str()); for (auto& j : jobs) eleven_destroy(j.ctx); return 1; }
+    ElevenSceneDesc desc = scene.desc();
+    printf("%s: %zu triangles, %zu textures, %ux%u, loaded in %.0f ms (CUDA contexts ready after %.0f ms, in parallel)\n", scenePath.c_str(), scene.tris.size(),
+           scene.textures.size(), desc.camera.xRes, desc.camera.yRes, loadS * 1e3, initS * 1e3);
+    for (int g = 0; g < gpus; g++) { jobs[g].desc = &desc; ctxs[g] = jobs[g].ctx; }
     if (gpus > 1 && eleven_comm_init_all(ctxs.data(), gpus)) { fprintf(stderr, "eleven: %s\n", eleven_last_error()); return 1; }
     t0 = nowS();
     std::vector<std::thread> th;
@@ -166,8 +176,8 @@ int main(int argc, char** argv) {
     printf("%d spp on %d GPU(s): render %.1f ms (wall incl. upload %.1f ms), %.1f M pixel-samples/s, %.1f Mrays/s, BVH8 %u nodes built in %.1f ms\n",
            spp, gpus, renderMs, wall * 1e3, samples / renderMs / 1e3, rays / renderMs / 1e3, jobs[0].stats.bvh_nodes, jobs[0].stats.bvh_build_ms);
     // the job as a user times it (process start -> picture on disk), phase by phase: what a strong-scaling number must include
-    printf("job: {\"gpus\": %d, \"spp\": %d, \"load_s\": %.3f, \"upload_s\": %.3f, \"render_s\": %.3f, \"render_device_ms\": %.1f, \"reduce_device_ms\": %.2f, \"total_s\": %.3f}\n",
-           gpus, spp, loadS, uploadS, renderS, renderMs, reduceMs, nowS() - tProcess);
+    printf("job: {\"gpus\": %d, \"spp\": %d, \"load_s\": %.3f, \"init_s\": %.3f, \"upload_s\": %.3f, \"render_s\": %.3f, \"render_device_ms\": %.1f, \"reduce_device_ms\": %.2f, \"total_s\": %.3f}\n",
+           gpus, spp, loadS, initS, uploadS, renderS, renderMs, reduceMs, nowS() - tProcess);
     for (auto& j : jobs) eleven_destroy(j.ctx);
     return 0;
 }
