@@ -233,7 +233,13 @@ def ncu_counters(args, git_sha):
 
 def git_head():
     try:
-        return subprocess.run(["git", "-C", ROOT, "rev-parse", "--short=12", "HEAD"], capture_output=True, text=True, timeout=10).stdout.strip() or "unknown"
+        sha = subprocess.run(["git", "-C", ROOT, "rev-parse", "--short=12", "HEAD"], capture_output=True, text=True, timeout=10).stdout.strip()
+        if sha:
+            return sha
+    except Exception:            # noqa: BLE001
+        pass
+    try:                         # a gpurun snapshot has no .git: __graft_entry__.build() left the commit next to the library
+        return json.load(open(os.path.join(ROOT, "tfg-pathtracer_b200", "_build_info.json")))["git"]
     except Exception:            # noqa: BLE001
         return "unknown"
 

@@ -63,7 +63,7 @@ typedef struct ElevenConfig {
     uint32_t flags;         /* ELEVEN_FLAG_*                                                           */
     uint64_t seed;          /* fast rng key; the reference mode always uses seed 0 like the reference  */
     uint32_t wave_spp;      /* samples of every pixel in flight per wave (power of two, <= 16); 0 = auto: as many as keep
-                             * a wave <= 2^25 paths.  Only ELEVEN_RNG_FAST can have more than 1 (the reference's per-pixel
+                             * a wave <= 2^26 paths (and within the device's free memory).  Only ELEVEN_RNG_FAST can have more than 1 (the reference's per-pixel
                              * XORWOW stream is sequential across samples, S/kernel.cu:380,480).  Same image for any value. */
     uint32_t bvh_builder;   /* ELEVEN_BVH_*                                                            */
 } ElevenConfig;

@@ -65,6 +65,19 @@ def test_sample_plan_partitions_all_samples():
             assert sorted(seen) == list(range(total))
 
 
+def test_job_plan_partitions_all_samples_in_whole_waves():
+    for world in (1, 2, 3, 4, 8):
+        for total in (0, 1, 5, 16, 100, 1000, 4096):
+            seen, most = [], 0
+            for r in range(world):
+                off, stride, local = D.job_plan(total, r, world, 16)
+                assert stride == 1 and (off % 16 == 0 or local == 0)
+                seen += list(range(off, off + local)); most = max(most, local)
+            assert sorted(seen) == list(range(total))
+            assert most <= 16 * -(-(-(-total // 16)) // world)            # nobody renders more than ceil(waves / world) waves
+    assert [D.job_plan(1000, r, 8)[2] for r in range(8)] == [128] * 7 + [104]
+
+
 def test_two_rank_film_reduce_matches_single_rank_at_every_step():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))

@@ -221,11 +221,12 @@ static int uploadTexture(ElevenCtx* c, const ElevenTexture& t, DevTex& out, bool
 static int allocWaveK(ElevenCtx* c);
 
 static int allocWave(ElevenCtx* c) {
-    // samples per pixel in flight: as many as keep a wave within 2^25 paths (~12 GB of wave state), at most 16
+    // samples per pixel in flight: as many as keep a wave within 2^26 paths (~24 GB of wave state on a 180 GB device: 16 at 1080p,
+    // 8 at 3840x2160), at most 16; halved below until the allocation fits
     c->maxLogK = 0;
     if (c->cfg.rng_mode == ELEVEN_RNG_FAST) {
         if (c->cfg.wave_spp) { while ((1u << c->maxLogK) < c->cfg.wave_spp) c->maxLogK++; }
-        else while (c->maxLogK < 4 && ((uint64_t)c->nPixels << (c->maxLogK + 1)) <= (1ull << 25)) c->maxLogK++;
+        else while (c->maxLogK < 4 && ((uint64_t)c->nPixels << (c->maxLogK + 1)) <= (1ull << 26)) c->maxLogK++;
     }
     if (((uint64_t)c->nPixels << c->maxLogK) > 0x7fffffffull) return fail(ELEVEN_ERR_ARG, "wave_spp x resolution exceeds 2^31 paths");
     // an automatic width that does not fit the device's free memory is halved until it does (the image does not depend on it)

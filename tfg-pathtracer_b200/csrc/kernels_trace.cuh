@@ -14,6 +14,9 @@
 
 namespace eleven {
 
+#ifndef EL_SHADOW_PREFETCH
+#define EL_SHADOW_PREFETCH 0
+#endif
 #ifndef EL_FAST_TRI
 #define EL_FAST_TRI 1            /* fast-math configuration: Moeller-Trumbore with contracted multiply-adds and MUFU reciprocal (mollerTrumboreFast) */
 #endif
@@ -97,6 +100,12 @@ struct ShadowEnvSource {
         const float4 p = neeRec(W, pid, NEE_POS), e = neeRec(W, pid, NEE_ENV_DIR);
         lr.ray.o = f3(p.x, p.y, p.z); lr.ray.d = f3(e.x, e.y, e.z);       // Ray(point + newDir*0.001, newDir), S/kernel.cu:246: built by k_shade
         lr.tmaxAny = INFINITY; lr.tag = pid;
+#if EL_SHADOW_PREFETCH
+        // what the sink's MIS combination will read when this ray is done (second sector of the NEE line, throughput / radiance): into
+        // L2 now, while the ray is traced (ncu: long_scoreboard 4.7-6.3 warps per issue cycle, a quarter of the stall samples in the sink)
+        asm volatile("prefetch.global.L2 [%0];" :: "l"(&neeRec(W, pid, NEE_ENV_C)));
+        asm volatile("prefetch.global.L2 [%0];" :: "l"(&W.tr[2 * (size_t)pid]));
+#endif
     }
 };
 template <bool LIGHTS>

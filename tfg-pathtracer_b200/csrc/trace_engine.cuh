@@ -26,6 +26,11 @@ namespace eleven {
 #ifndef EL_TRIS_PER_ITER
 #define EL_TRIS_PER_ITER 2     /* triangle tests per lane per loop iteration */
 #endif
+/* Round 2 tried a per-warp shared-memory RING of set-up rays (one atomicAdd + one coalesced queue read + the set-up arithmetic for 32
+ * rays with all lanes busy; an idle lane then starts a ray with 12 LDS) so that the refill could run at 2-8 idle lanes instead of 12.
+ * Bit-identical, and SLOWER on one box back to back: k_extend 17.54 vs 16.70 ms, shadow 6.21 vs 5.80 (refill at 2 / 4 / 6 / 8 idle lanes:
+ * 17.69 / 17.54 / 17.56 / 17.62; a 32-slot ring: 17.40) — profiles/r2_variants_session5.json.  The refill threshold is NOT where the
+ * lanes are lost, and 15 KB of shared memory per CTA come out of the L1 the node fetches live in.  Removed again. */
 #ifndef EL_REFILL
 #define EL_REFILL 12           /* idle lanes that trigger a queue fetch (4 / 8 / 12 / 16 measured on 16-sample waves: k_extend 19.9 / 18.85 / 18.4 / 18.5 ms) */
 #endif
@@ -103,7 +108,8 @@ __device__ __forceinline__ void traceQueue(const DevScene& S, uint32_t n, uint32
 
     bool active = false, exhausted = (S.nodeCount == 0 && false);
     LaneRay lr; lr.tag = 0; lr.tmaxAny = INFINITY; lr.ray.o = f3(0.f); lr.ray.d = f3(0.f, 0.f, 1.f);
-    float idx = 0.f, idy = 0.f, idz = 0.f, dx = 1.f, dy = 1.f, dz = 1.f, tscale = 1.f;
+    float idx = 0.f, idy = 0.f, idz = 0.f, tscale = 1.f;
+    float dx = 1.f, dy = 1.f, dz = 1.f;
     uint32_t octinv = 0, tvalid = 0, tpostValid = 0;
     float slack = 0.f, epsRay = 0.f, tcull = INFINITY, bestLo = INFINITY, bestHi = INFINITY;   // [bestLo, bestHi] brackets the best key
     bool bestExact = false;
@@ -204,9 +210,11 @@ __device__ __forceinline__ void traceQueue(const DevScene& S, uint32_t n, uint32
                     const uint32_t qlox = __float_as_uint(half ? n2.y : n2.x), qloy = __float_as_uint(half ? n2.w : n2.z);
                     const uint32_t qloz = __float_as_uint(half ? n3.y : n3.x), qhix = __float_as_uint(half ? n3.w : n3.z);
                     const uint32_t qhiy = __float_as_uint(half ? n4.y : n4.x), qhiz = __float_as_uint(half ? n4.w : n4.z);
-                    const uint32_t xmin = dx < 0.f ? qhix : qlox, xmax = dx < 0.f ? qlox : qhix;
-                    const uint32_t ymin = dy < 0.f ? qhiy : qloy, ymax = dy < 0.f ? qloy : qhiy;
-                    const uint32_t zmin = dz < 0.f ? qhiz : qloz, zmax = dz < 0.f ? qloz : qhiz;
+                    // octinv bit set = direction component >= 0 (near plane = low plane)
+                    const bool xNeg = !(octinv & 4u), yNeg = !(octinv & 2u), zNeg = !(octinv & 1u);
+                    const uint32_t xmin = xNeg ? qhix : qlox, xmax = xNeg ? qlox : qhix;
+                    const uint32_t ymin = yNeg ? qhiy : qloy, ymax = yNeg ? qloy : qhiy;
+                    const uint32_t zmin = zNeg ? qhiz : qloz, zmax = zNeg ? qloz : qhiz;
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
                         const uint32_t sel = 0x7504u + ((uint32_t)j << 4);       // bytes: 0x00, q_j, 0x00, 0x47

@@ -23,6 +23,21 @@ def sample_plan(total_spp: int, rank: int, world: int):
     return rank, world, local
 
 
+def job_plan(total_spp: int, rank: int, world: int, wave_spp: int = 16):
+    """Strong-scaling split of a FIXED job (`eleven <scene> 1000 out.bmp --gpus N`): the job's samples are cut into waves of
+    `wave_spp` (what a context renders per wave at full speed) and rank r gets a contiguous run of whole waves, so that no rank
+    renders ragged 8 + 4 + 1-sample waves: with s % world, 1000 spp on 8 GPUs is 125 per GPU = 7 full waves + 3 small ones; here it
+    is 8 waves on seven GPUs and 7 (the last one half full) on the eighth.  The counter RNG is keyed by the GLOBAL sample index, so
+    the union over ranks — the image — is the same for any split.  Returns (sample_offset, sample_stride = 1, local_spp)."""
+    if not (0 <= rank < world):
+        raise ValueError("rank out of range")
+    waves = (total_spp + wave_spp - 1) // wave_spp
+    w0 = rank * (waves // world) + min(rank, waves % world)
+    w1 = w0 + waves // world + (1 if rank < waves % world else 0)
+    s0, s1 = min(total_spp, w0 * wave_spp), min(total_spp, w1 * wave_spp)
+    return s0, 1, s1 - s0
+
+
 def init_comm(renderer, rank: int, world: int, src: int = 0, group=None):
     """Creates the film-reduce communicator of `renderer` (eleven_comm_init_rank): rank `src` draws the NCCL unique id,
     torch.distributed (any backend) hands it to the others.  Collective."""

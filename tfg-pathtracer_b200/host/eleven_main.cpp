@@ -112,9 +112,15 @@ int main(int argc, char** argv) {
         j.cfg.device = g; j.cfg.max_bounces = 5;
         j.cfg.rng_mode = fast ? ELEVEN_RNG_FAST : ELEVEN_RNG_REFERENCE; j.cfg.env_mode = fast ? ELEVEN_ENV_ALIAS : ELEVEN_ENV_CDF;
         j.cfg.hit_mode = ELEVEN_HIT_KEY; j.cfg.flags = fast ? (ELEVEN_FLAG_TERMINATE_DEAD_PATHS | ELEVEN_FLAG_SKIP_NULL_NEE | ELEVEN_FLAG_FAST_MATH | ELEVEN_FLAG_ANYHIT_LIGHT_SHADOWS) : 0u;
-        j.cfg.sample_offset = (uint32_t)g; j.cfg.sample_stride = (uint32_t)gpus;
+        // the job's samples in waves of 16 (what a context renders per wave at full speed), a contiguous run of whole waves per device:
+        // nobody renders ragged 8 + 4 + 1-sample waves (1000 spp on 8 devices: 128 x 7 + 104 instead of 125 x 8 = 7 full waves + 3 small
+        // ones each).  The counter RNG is keyed by the global sample index: the image is the same for any split.
+        const int waveSpp = 16, waves = (spp + waveSpp - 1) / waveSpp;
+        const int w0 = g * (waves / gpus) + std::min(g, waves % gpus), w1 = w0 + waves / gpus + (g < waves % gpus ? 1 : 0);
+        const int s0 = std::min(spp, w0 * waveSpp), s1 = std::min(spp, w1 * waveSpp);
+        j.cfg.sample_offset = fast ? (uint32_t)s0 : 0u; j.cfg.sample_stride = 1u;
         j.cfg.bvh_builder = deviceBvh ? ELEVEN_BVH_DEVICE : ELEVEN_BVH_HOST;
-        j.spp = spp / gpus + (g < spp % gpus ? 1 : 0);          // global sample s goes to device s % gpus
+        j.spp = s1 - s0;
         j.allPasses = aovPrefix != nullptr;
         if (g == 0) j.previewPath = previewPath;                 // device 0's share of the samples is an unbiased picture of its own
         initTh.emplace_back([&j]() { if ((j.rc = eleven_init(&j.cfg, &j.ctx))) j.err = eleven_last_error(); });

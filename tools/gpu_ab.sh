@@ -6,7 +6,7 @@ out=gpurun_out/$tag
 mkdir -p $out
 export PYTHONUNBUFFERED=1
 if [ -z "$2" ]; then
-  timeout 1500 python -m pytest tests -m gpu -q -x --durations=8 > $out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -15 $out/pytest_gpu.log
+  timeout 1500 python -m pytest tests -m gpu -q --durations=8 > $out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -15 $out/pytest_gpu.log
 fi
 timeout 600 python bench.py > $out/bench_main.json 2> $out/bench_main.err; echo "bench rc=$?"
 short() {   # name, env assignments...
