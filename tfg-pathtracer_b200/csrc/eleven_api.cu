@@ -54,6 +54,7 @@ struct ElevenCtx {
     ncclComm_t comm = nullptr;                   // film-reduce communicator (eleven_comm_init_rank / eleven_comm_init_all)
     int commRank = -1, commSize = 0;
     float4* d_reduced = nullptr;                 // root only: sum over ranks of the film passes (eleven_reduce_film)
+    float* d_commWarm = nullptr;                 // 16 bytes reduced once when the communicator is created (NCCL's lazy channel set-up)
     int reducedPasses = 0;
     std::vector<void*> sceneAllocs, waveAllocs;
     DevScene scene;
@@ -142,6 +143,7 @@ extern "C" void eleven_destroy(ElevenCtx* c) {
     commDestroy(c);
     freeAll(c->sceneAllocs); freeAll(c->waveAllocs);
     if (c->d_reduced) cudaFree(c->d_reduced);
+    if (c->d_commWarm) cudaFree(c->d_commWarm);
     if (c->bvhArena.base) cudaFree(c->bvhArena.base);
     for (cudaEvent_t e : {c->ev0, c->ev1, c->evR0, c->evR1, c->evFork, c->evJoin}) if (e) cudaEventDestroy(e);
     if (c->auxStream) cudaStreamDestroy(c->auxStream);
@@ -885,6 +887,8 @@ struct NcclApi {
     ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*Reduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
     std::string err;
 };
@@ -902,6 +906,8 @@ NcclApi* ncclApi() {
         api.CommInitAll = (decltype(api.CommInitAll))sym("ncclCommInitAll");
         api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
         api.Reduce = (decltype(api.Reduce))sym("ncclReduce");
+        api.GroupStart = (decltype(api.GroupStart))sym("ncclGroupStart");
+        api.GroupEnd = (decltype(api.GroupEnd))sym("ncclGroupEnd");
         api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
         if (!ok) { dlclose(api.h); api.h = nullptr; }
     });
@@ -912,6 +918,16 @@ int ncclFail(const char* what, ncclResult_t r) { return fail(ELEVEN_ERR_CUDA, st
 
 static void commDestroy(ElevenCtx* c) {
     if (c->comm) { ncclApi()->CommDestroy(c->comm); c->comm = nullptr; c->commRank = -1; c->commSize = 0; }
+}
+
+// NCCL sets up its channels (peer buffers over NVLink, proxy threads) lazily inside the FIRST collective of a communicator: ~0.5 s on a
+// B200 box.  A job has exactly one film reduce, i.e. it would pay that at the very end, on the critical path between the last wave and
+// the picture.  So communicator creation ends with a 16-byte reduce on the auxiliary stream: the set-up cost moves to where the caller
+// can overlap it with the scene upload and the rendering (the CLI creates the communicator on a thread of its own).
+static int commWarmupEnqueue(ElevenCtx* c) {
+    if (!c->d_commWarm) CK(cudaMalloc((void**)&c->d_commWarm, 64));
+    ncclResult_t r = ncclApi()->Reduce(c->d_commWarm, c->d_commWarm, 4, ncclFloat, ncclSum, 0, c->comm, c->auxStream);
+    return r == ncclSuccess ? ELEVEN_OK : ncclFail("ncclReduce (communicator warm-up)", r);
 }
 
 extern "C" int eleven_comm_unique_id(void* idOut) {
@@ -937,6 +953,8 @@ extern "C" int eleven_comm_init_rank(ElevenCtx* c, const void* idIn, int nranks,
     ncclResult_t r = N->CommInitRank(&c->comm, nranks, id, rank);
     if (r != ncclSuccess) { c->comm = nullptr; return ncclFail("ncclCommInitRank", r); }
     c->commRank = rank; c->commSize = nranks;
+    if (int rc = commWarmupEnqueue(c)) return rc;
+    CK(cudaStreamSynchronize(c->auxStream));
     return ELEVEN_OK;
 }
 
@@ -954,6 +972,15 @@ extern "C" int eleven_comm_init_all(ElevenCtx** ctxs, int n) {
     ncclResult_t r = N->CommInitAll(comms.data(), n, devs.data());
     if (r != ncclSuccess) return ncclFail("ncclCommInitAll", r);
     for (int i = 0; i < n; i++) { ctxs[i]->comm = comms[i]; ctxs[i]->commRank = i; ctxs[i]->commSize = n; }
+    if (n > 1) {
+        int rc = ELEVEN_OK;
+        N->GroupStart();                                    // one thread drives all ranks: the collective must be issued as a group
+        for (int i = 0; i < n && !rc; i++) { if (cudaSetDevice(devs[i]) != cudaSuccess) rc = fail(ELEVEN_ERR_CUDA, "cudaSetDevice"); else rc = commWarmupEnqueue(ctxs[i]); }
+        r = N->GroupEnd();
+        if (rc) return rc;
+        if (r != ncclSuccess) return ncclFail("ncclGroupEnd (communicator warm-up)", r);
+        for (int i = 0; i < n; i++) { CK(cudaSetDevice(devs[i])); CK(cudaStreamSynchronize(ctxs[i]->auxStream)); }
+    }
     return ELEVEN_OK;
 }
 

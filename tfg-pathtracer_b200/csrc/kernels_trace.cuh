@@ -14,14 +14,18 @@
 
 namespace eleven {
 
+#ifndef EL_SHADOW_MIN_CTAS
+#define EL_SHADOW_MIN_CTAS 9      /* 56 registers: shadow kernels 5.93 -> 5.73 ms per 16-spp step; 10 CTAs: 6.10 (profiles/r2_variants_session7.json) */
+#endif
 #ifndef EL_SHADOW_PREFETCH
-#define EL_SHADOW_PREFETCH 0
+#define EL_SHADOW_PREFETCH 1      /* shadow kernels 5.80 -> 5.70 ms per 16-spp step (profiles/r2_variants_session6.json) */
 #endif
 #ifndef EL_FAST_TRI
 #define EL_FAST_TRI 1            /* fast-math configuration: Moeller-Trumbore with contracted multiply-adds and MUFU reciprocal (mollerTrumboreFast) */
 #endif
 #ifndef EL_EXTEND_MIN_CTAS
-#define EL_EXTEND_MIN_CTAS 7      /* <= 72 registers, 7 CTAs per SM: no spills; 64 registers x 8 CTAs measured equal (but spills in KEY mode), no bound (93 registers x 5 CTAs) is 13 % slower */
+#define EL_EXTEND_MIN_CTAS 8      /* 64 registers, 8 CTAs per SM: k_extend 16.69 -> 16.06 ms per 16-spp step since the ray's sign tests come from the octant bits
+                                   * (3 registers fewer); 7 CTAs x 72 registers was round 1's point, 6 CTAs: 17.75 ms (profiles/r2_variants_session6.json) */
 #endif
 
 // ---- extension rays -----------------------------------------------------------------------------------------------------
@@ -118,7 +122,7 @@ struct ShadowEnvSink {
     }
 };
 template <bool LIGHTS, bool COUNT, bool FM>
-__global__ void __launch_bounds__(128) k_shadowEnv(const __grid_constant__ WaveState W, const __grid_constant__ DevScene S) {
+__global__ void __launch_bounds__(128, EL_SHADOW_MIN_CTAS) k_shadowEnv(const __grid_constant__ WaveState W, const __grid_constant__ DevScene S) {
     TraceCounters tc; tc.nodes = 0; tc.tris = 0; tc.keys = 0;
     ShadowEnvSource src{W}; ShadowEnvSink<LIGHTS> sink{W};
     traceQueue<TRACE_ANY, COUNT, false, FM && EL_FAST_TRI>(S, W.cnt[CNT_NEE], &W.cnt[CNT_WORK_CONNECT], src, sink, tc);
@@ -157,7 +161,8 @@ struct ShadowLightSink {
     }
 };
 template <int HITMODE, bool COUNT, bool FM>
-__global__ void __launch_bounds__(128) k_shadowLight(const __grid_constant__ WaveState W, const __grid_constant__ DevScene S) {
+__global__ void __launch_bounds__(128, (HITMODE == ELEVEN_HIT_KEY ? 7 : EL_SHADOW_MIN_CTAS)) k_shadowLight(   // closest-hit (KEY) flavour: 72 registers
+const __grid_constant__ WaveState W, const __grid_constant__ DevScene S) {
     TraceCounters tc; tc.nodes = 0; tc.tris = 0; tc.keys = 0;
     ShadowLightSource<HITMODE> src{W}; ShadowLightSink<HITMODE> sink{W, S};
     traceQueue<(HITMODE == ELEVEN_HIT_KEY ? TRACE_CLOSEST_KEY : TRACE_ANY), COUNT, false, FM && EL_FAST_TRI>(S, W.cnt[CNT_NEE], &W.cnt[CNT_WORK_LIGHT], src, sink, tc);

@@ -77,6 +77,7 @@ __device__ __forceinline__ float fmaSat(float a, float b, float c) {
 // pipe, which the node test saturates (ncu: ALU pipe 72 % at 78 % issue; SASS: 150 of the 272 node-phase instructions on ALU).
 struct TraceLut { uint32_t expand[256]; uint8_t perm[8][256]; };
 
+
 __device__ __forceinline__ void traceLutInit(TraceLut& L) {
     for (uint32_t h = threadIdx.x; h < 256u; h += blockDim.x) {
         uint32_t e = 0;

@@ -16,6 +16,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <future>
 #include <thread>
 #include <vector>
 
@@ -33,6 +34,7 @@ struct DeviceJob {
     ElevenStats stats; std::string err; int rc = 0;
     double uploadS = 0, renderS = 0, reduceS = 0;
     ElevenCtx* ctx = nullptr;
+    std::shared_future<int> commReady;        // the NCCL communicator is created (and warmed up) on its own thread while this device uploads and renders
 };
 
 // One host thread per device: upload the (replicated) scene, render this device's share of the samples, then take part in the ONE
@@ -41,6 +43,9 @@ static void runDevice(DeviceJob* j, int slice, bool report) {
     double t0 = nowS();
     if ((j->rc = eleven_scene_upload(j->ctx, j->desc))) { j->err = eleven_last_error(); }
     j->uploadS = nowS() - t0;
+    // the communicator is being created meanwhile (its cudaMalloc / IPC set-up calls are device-wide synchronisation points that would
+    // stall the wavefront pipeline's launches again and again: 690 instead of 249 ms for 125 spp per device on 8 GPUs): render once it is there
+    if (j->commReady.valid()) j->commReady.wait();
     t0 = nowS();
     double lastReport = t0;
     for (int done = 0; !j->rc && done < j->spp;) {
@@ -66,6 +71,7 @@ static void runDevice(DeviceJob* j, int slice, bool report) {
     }
     j->renderS = nowS() - t0;
     // a device that failed still joins the collective (with whatever film it has) so that the others do not hang in NCCL
+    if (j->commReady.valid() && j->commReady.get() != 0) { if (!j->rc) { j->rc = -1; j->err = "communicator creation failed"; } return; }
     t0 = nowS();
     const int rrc = eleven_reduce_film(j->ctx, 0, j->allPasses ? 1 : 0);
     if (!j->rc && rrc) { j->rc = rrc; j->err = eleven_last_error(); }
@@ -100,8 +106,16 @@ int main(int argc, char** argv) {
     if (spp <= 0 || gpus < 1) { fprintf(stderr, "eleven: bad sample or GPU count\n"); return 2; }
     if (!fast && gpus > 1) { fprintf(stderr, "eleven: the reference RNG stream cannot be split across GPUs; use --mode fast\n"); return 2; }
 
-    // CUDA context creation (~1 s per process on a B200 box) does not depend on the scene: one thread per device creates the
-    // contexts while this thread reads and parses the scene files
+    // The driver initialises EVERY visible device of the box when the process makes its first CUDA call: ~6 s on an 8 x B200 box against
+    // ~1.3 s with one device visible, whatever the job uses.  Narrow the visibility to the devices this job renders on (unless the user
+    // has set it): must happen before the first CUDA call.
+    if (!getenv("CUDA_VISIBLE_DEVICES")) {
+        std::string vis;
+        for (int g = 0; g < gpus; g++) vis += (g ? "," : "") + std::to_string(g);
+        setenv("CUDA_VISIBLE_DEVICES", vis.c_str(), 1);
+    }
+    // CUDA context creation does not depend on the scene: one thread per device creates the contexts while this thread reads and
+    // parses the scene files
     std::vector<DeviceJob> jobs(gpus);
     std::vector<ElevenCtx*> ctxs(gpus, nullptr);
     std::vector<std::thread> initTh;
@@ -139,13 +153,20 @@ int main(int argc, char** argv) {
     printf("%s: %zu triangles, %zu textures, %ux%u, loaded in %.0f ms (CUDA contexts ready after %.0f ms, in parallel)\n", scenePath.c_str(), scene.tris.size(),
            scene.textures.size(), desc.camera.xRes, desc.camera.yRes, loadS * 1e3, initS * 1e3);
     for (int g = 0; g < gpus; g++) { jobs[g].desc = &desc; ctxs[g] = jobs[g].ctx; }
-    if (gpus > 1 && eleven_comm_init_all(ctxs.data(), gpus)) { fprintf(stderr, "eleven: %s\n", eleven_last_error()); return 1; }
+    // NCCL communicator + its first (tiny) collective on a thread of its own: ~1-2 s that overlap the upload and the rendering
+    std::string commErr; double commS = 0;
+    std::shared_future<int> commReady;
+    if (gpus > 1) {
+        commReady = std::async(std::launch::async, [&]() { const double tc = nowS(); const int rc = eleven_comm_init_all(ctxs.data(), gpus); if (rc) commErr = eleven_last_error(); commS = nowS() - tc; return rc; }).share();
+        for (auto& j : jobs) j.commReady = commReady;
+    }
     t0 = nowS();
     std::vector<std::thread> th;
     for (int g = 1; g < gpus; g++) th.emplace_back(runDevice, &jobs[g], slice, false);
     runDevice(&jobs[0], slice, true);
     for (auto& t : th) t.join();
     printf("\n");
+    if (gpus > 1 && commReady.get() != 0) { fprintf(stderr, "eleven: %s\n", commErr.c_str()); return 1; }
     for (auto& j : jobs) if (j.rc) { fprintf(stderr, "eleven: device %d: %s\n", j.device, j.err.c_str()); return 1; }
     const double wall = nowS() - t0;
 
@@ -182,8 +203,8 @@ int main(int argc, char** argv) {
     printf("%d spp on %d GPU(s): render %.1f ms (wall incl. upload %.1f ms), %.1f M pixel-samples/s, %.1f Mrays/s, BVH8 %u nodes built in %.1f ms\n",
            spp, gpus, renderMs, wall * 1e3, samples / renderMs / 1e3, rays / renderMs / 1e3, jobs[0].stats.bvh_nodes, jobs[0].stats.bvh_build_ms);
     // the job as a user times it (process start -> picture on disk), phase by phase: what a strong-scaling number must include
-    printf("job: {\"gpus\": %d, \"spp\": %d, \"load_s\": %.3f, \"init_s\": %.3f, \"upload_s\": %.3f, \"render_s\": %.3f, \"render_device_ms\": %.1f, \"reduce_device_ms\": %.2f, \"total_s\": %.3f}\n",
-           gpus, spp, loadS, initS, uploadS, renderS, renderMs, reduceMs, nowS() - tProcess);
+    printf("job: {\"gpus\": %d, \"spp\": %d, \"load_s\": %.3f, \"init_s\": %.3f, \"comm_init_s\": %.3f, \"upload_s\": %.3f, \"render_s\": %.3f, \"render_device_ms\": %.1f, \"reduce_device_ms\": %.2f, \"total_s\": %.3f}\n",
+           gpus, spp, loadS, initS, commS, uploadS, renderS, renderMs, reduceMs, nowS() - tProcess);
     for (auto& j : jobs) eleven_destroy(j.ctx);
     return 0;
 }
