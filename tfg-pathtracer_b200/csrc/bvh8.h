@@ -68,8 +68,13 @@ struct Bvh8 {
     uint32_t maxDepth;
 };
 
-/* Builds the BVH8 over `tris`.  triMaterial[i] = material id of triangle i (object -> material resolved). */
-void buildBvh8(const ElevenTri* tris, uint32_t n, const int32_t* triMaterial, Bvh8& out, int threads);
+/* One piece of a pre-split triangle (bvh8_build.cpp: presplitTriangles): the box of the part of triangle `tri` inside one cell. */
+struct PresplitPiece { float lo[3], hi[3]; uint32_t tri; };
+void presplitTriangles(const ElevenTri* tris, uint32_t n, std::vector<PresplitPiece>& out);
+
+/* Builds the BVH8 over `tris`.  triMaterial[i] = material id of triangle i (object -> material resolved).
+ * presplit: sliver triangles enter the build as several references (their slots are repeated in the leaves). */
+void buildBvh8(const ElevenTri* tris, uint32_t n, const int32_t* triMaterial, Bvh8& out, int threads, bool presplit = true);
 
 } // namespace eleven
 #endif

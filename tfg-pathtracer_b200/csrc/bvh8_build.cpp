@@ -124,16 +124,98 @@ static uint8_t quantExp(float extent) {
     return (uint8_t)(e + 127);
 }
 
+
+// ---- triangle pre-splitting ("early split clipping") -------------------------------------------------------------------------
+// A binned-SAH tree over whole-triangle boxes is helpless against slivers whose boxes overlap: the ~100 wedges of a disc modelled as a
+// fan all own most of the disc's box, and a ray through the disc tests every one of them (the clock face of the benchmark scene: camera
+// rays that hit it ran 80-99 triangle tests for 1 hit, 10 % of all camera rays more than 37; CPU walk of tests/bvh8_walk.py).  Such a
+// triangle is handed to the builder as several REFERENCES, each with the box of the part of the triangle inside one cell of a recursive
+// midpoint split of its box: the pieces' boxes are small and disjoint, the leaves simply list the triangle more than once (a ray may
+// test it twice; Moeller-Trumbore gives the same answer twice).  Split rule, per triangle: box area > PRESPLIT_AREA x the mean box
+// area of the scene AND box area > PRESPLIT_SLIVER x twice the triangle's own area (a well-shaped triangle fills its box; plain large
+// triangles and the millions of similar triangles of a grid are left alone), pieces until their boxes are below the mean, <= 2^5 each.
+struct Ref { Box box; int tri; };
+
+static void clipPoly(const std::vector<double>& in, int axis, double pos, bool keepBelow, std::vector<double>& out) {   // Sutherland-Hodgman against one axis-aligned plane
+    out.clear();
+    const size_t m = in.size() / 3;
+    for (size_t i = 0; i < m; i++) {
+        const double* a = &in[3 * i]; const double* b = &in[3 * ((i + 1) % m)];
+        const bool ina = keepBelow ? a[axis] <= pos : a[axis] >= pos, inb = keepBelow ? b[axis] <= pos : b[axis] >= pos;
+        if (ina) out.insert(out.end(), a, a + 3);
+        if (ina != inb) {
+            const double t = (pos - a[axis]) / (b[axis] - a[axis]);
+            double q[3]; for (int k = 0; k < 3; k++) q[k] = a[k] + t * (b[k] - a[k]);
+            q[axis] = pos;
+            out.insert(out.end(), q, q + 3);
+        }
+    }
+}
+static void splitRec(const std::vector<double>& poly, const Box& box, int tri, float targetArea, int depth, std::vector<Ref>& out) {
+    if (depth == 0 || box.area() <= targetArea || poly.size() < 9) { out.push_back({box, tri}); return; }
+    int axis = 0; float ext = box.hi[0] - box.lo[0];
+    for (int a = 1; a < 3; a++) if (box.hi[a] - box.lo[a] > ext) { ext = box.hi[a] - box.lo[a]; axis = a; }
+    const double mid = 0.5 * ((double)box.lo[axis] + (double)box.hi[axis]);
+    std::vector<double> part[2];
+    clipPoly(poly, axis, mid, true, part[0]); clipPoly(poly, axis, mid, false, part[1]);
+    if (part[0].size() < 9 || part[1].size() < 9) { out.push_back({box, tri}); return; }
+    for (int h = 0; h < 2; h++) {
+        Box b; b.reset();
+        for (size_t i = 0; i < part[h].size() / 3; i++) for (int a = 0; a < 3; a++) {
+            const double v = part[h][3 * i + a];
+            b.lo[a] = std::min(b.lo[a], std::nextafter((float)v, -INFINITY)); b.hi[a] = std::max(b.hi[a], std::nextafter((float)v, INFINITY));   // float box of double points, outwards
+        }
+        for (int a = 0; a < 3; a++) { b.lo[a] = std::max(b.lo[a], box.lo[a]); b.hi[a] = std::min(b.hi[a], box.hi[a]); }
+        splitRec(part[h], b, tri, targetArea, depth - 1, out);
+    }
+}
+static const float PRESPLIT_AREA = [] { const char* e = getenv("ELEVEN_PRESPLIT_AREA"); return e ? (float)atof(e) : 2.0f; }();
+static const float PRESPLIT_SLIVER = [] { const char* e = getenv("ELEVEN_PRESPLIT_SLIVER"); return e ? (float)atof(e) : 8.0f; }();
+static const int PRESPLIT_DEPTH = [] { const char* e = getenv("ELEVEN_PRESPLIT_DEPTH"); return e ? atoi(e) : 5; }();
+
 } // namespace
 
-void buildBvh8(const ElevenTri* tris, uint32_t n, const int32_t* triMaterial, Bvh8& out, int threads) {
+// Pieces of the triangles the rule above splits: out[k] = (box, triangle).  A split triangle contributes >= 2 pieces, an unsplit one none.
+void presplitTriangles(const ElevenTri* tris, uint32_t n, std::vector<PresplitPiece>& out) {
+    out.clear();
+    if (n == 0 || PRESPLIT_DEPTH <= 0) return;
+    double sum = 0;
+    std::vector<float> area(n);
+    for (uint32_t i = 0; i < n; i++) { Box b; b.reset(); for (int k = 0; k < 3; k++) b.grow(tris[i].vertices[k]); area[i] = b.area(); sum += area[i]; }
+    const float mean = (float)(sum / n);
+    std::vector<Ref> pieces; std::vector<double> poly(9);
+    for (uint32_t i = 0; i < n; i++) {
+        if (!(area[i] > PRESPLIT_AREA * mean)) continue;
+        const float (*v)[3] = tris[i].vertices;
+        double e1[3], e2[3]; for (int a = 0; a < 3; a++) { e1[a] = (double)v[1][a] - v[0][a]; e2[a] = (double)v[2][a] - v[0][a]; }
+        const double cx = e1[1] * e2[2] - e1[2] * e2[1], cy = e1[2] * e2[0] - e1[0] * e2[2], cz = e1[0] * e2[1] - e1[1] * e2[0];
+        const double twiceTri = std::sqrt(cx * cx + cy * cy + cz * cz);          // 2 x the triangle's area = the area of a box that fits it flat
+        if (!((double)area[i] > (double)PRESPLIT_SLIVER * twiceTri)) continue;
+        Box b; b.reset(); for (int k = 0; k < 3; k++) b.grow(v[k]);
+        for (int k = 0; k < 3; k++) for (int a = 0; a < 3; a++) poly[3 * k + a] = v[k][a];
+        pieces.clear();
+        splitRec(poly, b, (int)i, mean, PRESPLIT_DEPTH, pieces);
+        if (pieces.size() < 2) continue;
+        for (const Ref& r : pieces) { PresplitPiece p; p.tri = (uint32_t)r.tri; for (int a = 0; a < 3; a++) { p.lo[a] = r.box.lo[a]; p.hi[a] = r.box.hi[a]; } out.push_back(p); }
+    }
+}
+
+void buildBvh8(const ElevenTri* tris, uint32_t n, const int32_t* triMaterial, Bvh8& out, int threads, bool presplit) {
     auto t0 = std::chrono::steady_clock::now();
     out.nodes.clear(); out.slots.clear(); out.keySlack = 0; out.maxDepth = 0;
     for (int a = 0; a < 3; a++) { out.boundsLo[a] = 0; out.boundsHi[a] = 0; }
     if (threads < 1) threads = 1;
 
-    Builder B; B.tris = tris; B.n = n; B.threads = threads; B.liveTasks = 0;
-    B.tbox.resize(n); B.cen.resize(3 * (size_t)n); B.idx.resize(n);
+    // references: one per triangle, or the pieces of a pre-split triangle (the first piece takes the triangle's own place)
+    std::vector<PresplitPiece> pieces;
+    if (const char* e = getenv("ELEVEN_PRESPLIT")) presplit = atoi(e) != 0;     // A/B knob
+    if (presplit) presplitTriangles(tris, n, pieces);
+    std::vector<int> refTri(n);
+    for (uint32_t i = 0; i < n; i++) refTri[i] = (int)i;
+    const uint32_t nr = n + (uint32_t)pieces.size() - [&] { uint32_t c = 0; for (size_t k = 0; k < pieces.size(); k++) if (k == 0 || pieces[k].tri != pieces[k - 1].tri) c++; return c; }();
+    Builder B; B.tris = tris; B.n = nr; B.threads = threads; B.liveTasks = 0;
+    B.tbox.resize(nr); B.cen.resize(3 * (size_t)nr); B.idx.resize(nr);
+    refTri.resize(nr);
     Box scene; scene.reset();
     double slack = 0;
     std::vector<float> triShift(n);
@@ -141,7 +223,6 @@ void buildBvh8(const ElevenTri* tris, uint32_t n, const int32_t* triMaterial, Bv
         Box b; b.reset();
         for (int k = 0; k < 3; k++) b.grow(tris[i].vertices[k]);
         B.tbox[i] = b; scene.grow(b);
-        for (int a = 0; a < 3; a++) B.cen[3 * (size_t)i + a] = 0.5f * (b.lo[a] + b.hi[a]);
         B.idx[i] = (int)i;
         // Bound on the shadow-terminator shift |shadingPosition - geomPosition| (S/Tri.hpp:81-89): shadingPosition is
         // a convex combination of the projections p_i = P - dot(P - v_i, n_i) n_i, and dot(P - v_i, n_i) is linear in
@@ -160,6 +241,16 @@ void buildBvh8(const ElevenTri* tris, uint32_t n, const int32_t* triMaterial, Bv
         triShift[i] = (float)(mine * 1.0001);
         slack = std::max(slack, mine);
     }
+    {
+        uint32_t next = n;
+        for (size_t k = 0; k < pieces.size(); k++) {
+            const bool first = k == 0 || pieces[k].tri != pieces[k - 1].tri;
+            const uint32_t r = first ? pieces[k].tri : next++;
+            for (int a = 0; a < 3; a++) { B.tbox[r].lo[a] = pieces[k].lo[a]; B.tbox[r].hi[a] = pieces[k].hi[a]; }
+            refTri[r] = (int)pieces[k].tri; B.idx[r] = (int)r;
+        }
+    }
+    for (uint32_t r = 0; r < nr; r++) for (int a = 0; a < 3; a++) B.cen[3 * (size_t)r + a] = 0.5f * (B.tbox[r].lo[a] + B.tbox[r].hi[a]);
     if (n == 0) { scene.lo[0] = scene.lo[1] = scene.lo[2] = 0; scene.hi[0] = scene.hi[1] = scene.hi[2] = 0; }
     float ext = 0, mag = 0;
     for (int a = 0; a < 3; a++) {
@@ -169,13 +260,13 @@ void buildBvh8(const ElevenTri* tris, uint32_t n, const int32_t* triMaterial, Bv
     }
     // pad triangle boxes so that float rounding in the slab test can never cull a triangle Moeller-Trumbore accepts
     float pad = 4e-6f * std::max(ext, mag) + 1e-30f;
-    for (uint32_t i = 0; i < n; i++) for (int a = 0; a < 3; a++) { B.tbox[i].lo[a] -= pad; B.tbox[i].hi[a] += pad; }
+    for (uint32_t i = 0; i < nr; i++) for (int a = 0; a < 3; a++) { B.tbox[i].lo[a] -= pad; B.tbox[i].hi[a] += pad; }
     out.keySlack = (float)(slack * 1.0001 + 1e-5 * std::max(ext, mag));
 
     // ---- binary binned-SAH build ----------------------------------------------------------------
-    B.nodes.resize(std::max<size_t>(1, 2 * (size_t)n));
+    B.nodes.resize(std::max<size_t>(1, 2 * (size_t)nr));
     B.nodeCount = 1;
-    if (n > 0) B.build(0, 0, (int)n, 0);
+    if (n > 0) B.build(0, 0, (int)nr, 0);
     else { B.nodes[0].box = scene; B.nodes[0].left = B.nodes[0].right = -1; B.nodes[0].first = 0; B.nodes[0].count = 0; }
 
     // ---- optional: SAH-optimal collapse (Ylitie, Karras, Laine 2017, section 3.1) -----------------------------------------------
@@ -219,8 +310,8 @@ void buildBvh8(const ElevenTri* tris, uint32_t n, const int32_t* triMaterial, Bv
 
     // ---- collapse to 8-wide, breadth-first so that a node's internal children are contiguous ---------
     struct Item { int n2; uint32_t n8; uint32_t depth; };
-    std::vector<Item> queue; queue.reserve(n / 4 + 16);
-    out.nodes.reserve(n / 3 + 16); out.slots.reserve(n); out.nodeSlack.clear(); out.nodeSlack.reserve(n / 3 + 16);
+    std::vector<Item> queue; queue.reserve(nr / 4 + 16);
+    out.nodes.reserve(nr / 3 + 16); out.slots.reserve(nr); out.nodeSlack.clear(); out.nodeSlack.reserve(n / 3 + 16);
     out.nodes.emplace_back(); memset(&out.nodes[0], 0, sizeof(Node8));
     queue.push_back({0, 0u, 1u});
     for (size_t qi = 0; qi < queue.size(); qi++) {
@@ -281,7 +372,7 @@ void buildBvh8(const ElevenTri* tris, uint32_t n, const int32_t* triMaterial, Bv
                 uint32_t cnt = (uint32_t)c.count;               // <= EL_MAX_LEAF (the layout allows 3)
                 N.triMask |= ((1u << cnt) - 1u) << (3 * s);
                 for (uint32_t k = 0; k < cnt; k++) {
-                    int t = B.idx[c.first + k];
+                    int t = refTri[B.idx[c.first + k]];
                     const ElevenTri& T = tris[t];
                     TriSlot S;
                     S.v0x = T.vertices[0][0]; S.v0y = T.vertices[0][1]; S.v0z = T.vertices[0][2];
@@ -306,7 +397,7 @@ void buildBvh8(const ElevenTri* tris, uint32_t n, const int32_t* triMaterial, Bv
         out.nodes[it.n8] = N;
         {   // largest shift bound of any triangle below this node: lets the traversal cull with a LOCAL slack
             float ms = 0.f;
-            for (int k = root.first; k < root.first + root.span; k++) ms = std::max(ms, triShift[B.idx[k]]);
+            for (int k = root.first; k < root.first + root.span; k++) ms = std::max(ms, triShift[refTri[B.idx[k]]]);
             if (out.nodeSlack.size() <= it.n8) out.nodeSlack.resize(it.n8 + 1, 0.f);
             out.nodeSlack[it.n8] = ms;
             out.nodes[it.n8].slack = ms;

@@ -124,6 +124,22 @@ __global__ void __launch_bounds__(256) k_prep(const ElevenTri* __restrict__ tris
     if ((threadIdx.x & 31u) == 0u) atomicMax(&scene[SCENE_SHIFT], s);
 }
 
+// Pre-split triangles (bvh8_build.cpp: presplitTriangles): piece k becomes reference refOf[k] — the triangle's own slot for its first
+// piece, slot nTris + j for the others — with the piece's box and the triangle's shift bound.
+__global__ void k_applyPieces(const PresplitPiece* __restrict__ pieces, const uint32_t* __restrict__ refOf, uint32_t nPieces,
+                              float4* __restrict__ boxLo, float4* __restrict__ boxHi, uint32_t* __restrict__ idx, uint32_t* __restrict__ owner,
+                              uint32_t nTris, uint32_t* __restrict__ extraTri) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nPieces) return;
+    const PresplitPiece P = pieces[k];
+    const uint32_t r = refOf[k];
+    const float shift = boxLo[P.tri].w;                              // .w is never rewritten: no race with the first piece's thread
+    if (r == P.tri) { float4 lo = make_float4(P.lo[0], P.lo[1], P.lo[2], shift); boxLo[r] = lo; }
+    else { boxLo[r] = make_float4(P.lo[0], P.lo[1], P.lo[2], shift); extraTri[r - nTris] = P.tri; }
+    boxHi[r] = make_float4(P.hi[0], P.hi[1], P.hi[2], 0.f);
+    idx[r] = r; owner[r] = 0u;
+}
+
 // ---- per level ---------------------------------------------------------------------------------------------------------------
 __global__ void k_initBins(uint32_t* __restrict__ bins, size_t words) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -441,6 +457,7 @@ __global__ void __launch_bounds__(128) k_collapseGather(const Node2G* __restrict
 
 __global__ void __launch_bounds__(128) k_collapseEmit(const Node2G* __restrict__ nodes, const uint32_t* __restrict__ idx, const ElevenTri* __restrict__ tris,
                                                       const int32_t* __restrict__ triMaterial, const float4* __restrict__ boxLo,
+                                                      uint32_t nTris, const uint32_t* __restrict__ extraTri,
                                                       const Item8* __restrict__ items, uint32_t itemCount, const int32_t* __restrict__ childAtIn,
                                                       const uint32_t* __restrict__ offInt, const uint32_t* __restrict__ offTri, uint32_t n8Base, uint32_t slotBase,
                                                       Item8* __restrict__ nextItems, Node8* __restrict__ out8, TriSlot* __restrict__ slots,
@@ -480,18 +497,19 @@ __global__ void __launch_bounds__(128) k_collapseEmit(const Node2G* __restrict__
             N.triMask |= ((1u << cnt) - 1u) << (3 * s);
             uint32_t t3[3];
             for (uint32_t k = 0; k < cnt; k++) t3[k] = idx[c.first + k];
-            // arrival order of the partition atomics is not deterministic: emit in triangle-id order
+            // arrival order of the partition atomics is not deterministic: emit in reference-id order
             if (cnt > 1 && t3[0] > t3[1]) { const uint32_t x = t3[0]; t3[0] = t3[1]; t3[1] = x; }
             if (cnt > 2 && t3[1] > t3[2]) { const uint32_t x = t3[1]; t3[1] = t3[2]; t3[2] = x; }
             if (cnt > 1 && t3[0] > t3[1]) { const uint32_t x = t3[0]; t3[0] = t3[1]; t3[1] = x; }
             for (uint32_t k = 0; k < cnt; k++) {
-                const uint32_t t = t3[k];
+                const uint32_t r = t3[k];
+                const uint32_t t = r < nTris ? r : extraTri[r - nTris];      // reference -> triangle (pieces of pre-split triangles beyond the first)
                 const ElevenTri& T = tris[t];
                 TriSlot S;
                 S.v0x = T.vertices[0][0]; S.v0y = T.vertices[0][1]; S.v0z = T.vertices[0][2];
                 S.e1x = __fsub_rn(T.vertices[1][0], T.vertices[0][0]); S.e1y = __fsub_rn(T.vertices[1][1], T.vertices[0][1]); S.e1z = __fsub_rn(T.vertices[1][2], T.vertices[0][2]);
                 S.e2x = __fsub_rn(T.vertices[2][0], T.vertices[0][0]); S.e2y = __fsub_rn(T.vertices[2][1], T.vertices[0][1]); S.e2z = __fsub_rn(T.vertices[2][2], T.vertices[0][2]);
-                S.tri = (int32_t)t; S.material = triMaterial[t]; S.shiftBound = boxLo[t].w;
+                S.tri = (int32_t)t; S.material = triMaterial[t]; S.shiftBound = boxLo[r].w;
                 slots[triBase + triOff + k] = S;
             }
             triOff += cnt;
@@ -541,7 +559,13 @@ enum { BIN_CHUNK_NODES = 131072 };   // nodes binned per launch: 131 072 x 1 536
 #define GB_CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { err = std::string(#call) + ": " + cudaGetErrorString(e_); return false; } } while (0)
 
 // d_tris: the scene's triangles already on the device; d_triMaterial: per-triangle material.  n > 0.
-static bool buildBvh8Device(const ElevenTri* d_tris, const int32_t* d_triMaterial, uint32_t n, cudaStream_t st, BuildArena& arena, DeviceBvh& out, std::string& err) {
+static bool buildBvh8Device(const ElevenTri* d_tris, const int32_t* d_triMaterial, uint32_t nTris, const std::vector<PresplitPiece>& pieces, cudaStream_t st,
+                            BuildArena& arena, DeviceBvh& out, std::string& err) {
+    // references = triangles + the extra pieces of pre-split triangles; everything below the prep kernel works on references
+    std::vector<uint32_t> refOf(pieces.size());
+    uint32_t nExtra = 0;
+    for (size_t k = 0; k < pieces.size(); k++) refOf[k] = (k == 0 || pieces[k].tri != pieces[k - 1].tri) ? pieces[k].tri : nTris + nExtra++;
+    const uint32_t n = nTris + nExtra;
     const auto t0 = std::chrono::steady_clock::now();
     auto msSince = [&](std::chrono::steady_clock::time_point a) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a).count(); };
     const bool verbose = getenv("ELEVEN_BVH_VERBOSE") != nullptr;
@@ -561,7 +585,7 @@ static bool buildBvh8Device(const ElevenTri* d_tris, const int32_t* d_triMateria
 
     float4 *boxLo, *boxHi; uint32_t *idxA, *idxB, *ownA, *ownB, *scene, *counters, *actA, *actB, *bins; Node2G* nodes;
     Node8* out8; TriSlot* slots; float* slack; Item8 *itA, *itB; int32_t* childAt; uint32_t *nInt, *nTri, *offInt, *offTri; void* scanTmp;
-    float* dpC; uint8_t* dpK;
+    float* dpC; uint8_t* dpK; PresplitPiece* dPieces; uint32_t *dRefOf, *extraTri;
     auto layout = [&](char* base) -> size_t {
         size_t off = 0;
         auto take = [&](size_t bytes) -> char* { off = (off + 255) & ~(size_t)255; char* r = base ? base + off : nullptr; off += bytes; return r; };
@@ -577,6 +601,7 @@ static bool buildBvh8Device(const ElevenTri* d_tris, const int32_t* d_triMateria
         nInt = (uint32_t*)take(wideCap * 4); nTri = (uint32_t*)take(wideCap * 4); offInt = (uint32_t*)take(wideCap * 4); offTri = (uint32_t*)take(wideCap * 4);
         scanTmp = take(scanBytes);
         dpC = (float*)take(maxNodes * 8 * 4); dpK = (uint8_t*)take(maxNodes * 8);
+        dPieces = (PresplitPiece*)take(pieces.size() * sizeof(PresplitPiece)); dRefOf = (uint32_t*)take(pieces.size() * 4); extraTri = (uint32_t*)take((size_t)nExtra * 4 + 4);
         return off;
     };
     const size_t need = layout(nullptr);
@@ -592,7 +617,12 @@ static bool buildBvh8Device(const ElevenTri* d_tris, const int32_t* d_triMateria
     const uint32_t sceneInit[SCENE_WORDS] = {EL_ENC_POS_INF, EL_ENC_POS_INF, EL_ENC_POS_INF, EL_ENC_NEG_INF, EL_ENC_NEG_INF, EL_ENC_NEG_INF, 0u, 0u};
     GB_CK(cudaMemcpyAsync(scene, sceneInit, sizeof sceneInit, cudaMemcpyHostToDevice, st));
     const int gridN = (int)((n + 255) / 256);
-    k_prep<<<gridN, 256, 0, st>>>(d_tris, n, boxLo, boxHi, idxA, ownA, scene);
+    k_prep<<<(int)((nTris + 255) / 256), 256, 0, st>>>(d_tris, nTris, boxLo, boxHi, idxA, ownA, scene);
+    if (!pieces.empty()) {
+        GB_CK(cudaMemcpyAsync(dPieces, pieces.data(), pieces.size() * sizeof(PresplitPiece), cudaMemcpyHostToDevice, st));
+        GB_CK(cudaMemcpyAsync(dRefOf, refOf.data(), refOf.size() * 4, cudaMemcpyHostToDevice, st));
+        k_applyPieces<<<(unsigned)((pieces.size() + 255) / 256), 256, 0, st>>>(dPieces, dRefOf, (uint32_t)pieces.size(), boxLo, boxHi, idxA, ownA, nTris, extraTri);
+    }
     uint32_t sceneHost[SCENE_WORDS];
     GB_CK(cudaMemcpyAsync(sceneHost, scene, sizeof sceneHost, cudaMemcpyDeviceToHost, st));
     GB_CK(cudaStreamSynchronize(st));
@@ -669,7 +699,7 @@ static bool buildBvh8Device(const ElevenTri* d_tris, const int32_t* d_triMateria
         GB_CK(cudaStreamSynchronize(st));
         const uint32_t next = last[0] + last[1];
         if ((size_t)n8Base + next > wideCap || (size_t)slotBase + last[2] + last[3] > n) { overflow = true; break; }   // before anything is written out of bounds
-        k_collapseEmit<<<grid, 128, 0, st>>>(nodes, idxA, d_tris, d_triMaterial, boxLo, itA, itemCount, childAt, offInt, offTri, n8Base, slotBase,
+        k_collapseEmit<<<grid, 128, 0, st>>>(nodes, idxA, d_tris, d_triMaterial, boxLo, nTris, extraTri, itA, itemCount, childAt, offInt, offTri, n8Base, slotBase,
                                              itB, out8, slots, slack);
         GB_CK(cudaGetLastError());
         n8Base += next; slotBase += last[2] + last[3];
@@ -683,7 +713,7 @@ static bool buildBvh8Device(const ElevenTri* d_tris, const int32_t* d_triMateria
     GB_CK(cudaStreamSynchronize(st));
     out.nodeCount = n8Base; out.slotCount = slotBase; out.maxDepth = depth;
     tCollapse = msSince(tA) - tAlloc - tPrep - tLevels;
-    if (out.slotCount != n) { err = "device BVH build: emitted " + std::to_string(out.slotCount) + " triangle slots for " + std::to_string(n) + " triangles"; return false; }
+    if (out.slotCount != n) { err = "device BVH build: emitted " + std::to_string(out.slotCount) + " triangle slots for " + std::to_string(n) + " references"; return false; }
 
     // exact-size results (the arena is scratch)
     void *rn = nullptr, *rs = nullptr, *rk = nullptr;

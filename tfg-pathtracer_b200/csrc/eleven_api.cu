@@ -363,7 +363,9 @@ extern "C" int eleven_scene_upload(ElevenCtx* c, const ElevenSceneDesc* d) {
         if (e != cudaSuccess) return fail(ELEVEN_ERR_NOMEM, std::string("cudaMalloc(triangles): ") + cudaGetErrorString(e));
         e = cudaMemcpyAsync(d_tris, d->tris, (size_t)d->triCount * sizeof(ElevenTri), cudaMemcpyHostToDevice, c->stream);
         gpubvh::DeviceBvh db; std::string berr;
-        const bool ok = e == cudaSuccess && gpubvh::buildBvh8Device(d_tris, S.triMaterial, d->triCount, c->stream, c->bvhArena, db, berr);
+        std::vector<PresplitPiece> pieces;                  // sliver triangles enter the build as several references (bvh8_build.cpp)
+        { const char* ps = getenv("ELEVEN_PRESPLIT"); if (!ps || atoi(ps) != 0) presplitTriangles(d->tris, d->triCount, pieces); }
+        const bool ok = e == cudaSuccess && gpubvh::buildBvh8Device(d_tris, S.triMaterial, d->triCount, pieces, c->stream, c->bvhArena, db, berr);
         float4* st = nullptr;
         if (ok && (rc = devAlloc(c->sceneAllocs, &st, (size_t)d->triCount * 9)) == 0) {
             gpubvh::k_shadeTris<<<(d->triCount + 255) / 256, 256, 0, c->stream>>>(d_tris, d->triCount, (float*)st);
