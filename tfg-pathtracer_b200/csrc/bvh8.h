@@ -71,6 +71,10 @@ struct Bvh8 {
 /* One piece of a pre-split triangle (bvh8_build.cpp: presplitTriangles): the box of the part of triangle `tri` inside one cell. */
 struct PresplitPiece { float lo[3], hi[3]; uint32_t tri; };
 void presplitTriangles(const ElevenTri* tris, uint32_t n, std::vector<PresplitPiece>& out);
+/* The two halves separately, for the device builder: it selects the candidates on the GPU (same rule, thresholds from presplitParams) and
+ * has the host clip only those (ascending triangle indices). */
+void presplitParams(float& areaFactor, float& sliverFactor, int& depth);
+void presplitCandidates(const ElevenTri* tris, const uint32_t* cand, size_t nc, float meanArea, std::vector<PresplitPiece>& out);
 
 /* Builds the BVH8 over `tris`.  triMaterial[i] = material id of triangle i (object -> material resolved).
  * presplit: sliver triangles enter the build as several references (their slots are repeated in the leaves). */

@@ -179,22 +179,61 @@ static const int PRESPLIT_DEPTH = [] { const char* e = getenv("ELEVEN_PRESPLIT_D
 void presplitTriangles(const ElevenTri* tris, uint32_t n, std::vector<PresplitPiece>& out) {
     out.clear();
     if (n == 0 || PRESPLIT_DEPTH <= 0) return;
-    double sum = 0;
+    // fixed chunks, combined in chunk order: the result does not depend on the number of threads (both builders and every GPU of a job
+    // must see the same pieces)
+    const uint32_t CHUNK = 65536, chunks = (n + CHUNK - 1) / CHUNK;
+    const unsigned nth = std::max(1u, std::min(std::thread::hardware_concurrency(), chunks));
+    auto parallel = [&](const std::function<void(uint32_t)>& body) {
+        std::atomic<uint32_t> next(0);
+        auto run = [&]() { for (;;) { const uint32_t c = next.fetch_add(1); if (c >= chunks) break; body(c); } };
+        std::vector<std::thread> th;
+        for (unsigned t = 1; t < nth; t++) th.emplace_back(run);
+        run();
+        for (auto& t : th) t.join();
+    };
     std::vector<float> area(n);
-    for (uint32_t i = 0; i < n; i++) { Box b; b.reset(); for (int k = 0; k < 3; k++) b.grow(tris[i].vertices[k]); area[i] = b.area(); sum += area[i]; }
+    std::vector<double> chunkSum(chunks, 0.0);
+    parallel([&](uint32_t c) {
+        double sum = 0;
+        for (uint32_t i = c * CHUNK, e = std::min(n, (c + 1) * CHUNK); i < e; i++) { Box b; b.reset(); for (int k = 0; k < 3; k++) b.grow(tris[i].vertices[k]); area[i] = b.area(); sum += area[i]; }
+        chunkSum[c] = sum;
+    });
+    double sum = 0; for (double v : chunkSum) sum += v;
     const float mean = (float)(sum / n);
+    std::vector<std::vector<PresplitPiece>> chunkOut(chunks);
+    parallel([&](uint32_t c) {
+        std::vector<Ref> pieces; std::vector<double> poly(9);
+        for (uint32_t i = c * CHUNK, e = std::min(n, (c + 1) * CHUNK); i < e; i++) {
+            if (!(area[i] > PRESPLIT_AREA * mean)) continue;
+            const float (*v)[3] = tris[i].vertices;
+            double e1[3], e2[3]; for (int a = 0; a < 3; a++) { e1[a] = (double)v[1][a] - v[0][a]; e2[a] = (double)v[2][a] - v[0][a]; }
+            const double cx = e1[1] * e2[2] - e1[2] * e2[1], cy = e1[2] * e2[0] - e1[0] * e2[2], cz = e1[0] * e2[1] - e1[1] * e2[0];
+            const double twiceTri = std::sqrt(cx * cx + cy * cy + cz * cz);          // 2 x the triangle's area = the area of a box that fits it flat
+            if (!((double)area[i] > (double)PRESPLIT_SLIVER * twiceTri)) continue;
+            Box b; b.reset(); for (int k = 0; k < 3; k++) b.grow(v[k]);
+            for (int k = 0; k < 3; k++) for (int a = 0; a < 3; a++) poly[3 * k + a] = v[k][a];
+            pieces.clear();
+            splitRec(poly, b, (int)i, mean, PRESPLIT_DEPTH, pieces);
+            if (pieces.size() < 2) continue;
+            for (const Ref& r : pieces) { PresplitPiece p; p.tri = (uint32_t)r.tri; for (int a = 0; a < 3; a++) { p.lo[a] = r.box.lo[a]; p.hi[a] = r.box.hi[a]; } chunkOut[c].push_back(p); }
+        }
+    });
+    for (auto& v : chunkOut) out.insert(out.end(), v.begin(), v.end());
+}
+
+void presplitParams(float& areaFactor, float& sliverFactor, int& depth) { areaFactor = PRESPLIT_AREA; sliverFactor = PRESPLIT_SLIVER; depth = PRESPLIT_DEPTH; }
+
+// The clipping half on its own: `cand` (ascending triangle indices) were selected by the rule above — on the device, by the device builder.
+void presplitCandidates(const ElevenTri* tris, const uint32_t* cand, size_t nc, float meanArea, std::vector<PresplitPiece>& out) {
+    out.clear();
     std::vector<Ref> pieces; std::vector<double> poly(9);
-    for (uint32_t i = 0; i < n; i++) {
-        if (!(area[i] > PRESPLIT_AREA * mean)) continue;
+    for (size_t c = 0; c < nc; c++) {
+        const uint32_t i = cand[c];
         const float (*v)[3] = tris[i].vertices;
-        double e1[3], e2[3]; for (int a = 0; a < 3; a++) { e1[a] = (double)v[1][a] - v[0][a]; e2[a] = (double)v[2][a] - v[0][a]; }
-        const double cx = e1[1] * e2[2] - e1[2] * e2[1], cy = e1[2] * e2[0] - e1[0] * e2[2], cz = e1[0] * e2[1] - e1[1] * e2[0];
-        const double twiceTri = std::sqrt(cx * cx + cy * cy + cz * cz);          // 2 x the triangle's area = the area of a box that fits it flat
-        if (!((double)area[i] > (double)PRESPLIT_SLIVER * twiceTri)) continue;
         Box b; b.reset(); for (int k = 0; k < 3; k++) b.grow(v[k]);
         for (int k = 0; k < 3; k++) for (int a = 0; a < 3; a++) poly[3 * k + a] = v[k][a];
         pieces.clear();
-        splitRec(poly, b, (int)i, mean, PRESPLIT_DEPTH, pieces);
+        splitRec(poly, b, (int)i, meanArea, PRESPLIT_DEPTH, pieces);
         if (pieces.size() < 2) continue;
         for (const Ref& r : pieces) { PresplitPiece p; p.tri = (uint32_t)r.tri; for (int a = 0; a < 3; a++) { p.lo[a] = r.box.lo[a]; p.hi[a] = r.box.hi[a]; } out.push_back(p); }
     }

@@ -124,6 +124,71 @@ __global__ void __launch_bounds__(256) k_prep(const ElevenTri* __restrict__ tris
     if ((threadIdx.x & 31u) == 0u) atomicMax(&scene[SCENE_SHIFT], s);
 }
 
+// ---- pre-split candidates on the device (bvh8_build.cpp: presplitTriangles states the rule) ---------------------------------------
+// Box area per triangle, summed per block in a FIXED order (shared-memory tree) so that the mean — and with it the tree — is the same
+// on every run and every GPU; the host adds the block sums in block order.
+__device__ __forceinline__ float triBoxArea(const ElevenTri& T) {
+    float lo[3], hi[3];
+    for (int a = 0; a < 3; a++) { lo[a] = fminf(fminf(T.vertices[0][a], T.vertices[1][a]), T.vertices[2][a]); hi[a] = fmaxf(fmaxf(T.vertices[0][a], T.vertices[1][a]), T.vertices[2][a]); }
+    return boxArea(lo, hi);
+}
+__global__ void __launch_bounds__(256) k_presplitAreaSums(const ElevenTri* __restrict__ tris, uint32_t n, double* __restrict__ blockSum) {
+    __shared__ double sh[256];
+    const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+    sh[threadIdx.x] = i < n ? (double)triBoxArea(tris[i]) : 0.0;
+    __syncthreads();
+    for (uint32_t w = 128u; w > 0u; w >>= 1) { if (threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w]; __syncthreads(); }
+    if (threadIdx.x == 0) blockSum[blockIdx.x] = sh[0];
+}
+__global__ void __launch_bounds__(256) k_presplitSelect(const ElevenTri* __restrict__ tris, uint32_t n, float mean, float areaFactor, float sliverFactor,
+                                                        uint32_t* __restrict__ cand, uint32_t cap, uint32_t* __restrict__ count) {
+    const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+    if (i >= n) return;
+    const ElevenTri& T = tris[i];
+    const float area = triBoxArea(T);
+    if (!(area > areaFactor * mean)) return;
+    double e1[3], e2[3];
+    for (int a = 0; a < 3; a++) { e1[a] = (double)T.vertices[1][a] - (double)T.vertices[0][a]; e2[a] = (double)T.vertices[2][a] - (double)T.vertices[0][a]; }
+    const double cx = e1[1] * e2[2] - e1[2] * e2[1], cy = e1[2] * e2[0] - e1[0] * e2[2], cz = e1[0] * e2[1] - e1[1] * e2[0];
+    const double twiceTri = sqrt(cx * cx + cy * cy + cz * cz);
+    if (!((double)area > (double)sliverFactor * twiceTri)) return;
+    const uint32_t k = atomicAdd(count, 1u);
+    if (k < cap) cand[k] = i;
+}
+// Selects the sliver triangles of d_tris on the GPU and has the host clip them (h_tris: the same triangles in host memory) into pieces.
+// A scene without slivers costs two small kernels and one synchronisation.
+static bool devicePresplit(const ElevenTri* d_tris, const ElevenTri* h_tris, uint32_t n, cudaStream_t st, std::vector<PresplitPiece>& pieces, std::string& err) {
+    pieces.clear();
+    float areaFactor, sliverFactor; int depth;
+    presplitParams(areaFactor, sliverFactor, depth);
+    if (n == 0 || depth <= 0) return true;
+    const uint32_t blocks = (n + 255u) / 256u, cap = n / 8u + 4096u;
+    double* dSum = nullptr; uint32_t* dCand = nullptr;
+    if (cudaMallocAsync((void**)&dSum, (size_t)blocks * 8, st) != cudaSuccess || cudaMallocAsync((void**)&dCand, ((size_t)cap + 1) * 4, st) != cudaSuccess) { err = "device BVH build: out of memory (pre-split scratch)"; return false; }
+    uint32_t* dCount = dCand + cap;
+    std::vector<double> sums(blocks);
+    k_presplitAreaSums<<<blocks, 256, 0, st>>>(d_tris, n, dSum);
+    bool ok = cudaMemcpyAsync(sums.data(), dSum, (size_t)blocks * 8, cudaMemcpyDeviceToHost, st) == cudaSuccess && cudaMemsetAsync(dCount, 0, 4, st) == cudaSuccess &&
+              cudaStreamSynchronize(st) == cudaSuccess;
+    double total = 0; for (double v : sums) total += v;
+    const float mean = (float)(total / n);
+    uint32_t count = 0;
+    if (ok) {
+        k_presplitSelect<<<blocks, 256, 0, st>>>(d_tris, n, mean, areaFactor, sliverFactor, dCand, cap, dCount);
+        ok = cudaMemcpyAsync(&count, dCount, 4, cudaMemcpyDeviceToHost, st) == cudaSuccess && cudaStreamSynchronize(st) == cudaSuccess;
+    }
+    std::vector<uint32_t> cand;
+    if (ok && count > 0 && count <= cap) {                           // more candidates than the buffer holds: a scene OF slivers; build it unsplit
+        cand.resize(count);
+        ok = cudaMemcpyAsync(cand.data(), dCand, (size_t)count * 4, cudaMemcpyDeviceToHost, st) == cudaSuccess && cudaStreamSynchronize(st) == cudaSuccess;
+    }
+    cudaFreeAsync(dSum, st); cudaFreeAsync(dCand, st);
+    if (!ok) { err = std::string("device BVH build (pre-split): ") + cudaGetErrorString(cudaGetLastError()); return false; }
+    std::sort(cand.begin(), cand.end());                              // the atomics' arrival order is not deterministic
+    presplitCandidates(h_tris, cand.data(), cand.size(), mean, pieces);
+    return true;
+}
+
 // Pre-split triangles (bvh8_build.cpp: presplitTriangles): piece k becomes reference refOf[k] — the triangle's own slot for its first
 // piece, slot nTris + j for the others — with the piece's box and the triangle's shift bound.
 __global__ void k_applyPieces(const PresplitPiece* __restrict__ pieces, const uint32_t* __restrict__ refOf, uint32_t nPieces,

@@ -364,8 +364,12 @@ extern "C" int eleven_scene_upload(ElevenCtx* c, const ElevenSceneDesc* d) {
         e = cudaMemcpyAsync(d_tris, d->tris, (size_t)d->triCount * sizeof(ElevenTri), cudaMemcpyHostToDevice, c->stream);
         gpubvh::DeviceBvh db; std::string berr;
         std::vector<PresplitPiece> pieces;                  // sliver triangles enter the build as several references (bvh8_build.cpp)
-        { const char* ps = getenv("ELEVEN_PRESPLIT"); if (!ps || atoi(ps) != 0) presplitTriangles(d->tris, d->triCount, pieces); }
-        const bool ok = e == cudaSuccess && gpubvh::buildBvh8Device(d_tris, S.triMaterial, d->triCount, pieces, c->stream, c->bvhArena, db, berr);
+        const char* ps = getenv("ELEVEN_PRESPLIT");
+        bool ok = e == cudaSuccess;
+        const auto tPs = std::chrono::steady_clock::now();
+        if (ok && (!ps || atoi(ps) != 0)) ok = gpubvh::devicePresplit(d_tris, d->tris, d->triCount, c->stream, pieces, berr);
+        const double presplitMs = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tPs).count();
+        ok = ok && gpubvh::buildBvh8Device(d_tris, S.triMaterial, d->triCount, pieces, c->stream, c->bvhArena, db, berr);
         float4* st = nullptr;
         if (ok && (rc = devAlloc(c->sceneAllocs, &st, (size_t)d->triCount * 9)) == 0) {
             gpubvh::k_shadeTris<<<(d->triCount + 255) / 256, 256, 0, c->stream>>>(d_tris, d->triCount, (float*)st);
@@ -379,7 +383,7 @@ extern "C" int eleven_scene_upload(ElevenCtx* c, const ElevenSceneDesc* d) {
         if (db.maxDepth >= EL_STACK) return fail(ELEVEN_ERR_UNSUPPORTED, "BVH deeper than the traversal stack");
         S.nodes = db.nodes; S.slots = db.slots; S.nodeSlack = db.nodeSlack; S.shadeTris = st;
         S.nodeCount = db.nodeCount; S.triCount = d->triCount; S.keySlack = db.keySlack;
-        c->stats.bvh_build_ms = db.buildMs; c->stats.bvh_nodes = db.nodeCount; c->stats.bvh_tri_slots = db.slotCount; c->stats.key_slack = db.keySlack;
+        c->stats.bvh_build_ms = db.buildMs + presplitMs; c->stats.bvh_nodes = db.nodeCount; c->stats.bvh_tri_slots = db.slotCount; c->stats.key_slack = db.keySlack;
     } else {
         Bvh8 bvh;
         buildBvh8(d->tris, d->triCount, triMat.data(), bvh, (int)std::max(1u, std::thread::hardware_concurrency()));
