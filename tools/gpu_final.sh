@@ -6,7 +6,7 @@ tag=${1:-final}
 out=gpurun_out/$tag
 mkdir -p $out
 export PYTHONUNBUFFERED=1
-timeout 1500 python -m pytest tests -m gpu -q --durations=8 > $out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -4 $out/pytest_gpu.log
+if [ -z "$SKIP_TESTS" ]; then timeout 1500 python -m pytest tests -m gpu -q --durations=8 > $out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -4 $out/pytest_gpu.log; fi
 timeout 600 python bench.py --impl reference > $out/bench_reference.json 2> $out/bench_reference.err; echo "ref rc=$?"; cut -c1-400 $out/bench_reference.json
 timeout 600 python bench.py > $out/bench_ours.json 2> $out/bench_ours.err; echo "bench rc=$?"; cut -c1-300 $out/bench_ours.json
 cp gpurun_out/bench_ncu_counters_clock.csv $out/ 2>/dev/null
@@ -18,3 +18,9 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:"^k_
 dir=/tmp/eleven_bench_cache/clock_t4096_1920x1080_dir
 ( cd $dir && ELEVEN_UPLOAD_TRACE=1 $OLDPWD/tfg-pathtracer_b200/host/eleven $dir 1000 /tmp/o_dir.bmp ) > $out/job_dir_1gpu.log 2>&1; grep -E "job:|eleven_scene_upload|loaded" $out/job_dir_1gpu.log
 ls $out
+for v in $(ls tfg-pathtracer_b200/csrc/libeleven_b200_*.so 2>/dev/null); do
+  n=$(basename $v .so); n=${n#libeleven_b200_}
+  ELEVEN_LIB=$PWD/$v timeout 300 python bench.py --no-cpu-baseline --no-ncu > $out/bench_var_$n.json 2> $out/bench_var_$n.err
+  python -c "import json; d=json.load(open('$out/bench_var_$n.json')); s=d['roofline']['stage_ms']; print('variant $n %.1f M/s ext %.2f conn %.2f' % (d['value']/1e6, s['extend_ms'], s['connect_ms']))"
+done
+timeout 300 python bench.py --no-cpu-baseline --no-ncu > $out/bench_again.json 2> $out/bench_again.err; python -c "import json; d=json.load(open('$out/bench_again.json')); s=d['roofline']['stage_ms']; print('main again %.1f M/s ext %.2f conn %.2f' % (d['value']/1e6, s['extend_ms'], s['connect_ms']))"

@@ -24,4 +24,14 @@ f = R.Renderer(**dict(R.FAST, wave_spp=8)).render_setup(sc)
 f.render_cuda(11)
 print("fast", float(f.film()[..., :3].mean()), f.stats()["kernel_launches"])
 f.resolve_rgba8()
+f.reduce_film(0, all_passes=True)
+print("reduced", float(f.film_reduced()[..., :3].mean()))
 f.close()
+if not small:
+    # every shading path (clearcoat, anisotropy, sheen, emission, bilinear / float / packed maps) + a point light: k_shadowLight in both flavours
+    zoo = S.material_zoo(xres=48, yres=27, lights=1, env_size=(32, 16))
+    for cfg in (R.PARITY, R.FAST):
+        z = R.Renderer(**cfg).render_setup(zoo)
+        z.render_cuda(3)
+        print("zoo", float(z.film()[..., :3].mean()))
+        z.close()
