@@ -252,7 +252,7 @@ int  eleven_bvh_build_host(const ElevenTri* tris, uint32_t n, const int32_t* tri
 /* ncclGetUniqueId: call on one rank, hand the 128 bytes to every rank (any transport: torch.distributed, MPI, a file). */
 int  eleven_comm_unique_id(void* id_out);
 /* One process (or thread) per GPU: ncclCommInitRank on the context's device.  Collective: every rank must call it.
- * Both init calls end with a 16-byte reduce on the context's auxiliary stream: NCCL builds its channels inside the first collective
+ * Both init calls end with an 8 MB reduce on the context's auxiliary stream: NCCL builds its channels inside the first collective
  * of a communicator (~0.5 s), and a job's only reduce would otherwise pay that between the last wave and the picture.  Create the
  * communicator early (the CLI does it on a thread of its own while the scene uploads and renders). */
 int  eleven_comm_init_rank(ElevenCtx* ctx, const void* id, int nranks, int rank);

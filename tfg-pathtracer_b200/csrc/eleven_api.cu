@@ -54,7 +54,7 @@ struct ElevenCtx {
     ncclComm_t comm = nullptr;                   // film-reduce communicator (eleven_comm_init_rank / eleven_comm_init_all)
     int commRank = -1, commSize = 0;
     float4* d_reduced = nullptr;                 // root only: sum over ranks of the film passes (eleven_reduce_film)
-    float* d_commWarm = nullptr;                 // 16 bytes reduced once when the communicator is created (NCCL's lazy channel set-up)
+    float* d_commWarm = nullptr;                 // 8 MB reduced once when the communicator is created (NCCL's lazy channel set-up), then freed
     int reducedPasses = 0;
     std::vector<void*> sceneAllocs, waveAllocs;
     DevScene scene;
@@ -928,11 +928,16 @@ static void commDestroy(ElevenCtx* c) {
 
 // NCCL sets up its channels (peer buffers over NVLink, proxy threads) lazily inside the FIRST collective of a communicator: ~0.5 s on a
 // B200 box.  A job has exactly one film reduce, i.e. it would pay that at the very end, on the critical path between the last wave and
-// the picture.  So communicator creation ends with a 16-byte reduce on the auxiliary stream: the set-up cost moves to where the caller
+// the picture.  So communicator creation ends with an 8 MB reduce on the auxiliary stream: the set-up cost moves to where the caller
 // can overlap it with the scene upload and the rendering (the CLI creates the communicator on a thread of its own).
+static const size_t COMM_WARM_FLOATS = 2u << 20;       // 8 MB: large enough for the protocol and channel buffers a film-sized reduce uses (a 16-byte warm-up left
+                                                       // 37-44 ms of set-up in the first 33 MB reduce on 4 / 8 GPUs)
+static int commWarmupAlloc(ElevenCtx* c) {             // outside any NCCL group: cudaMalloc may synchronise
+    if (!c->d_commWarm) { CK(cudaMalloc((void**)&c->d_commWarm, COMM_WARM_FLOATS * 4)); CK(cudaMemsetAsync(c->d_commWarm, 0, COMM_WARM_FLOATS * 4, c->auxStream)); }
+    return ELEVEN_OK;
+}
 static int commWarmupEnqueue(ElevenCtx* c) {
-    if (!c->d_commWarm) CK(cudaMalloc((void**)&c->d_commWarm, 64));
-    ncclResult_t r = ncclApi()->Reduce(c->d_commWarm, c->d_commWarm, 4, ncclFloat, ncclSum, 0, c->comm, c->auxStream);
+    ncclResult_t r = ncclApi()->Reduce(c->d_commWarm, c->d_commWarm, COMM_WARM_FLOATS, ncclFloat, ncclSum, 0, c->comm, c->auxStream);
     return r == ncclSuccess ? ELEVEN_OK : ncclFail("ncclReduce (communicator warm-up)", r);
 }
 
@@ -959,8 +964,10 @@ extern "C" int eleven_comm_init_rank(ElevenCtx* c, const void* idIn, int nranks,
     ncclResult_t r = N->CommInitRank(&c->comm, nranks, id, rank);
     if (r != ncclSuccess) { c->comm = nullptr; return ncclFail("ncclCommInitRank", r); }
     c->commRank = rank; c->commSize = nranks;
+    if (int rc = commWarmupAlloc(c)) return rc;
     if (int rc = commWarmupEnqueue(c)) return rc;
     CK(cudaStreamSynchronize(c->auxStream));
+    cudaFree(c->d_commWarm); c->d_commWarm = nullptr;
     return ELEVEN_OK;
 }
 
@@ -980,12 +987,13 @@ extern "C" int eleven_comm_init_all(ElevenCtx** ctxs, int n) {
     for (int i = 0; i < n; i++) { ctxs[i]->comm = comms[i]; ctxs[i]->commRank = i; ctxs[i]->commSize = n; }
     if (n > 1) {
         int rc = ELEVEN_OK;
+        for (int i = 0; i < n; i++) { CK(cudaSetDevice(devs[i])); if ((rc = commWarmupAlloc(ctxs[i]))) return rc; }
         N->GroupStart();                                    // one thread drives all ranks: the collective must be issued as a group
         for (int i = 0; i < n && !rc; i++) { if (cudaSetDevice(devs[i]) != cudaSuccess) rc = fail(ELEVEN_ERR_CUDA, "cudaSetDevice"); else rc = commWarmupEnqueue(ctxs[i]); }
         r = N->GroupEnd();
         if (rc) return rc;
         if (r != ncclSuccess) return ncclFail("ncclGroupEnd (communicator warm-up)", r);
-        for (int i = 0; i < n; i++) { CK(cudaSetDevice(devs[i])); CK(cudaStreamSynchronize(ctxs[i]->auxStream)); }
+        for (int i = 0; i < n; i++) { CK(cudaSetDevice(devs[i])); CK(cudaStreamSynchronize(ctxs[i]->auxStream)); cudaFree(ctxs[i]->d_commWarm); ctxs[i]->d_commWarm = nullptr; }
     }
     return ELEVEN_OK;
 }

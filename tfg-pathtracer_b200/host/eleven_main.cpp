@@ -106,14 +106,8 @@ int main(int argc, char** argv) {
     if (spp <= 0 || gpus < 1) { fprintf(stderr, "eleven: bad sample or GPU count\n"); return 2; }
     if (!fast && gpus > 1) { fprintf(stderr, "eleven: the reference RNG stream cannot be split across GPUs; use --mode fast\n"); return 2; }
 
-    // The driver initialises EVERY visible device of the box when the process makes its first CUDA call: ~6 s on an 8 x B200 box against
-    // ~1.3 s with one device visible, whatever the job uses.  Narrow the visibility to the devices this job renders on (unless the user
-    // has set it): must happen before the first CUDA call.
-    if (!getenv("CUDA_VISIBLE_DEVICES")) {
-        std::string vis;
-        for (int g = 0; g < gpus; g++) vis += (g ? "," : "") + std::to_string(g);
-        setenv("CUDA_VISIBLE_DEVICES", vis.c_str(), 1);
-    }
+    // (Narrowing CUDA_VISIBLE_DEVICES to the devices in use was tried: the 6-7 s before the first CUDA call returns on the 8-GPU boxes of
+    // this pool — 1.3-2 s on its 1-GPU boxes — do not depend on it.)
     // CUDA context creation does not depend on the scene: one thread per device creates the contexts while this thread reads and
     // parses the scene files
     std::vector<DeviceJob> jobs(gpus);
