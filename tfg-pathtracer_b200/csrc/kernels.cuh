@@ -27,7 +27,7 @@
 
 namespace eleven {
 
-enum { CNT_CUR = 0, CNT_NEXT = 1, CNT_NEE = 2, CNT_WORK_TRACE = 3, CNT_WORK_SHADE = 4, CNT_WORK_CONNECT = 5, CNT_WORK_LIGHT = 6, CNT_WORK_CLASSIFY = 7,
+enum { CNT_CUR = 0, CNT_WORK_TRACE = 1, CNT_NEXT = 2, CNT_NEE = 3 /* (NEXT, NEE) = one aligned 64-bit word: k_shade reserves both with ONE atomic */, CNT_WORK_SHADE = 4, CNT_WORK_CONNECT = 5, CNT_WORK_LIGHT = 6, CNT_WORK_CLASSIFY = 7,
        CNT_BUCKET0 = 8, CNT_COUNT = 16 };
 enum { EL_BUCKETS = 8, EL_MISS_BUCKET = 7 };   // shading queue buckets: materials 0..5, 6 = all further materials, 7 = escaped rays
 enum { ST_RAYS_EXT = 0, ST_RAYS_ENV = 1, ST_RAYS_LIGHT = 2, ST_NODES = 3, ST_TRIS = 4, ST_KEYS = 5, ST_NODES_EXT = 6, ST_TRIS_EXT = 7, ST_COUNT = 8 };   // 3-5: all traversal kernels; 6-7: k_extend alone
@@ -221,6 +221,26 @@ __device__ __forceinline__ void appendWarpAggregated(uint32_t* q, uint32_t* coun
     q[base + __popc(mask & ((1u << lane) - 1u))] = value;
 }
 
+// Both of k_shade's queue appends with ONE 64-bit atomicAdd on the (CNT_NEXT, CNT_NEE) pair: the ncu source page had 9 % of the kernel's stall samples
+// on the two shuffles that wait for the two atomics' results.
+__device__ __forceinline__ void appendNextAndNee(const WaveState& W, bool toNext, bool toNee, uint32_t pid) {
+    const uint32_t mNext = __ballot_sync(0xffffffffu, toNext), mNee = __ballot_sync(0xffffffffu, toNee);   // called by all 32 lanes
+    if ((mNext | mNee) == 0u) return;
+    const uint32_t lane = threadIdx.x & 31u;
+    unsigned long long old = 0ull;
+    if (lane == 0u) old = atomicAdd(reinterpret_cast<unsigned long long*>(&W.cnt[CNT_NEXT]), (unsigned long long)__popc(mNext) | ((unsigned long long)__popc(mNee) << 32));
+    old = __shfl_sync(0xffffffffu, old, 0);
+    const uint32_t below = (1u << lane) - 1u;
+    if (toNext) W.qNext[(uint32_t)old + __popc(mNext & below)] = pid;
+    if (toNee) W.qNee[(uint32_t)(old >> 32) + __popc(mNee & below)] = pid;
+}
+
+#ifndef EL_SHADE_ONE_ATOMIC
+#define EL_SHADE_ONE_ATOMIC 1
+#endif
+#ifndef EL_SHADE_STATIC
+#define EL_SHADE_STATIC 1        /* queue blocks by a static stride over the grid's warps instead of an atomic work fetch (5 % of the stall samples sat on its shuffle) */
+#endif
 #ifndef EL_SHADE_PREFETCH
 #define EL_SHADE_PREFETCH 1
 #endif
@@ -253,15 +273,24 @@ __global__ void __launch_bounds__(128, EL_SHADE_MIN_CTAS) k_shade(WaveState W, c
     // 8.65 -> 7.52 ms per 16-spp step at 6 CTAs/SM, 6.40 ms at 5 CTAs/SM without spills (profiles/r2_variants_session{2,3}.json).
     // A two-deep version (hit record of block i+1 at the top, prefetch.global.L2 of its ray / throughput / triangle, queue entry of
     // block i+2) measured SLOWER: 6.69 ms — the extra L2 prefetches compete with the demand gathers of a kernel at 56 % of the HBM roof.
+#if EL_SHADE_STATIC
+    const uint32_t stride = gridDim.x * (blockDim.x >> 5) * 32u;     // every block of 32 queue entries costs about the same: a static stride balances as well as the atomic
+    uint32_t base = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32u;
+#else
     uint32_t base = warpFetch(&W.cnt[CNT_WORK_SHADE], lane);
+#endif
     uint32_t pid = 0; float4 hv = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (base + lane < n) { pid = queueEntry(base + lane); hv = W.hit[pid]; }
+    if (base < n && base + lane < n) { pid = queueEntry(base + lane); hv = W.hit[pid]; }
     for (;;) {
         if (base >= n) break;
         const uint32_t qi = base + lane;
+#if EL_SHADE_STATIC
+        const uint32_t nbase = (n - base > stride) ? base + stride : n;          // no wrap-around for n close to 2^32
+#else
         const uint32_t nbase = warpFetch(&W.cnt[CNT_WORK_SHADE], lane);
+#endif
         uint32_t npid = 0; float4 nhv = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (nbase + lane < n) npid = queueEntry(nbase + lane);
+        if (nbase < n && nbase + lane < n) npid = queueEntry(nbase + lane);
         bool toNee = false, toNext = false;
         if (qi < n) {
 #else
@@ -325,7 +354,7 @@ __global__ void __launch_bounds__(128, EL_SHADE_MIN_CTAS) k_shade(WaveState W, c
                 const float4 q4 = __ldg(tp + 4), q5 = __ldg(tp + 5), q6 = __ldg(tp + 6), q7 = __ldg(tp + 7), q8 = __ldg(tp + 8);
                 const TriGeom g = loadTriGeom(S.shadeTris, tri);
 #if EL_SHADE_PREFETCH
-                if (nbase + lane < n) nhv = W.hit[npid];            // the next block's hit record: requested behind this path's own gathers
+                if (nbase < n && nbase + lane < n) nhv = W.hit[npid];   // the next block's hit record: requested behind this path's own gathers
 #endif
                 F3 N;
                 const F3 Pp = hitPosition(ray, g, t, u, v, N);
@@ -414,10 +443,14 @@ __global__ void __launch_bounds__(128, EL_SHADE_MIN_CTAS) k_shade(WaveState W, c
                 }
             }
         }
+#if EL_SHADE_ONE_ATOMIC
+        appendNextAndNee(W, toNext, toNee, pid);
+#else
         appendWarpAggregated(W.qNee, &W.cnt[CNT_NEE], toNee, pid);
         appendWarpAggregated(W.qNext, &W.cnt[CNT_NEXT], toNext, pid);
+#endif
 #if EL_SHADE_PREFETCH
-        if (nbase + lane < n && !(qi < n && __float_as_int(hv.x) >= 0)) nhv = W.hit[npid];   // lanes that shaded no hit this round (escaped ray / ragged end) have not asked yet
+        if (nbase < n && nbase + lane < n && !(qi < n && __float_as_int(hv.x) >= 0)) nhv = W.hit[npid];   // lanes that shaded no hit this round (escaped ray / ragged end) have not asked yet
         base = nbase; pid = npid; hv = nhv;
 #endif
     }

@@ -31,6 +31,9 @@ namespace eleven {
  * Bit-identical, and SLOWER on one box back to back: k_extend 17.54 vs 16.70 ms, shadow 6.21 vs 5.80 (refill at 2 / 4 / 6 / 8 idle lanes:
  * 17.69 / 17.54 / 17.56 / 17.62; a 32-slot ring: 17.40) — profiles/r2_variants_session5.json.  The refill threshold is NOT where the
  * lanes are lost, and 15 KB of shared memory per CTA come out of the L1 the node fetches live in.  Removed again. */
+#ifndef EL_DEFER_SINK
+#define EL_DEFER_SINK 1
+#endif
 #ifndef EL_REFILL
 #define EL_REFILL 12           /* idle lanes that trigger a queue fetch (4 / 8 / 12 / 16 measured on 16-sample waves: k_extend 19.9 / 18.85 / 18.4 / 18.5 ms) */
 #endif
@@ -118,11 +121,31 @@ __device__ __forceinline__ void traceQueue(const DevScene& S, uint32_t n, uint32
     uint2 ngroup = make_uint2(0u, 0u), tgroup = make_uint2(0u, 0u), tpost = make_uint2(0u, 0u);   // tpost: one postponed triangle group
     uint2 stack[EL_STACK];
     int sp = 0;
+#if EL_DEFER_SINK
+    // A finished lane keeps its result in its (now idle) registers and the sinks run TOGETHER at the next queue fetch, i.e. with EL_REFILL or more
+    // lanes at once.  Called the moment a lane finished, the shadow kernels' sink (the MIS combination: three dependent record loads, ~90
+    // instructions) ran 6.9 M times per launch with 1.7-3.3 of 32 lanes active: 14 % of the kernel's warp instructions and 16 % of its stall samples
+    // (ncu source page, profiles/r2_final_trace_ncu_full.txt).
+    bool pending = false;
+    auto flush = [&]() {
+        if (pending) {
+            if (MODE == TRACE_CLOSEST_KEY && NEED_KEY && best.tri >= 0 && !bestExact) {
+                const TriGeom g = loadTriGeom(S.shadeTris, best.tri);
+                F3 sn;
+                best.key = hitKey(lr.ray, hitPosition(lr.ray, g, best.t, best.u, best.v, sn));
+            }
+            sink.done(lr, best); pending = false;
+        }
+    };
+#endif
 
     for (;;) {
         // ---- dynamic fetch ---------------------------------------------------------------------------------------
         const uint32_t idle = __ballot_sync(FULL, !active);
         if (idle != 0u && !exhausted && (__popc(idle) >= EL_REFILL || idle == FULL)) {
+#if EL_DEFER_SINK
+            flush();
+#endif
             const uint32_t cnt = __popc(idle);
             uint32_t base = 0;
             if (lane == 0) base = atomicAdd(workCounter, cnt);
@@ -159,6 +182,9 @@ __device__ __forceinline__ void traceQueue(const DevScene& S, uint32_t n, uint32
             }
         }
         if (__ballot_sync(FULL, active) == 0u) {
+#if EL_DEFER_SINK
+            flush();
+#endif
             if (exhausted) break;
             continue;
         }
@@ -168,12 +194,16 @@ __device__ __forceinline__ void traceQueue(const DevScene& S, uint32_t n, uint32
             if (tgroup.y == 0u && tpost.y != 0u) { tgroup = tpost; tvalid = tpostValid; tpost.y = 0u; }
             if (ngroup.y <= 0x00ffffffu && sp > 0) ngroup = stack[--sp];
             if (ngroup.y <= 0x00ffffffu && tgroup.y == 0u) {
+#if EL_DEFER_SINK
+                pending = true; active = false;
+#else
                 if (MODE == TRACE_CLOSEST_KEY && NEED_KEY && best.tri >= 0 && !bestExact) {
                     const TriGeom g = loadTriGeom(S.shadeTris, best.tri);
                     F3 sn;
                     best.key = hitKey(lr.ray, hitPosition(lr.ray, g, best.t, best.u, best.v, sn));
                 }
                 sink.done(lr, best); active = false;
+#endif
             }
         }
 
@@ -298,7 +328,11 @@ __device__ __forceinline__ void traceQueue(const DevScene& S, uint32_t n, uint32
                     if (MODE == TRACE_ANY) {
                         if (t < lr.tmaxAny) {
                             best.tri = tri; best.t = t; best.u = u; best.v = v; best.key = t;
+#if EL_DEFER_SINK
+                            pending = true; active = false;
+#else
                             sink.done(lr, best); active = false;
+#endif
                         }
                     } else consider(t, u, v, tri, c.w);
                 }
