@@ -222,7 +222,7 @@ __device__ __forceinline__ void appendWarpAggregated(uint32_t* q, uint32_t* coun
 }
 
 // Both of k_shade's queue appends with ONE 64-bit atomicAdd on the (CNT_NEXT, CNT_NEE) pair: the ncu source page had 9 % of the kernel's stall samples
-// on the two shuffles that wait for the two atomics' results.
+// on the two shuffles that wait for the two atomics' results.  k_shade 6.47 -> 6.12 ms per 16-spp step (profiles/r2_variants_session9.json).
 __device__ __forceinline__ void appendNextAndNee(const WaveState& W, bool toNext, bool toNee, uint32_t pid) {
     const uint32_t mNext = __ballot_sync(0xffffffffu, toNext), mNee = __ballot_sync(0xffffffffu, toNee);   // called by all 32 lanes
     if ((mNext | mNee) == 0u) return;
@@ -239,7 +239,8 @@ __device__ __forceinline__ void appendNextAndNee(const WaveState& W, bool toNext
 #define EL_SHADE_ONE_ATOMIC 1
 #endif
 #ifndef EL_SHADE_STATIC
-#define EL_SHADE_STATIC 1        /* queue blocks by a static stride over the grid's warps instead of an atomic work fetch (5 % of the stall samples sat on its shuffle) */
+#define EL_SHADE_STATIC 0        /* 1: queue blocks by a static stride over the grid's warps instead of the atomic work fetch (5 % of the stall samples sit on its shuffle).
+                                  * Measured SLOWER: k_shade 6.48 vs 6.12 ms (profiles/r2_variants_session9.json): blocks of escaped rays and of hits do not cost the same */
 #endif
 #ifndef EL_SHADE_PREFETCH
 #define EL_SHADE_PREFETCH 1
