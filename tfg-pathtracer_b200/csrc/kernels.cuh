@@ -238,12 +238,10 @@ __device__ __forceinline__ void appendNextAndNee(const WaveState& W, bool toNext
 #ifndef EL_SHADE_ONE_ATOMIC
 #define EL_SHADE_ONE_ATOMIC 1
 #endif
-#ifndef EL_SHADE_FETCH_AHEAD
-#define EL_SHADE_FETCH_AHEAD 0
-#endif
 #ifndef EL_SHADE_STATIC
 #define EL_SHADE_STATIC 0        /* 1: queue blocks by a static stride over the grid's warps instead of the atomic work fetch (5 % of the stall samples sit on its shuffle).
-                                  * Measured SLOWER: k_shade 6.48 vs 6.12 ms (profiles/r2_variants_session9.json): blocks of escaped rays and of hits do not cost the same */
+                                  * Measured SLOWER: k_shade 6.48 vs 6.12 ms (profiles/r2_variants_session9.json): blocks of escaped rays and of hits do not cost the same.
+                                  * Issuing the fetch atomic one iteration ahead of its broadcast: 6.32 vs 6.12 ms (session 11), dropped. */
 #endif
 #ifndef EL_SHADE_PREFETCH
 #define EL_SHADE_PREFETCH 1
@@ -282,12 +280,6 @@ __global__ void __launch_bounds__(128, EL_SHADE_MIN_CTAS) k_shade(WaveState W, c
     uint32_t base = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32u;
 #else
     uint32_t base = warpFetch(&W.cnt[CNT_WORK_SHADE], lane);
-#if EL_SHADE_FETCH_AHEAD
-    // the work-fetch atomic is issued one iteration before its result is broadcast: the shuffle no longer waits for it
-    // (ncu source page: 5 % of the kernel's stall samples on that shuffle)
-    uint32_t aheadRaw = 0;
-    if (lane == 0u) aheadRaw = atomicAdd(&W.cnt[CNT_WORK_SHADE], 32u);
-#endif
 #endif
     uint32_t pid = 0; float4 hv = make_float4(0.f, 0.f, 0.f, 0.f);
     if (base < n && base + lane < n) { pid = queueEntry(base + lane); hv = W.hit[pid]; }
@@ -296,9 +288,6 @@ __global__ void __launch_bounds__(128, EL_SHADE_MIN_CTAS) k_shade(WaveState W, c
         const uint32_t qi = base + lane;
 #if EL_SHADE_STATIC
         const uint32_t nbase = (n - base > stride) ? base + stride : n;          // no wrap-around for n close to 2^32
-#elif EL_SHADE_FETCH_AHEAD
-        const uint32_t nbase = __shfl_sync(0xffffffffu, aheadRaw, 0);
-        if (lane == 0u && nbase < n) aheadRaw = atomicAdd(&W.cnt[CNT_WORK_SHADE], 32u);
 #else
         const uint32_t nbase = warpFetch(&W.cnt[CNT_WORK_SHADE], lane);
 #endif
