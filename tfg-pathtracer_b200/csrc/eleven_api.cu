@@ -763,21 +763,15 @@ extern "C" int eleven_trace_device(ElevenCtx* c, const float* d_rays, size_t n, 
     if (!c->haveScene) return fail(ELEVEN_ERR_STATE, "eleven_trace_device: no scene uploaded");
     if (n > 0xfffffff0ull) return fail(ELEVEN_ERR_ARG, "eleven_trace_device: too many rays");
     CK(cudaSetDevice(c->cfg.device));
-    const int grid = c->numSMs * 8;
     const bool count = (c->cfg.flags & ELEVEN_FLAG_COUNTERS) != 0;
     CK(cudaMemsetAsync(c->d_workCounter, 0, 4, c->stream));
     CK(cudaEventRecord(c->ev0, c->stream));
     const uint32_t nn = (uint32_t)n;
-    if (anyHit) {
-        if (count) k_traceBatch<TRACE_ANY, true><<<grid, 128, 0, c->stream>>>(d_rays, nn, d_hits, c->scene, c->d_workCounter, c->W.stats);
-        else k_traceBatch<TRACE_ANY, false><<<grid, 128, 0, c->stream>>>(d_rays, nn, d_hits, c->scene, c->d_workCounter, c->W.stats);
-    } else if (c->cfg.hit_mode == ELEVEN_HIT_KEY) {
-        if (count) k_traceBatch<TRACE_CLOSEST_KEY, true><<<grid, 128, 0, c->stream>>>(d_rays, nn, d_hits, c->scene, c->d_workCounter, c->W.stats);
-        else k_traceBatch<TRACE_CLOSEST_KEY, false><<<grid, 128, 0, c->stream>>>(d_rays, nn, d_hits, c->scene, c->d_workCounter, c->W.stats);
-    } else {
-        if (count) k_traceBatch<TRACE_CLOSEST_T, true><<<grid, 128, 0, c->stream>>>(d_rays, nn, d_hits, c->scene, c->d_workCounter, c->W.stats);
-        else k_traceBatch<TRACE_CLOSEST_T, false><<<grid, 128, 0, c->stream>>>(d_rays, nn, d_hits, c->scene, c->d_workCounter, c->W.stats);
-    }
+#define LAUNCH_BATCH(MODE, CNT) LAUNCH_PERSISTENT((k_traceBatch<MODE, CNT>), nullptr, d_rays, nn, d_hits, c->scene, c->d_workCounter, c->W.stats)   /* grid = resident CTAs, like the render kernels */
+    if (anyHit) { if (count) LAUNCH_BATCH(TRACE_ANY, true); else LAUNCH_BATCH(TRACE_ANY, false); }
+    else if (c->cfg.hit_mode == ELEVEN_HIT_KEY) { if (count) LAUNCH_BATCH(TRACE_CLOSEST_KEY, true); else LAUNCH_BATCH(TRACE_CLOSEST_KEY, false); }
+    else { if (count) LAUNCH_BATCH(TRACE_CLOSEST_T, true); else LAUNCH_BATCH(TRACE_CLOSEST_T, false); }
+#undef LAUNCH_BATCH
     CK(cudaEventRecord(c->ev1, c->stream));
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(c->stream));
