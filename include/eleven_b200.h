@@ -169,7 +169,7 @@ typedef struct ElevenStats {
     uint64_t extend_launches;    /* closest-hit kernel launches inside eleven_render         */
     double   bvh_build_ms;       /* wall time of the BVH8 build (host or device builder)     */
     uint32_t bvh_nodes;          /* BVH8 node count                                          */
-    uint32_t bvh_tri_slots;      /* triangle slots in leaf order                             */
+    uint32_t bvh_tri_slots;      /* triangle slots in leaf order (>= triCount: a pre-split sliver triangle owns several) */
     float    key_slack;          /* per-scene bound on |key - t| used for culling in HIT_KEY */
     uint32_t samples_done;       /* per-pixel sample count of pixel 0 (getSamples)           */
     uint64_t key_evals;          /* exact reference-key evaluations (only with ELEVEN_FLAG_COUNTERS) */
