@@ -84,7 +84,10 @@ int main(int argc, char** argv) {
     std::string err;
     if (argc >= 4 && !strcmp(argv[1], "--dump-flat")) {
         LoadedScene s;
-        if (!loadScene(argv[2], s, err) || !saveFlat(s, argv[3], err)) { fprintf(stderr, "eleven: %s\n", err.c_str()); return 1; }
+        const double tl = nowS();
+        if (!loadScene(argv[2], s, err)) { fprintf(stderr, "eleven: %s\n", err.c_str()); return 1; }
+        printf("loaded in %.0f ms\n", (nowS() - tl) * 1e3);
+        if (!saveFlat(s, argv[3], err)) { fprintf(stderr, "eleven: %s\n", err.c_str()); return 1; }
         printf("%zu triangles, %zu objects, %zu materials, %zu textures, %zu lights -> %s\n", s.tris.size(), s.objectMaterial.size(),
                s.materials.size(), s.textures.size(), s.lights.size(), argv[3]);
         return 0;

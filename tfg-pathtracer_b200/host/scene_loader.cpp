@@ -11,6 +11,8 @@
 #include <memory>
 #include <sstream>
 #include <sys/stat.h>
+#include <atomic>
+#include <thread>
 
 namespace eleven_host {
 
@@ -265,21 +267,35 @@ static bool loadDir(std::string dir, LoadedScene& s, std::string& err) {
         for (const char* key : {"map_Kd", "map_Ns", "map_Bump", "refl"}) if (line.find(key) != std::string::npos) maps.back()[key] = afterFirstSpace(line);
     }
     if (s.materials.empty()) { s.materials.push_back(defaultMaterial()); s.materialNames.push_back("default"); maps.emplace_back(); }
-    for (size_t i = 0; i < s.materials.size(); i++) for (auto& kv : maps[i]) {      // std::map order: map_Bump, map_Kd, map_Ns, refl
+    // texture ids in the reference's order (per material its std::map iteration order: map_Bump, map_Kd, map_Ns, refl; de-duplicated by path);
+    // the files themselves (12 x 50 MB for ClockCC0) are read and decoded by a pool of threads below, while another thread parses the OBJ
+    std::vector<std::string> texFile;
+    for (size_t i = 0; i < s.materials.size(); i++) for (auto& kv : maps[i]) {
         int id = -1;
         for (size_t j = 0; j < s.textures.size(); j++) if (s.textures[j].path == kv.second) id = (int)j;
         if (id < 0) {
-            LoadedTexture t; int w, h;
+            LoadedTexture t;
             std::string p = kv.second; if (!p.empty() && p[0] != '/') { struct stat st; if (stat(p.c_str(), &st) != 0) p = dir + p; }   // the reference resolves against the CWD
-            if (!readBmp24(p, w, h, t.bytes, err)) return false;
             t.path = kv.second;
-            t.view = ElevenTexture{nullptr, (uint32_t)(kv.first == "map_Kd" ? ELEVEN_TEX_U8_SRGB : ELEVEN_TEX_U8_LINEAR), w, h, 1.f, 1.f, 0.f, 0.f, 0u};
-            id = (int)s.textures.size(); s.textures.push_back(std::move(t));
+            t.view = ElevenTexture{nullptr, (uint32_t)(kv.first == "map_Kd" ? ELEVEN_TEX_U8_SRGB : ELEVEN_TEX_U8_LINEAR), 0, 0, 1.f, 1.f, 0.f, 0.f, 0u};
+            id = (int)s.textures.size(); s.textures.push_back(std::move(t)); texFile.push_back(p);
         }
         ElevenMaterial& m = s.materials[i];
         if (kv.first == "map_Kd") m.albedoTextureID = id; else if (kv.first == "map_Ns") m.roughnessTextureID = id;
         else if (kv.first == "refl") m.metallicTextureID = id; else if (kv.first == "map_Bump") m.normalTextureID = id;
     }
+    std::vector<std::string> texErr(s.textures.size());
+    std::atomic<size_t> nextTex(0);
+    auto texWorker = [&]() {
+        for (;;) {
+            const size_t k = nextTex.fetch_add(1); if (k >= s.textures.size()) break;
+            int w = 0, h = 0;
+            if (readBmp24(texFile[k], w, h, s.textures[k].bytes, texErr[k])) { s.textures[k].view.width = w; s.textures[k].view.height = h; }
+        }
+    };
+    std::vector<std::thread> texThreads;
+    for (unsigned t = 0; t < std::min<size_t>(s.textures.size(), std::max(1u, std::thread::hardware_concurrency())); t++) texThreads.emplace_back(texWorker);
+    struct JoinAll { std::vector<std::thread>& v; ~JoinAll() { for (auto& t : v) if (t.joinable()) t.join(); } } joinTex{texThreads};
     // geometry (S/ObjLoader.hpp:71-171)
     std::ifstream obj(dir + "scene.obj");
     if (!obj) { err = "cannot open " + dir + "scene.obj"; return false; }
@@ -322,6 +338,8 @@ static bool loadDir(std::string dir, LoadedScene& s, std::string& err) {
     }
     closeObject();
     if (s.objectMaterial.empty()) { s.objectMaterial.push_back(0); }
+    for (auto& t : texThreads) t.join();
+    for (const std::string& e : texErr) if (!e.empty()) { err = e; return false; }
     return true;
 }
 
