@@ -65,6 +65,13 @@ def test_loader_reports_errors(tmp_path):
     r = subprocess.run([EXE, "--dump-flat", str(tmp_path / "bad"), str(tmp_path / "o.flat")], capture_output=True, text=True)
     assert r.returncode != 0 and "resolution" in r.stderr
     assert subprocess.run([EXE], capture_output=True).returncode == 2
+    # a texture that cannot be read: reported by the loader's texture threads, the load fails as a whole
+    k = S.clock_standin(tex_res=8, xres=16, yres=9, env_size=(16, 8))
+    d = S.write_reference_scene_dir(k, str(tmp_path / "scene"))
+    victim = sorted(p for p in os.listdir(os.path.join(d, "textures")) if p.endswith(".bmp"))[3]
+    os.remove(os.path.join(d, "textures", victim))
+    r = subprocess.run([EXE, "--dump-flat", d, str(tmp_path / "o.flat")], capture_output=True, text=True, cwd=d)
+    assert r.returncode != 0 and "cannot open" in r.stderr and victim in r.stderr
 
 
 @pytest.mark.gpu
