@@ -21,6 +21,8 @@
  * the wave.  Queues hold path ids;
  * their counts live on the device and every kernel is a persistent grid that fetches 32-ray batches per warp with
  * one atomicAdd ("warp-level work fetch"), so a whole wave is enqueued without a single host synchronisation.
+ * Round 2: the connect (shadow) stage of bounce b runs on an auxiliary stream concurrently with extend + classify of bounce
+ * b+1 (eleven_api.cu: eleven_render; k_advance phases 2 / 3 split the counter hand-over accordingly).
  */
 #pragma once
 #include "shading.cuh"

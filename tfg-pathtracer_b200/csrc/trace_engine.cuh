@@ -17,6 +17,11 @@
  *
  * Source supplies rays by queue index, Sink consumes finished rays; both are small functors so that the same engine
  * serves the extension rays, the shadow rays and the plain ray batches of the test hook.
+ *
+ * Round 2: finished lanes keep their result and the sinks run together at the next queue fetch (EL_DEFER_SINK: the shadow
+ * kernels' sink is a 90-instruction MIS combination that used to run with 1.7-3.3 lanes active); the render kernels of the
+ * fast-math configuration intersect triangles with mollerTrumboreFast (FAST_TRI); the ray's sign tests come from its octant
+ * bits (64 registers: 8 CTAs per SM for k_extend, 9 for the shadow kernels).
  */
 #pragma once
 #include "traverse.cuh"
